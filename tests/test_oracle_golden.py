@@ -1,0 +1,87 @@
+"""Pins the CPU oracle (oracle/cchess_oracle.c) to golden vectors produced by the UNMODIFIED
+reference (oracle/gen_golden.py).  CPU-only; runs everywhere."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from oracle import oracle as O
+
+
+def sha(b):
+    return hashlib.sha256(b).hexdigest()[:16]
+
+
+def test_labels():
+    g = load_golden("labels.json")
+    assert O.labels() == g["labels"]
+    assert O.unflipped_index() == g["unflipped_index"]
+    assert g["sha_labels"] == "c6e10a93f1d69164"
+    assert g["sha_unflipped"] == "da24858f23137be3"
+    lab = g["labels"]
+    for i in (0, 223, 916, 1125, 1832, 2035, 2042, 2056):
+        m = lab[i]
+        assert O.label_index(O.move_from_str(m) & 127, O.move_from_str(m) >> 7) == i
+
+
+def test_rules_against_reference_vectors():
+    g = load_golden("movegen.json.gz")
+    assert g["n"] == len(g["records"]) > 7000
+    for r in g["records"]:
+        b = O.from_state(r["state"])
+        side = 0 if r["player"] == "w" else 1
+        assert O.to_state(b) == r["state"]
+        mv = O.legal_moves(b, side)
+        assert " ".join(O.move_str(m) for m in mv) == r["moves"], r["state"]
+        enc = O.encode(b, side)
+        assert [int(i) for i in np.nonzero(enc.reshape(-1))[0]] == r["enc"]
+        assert set(np.unique(enc)) <= {0.0, 1.0}
+        fb = O.flip_board(b) if side == 1 else b
+        assert O.to_state(fb) == r["flip"]
+        if "move" in r:
+            nb, cap = O.apply_move(b, O.move_from_str(r["move"]))
+            assert O.to_state(nb) == r["next"]
+            assert int(cap != 0) == r["kill"]
+
+
+def test_appendix_b_known_answers():
+    start = O.from_state(O.START)
+    mv = [O.move_str(m) for m in O.legal_moves(start, 0)]
+    assert len(mv) == 44 and mv[:5] == ["a0a1", "a0a2", "b0a2", "b0c2", "c0e2"] and mv[-1] == "i3i4"
+    enc = O.encode(start, 0)
+    assert enc.sum() == 26.0 and sha(enc.tobytes()) == "8ca9caf6c0b9416c"
+    assert np.array_equal(enc, O.encode(start, 1))
+    kk = O.from_state("4K4/9/9/9/9/9/9/9/9/4k4")
+    assert [O.move_str(m) for m in O.legal_moves(kk, 0)] == ["e0d0", "e0f0", "e0e1", "e0e9"]
+
+
+@pytest.mark.parametrize("i", range(13))
+def test_tree_against_reference(i):
+    g = load_golden("tree.json")
+    if i >= len(g["cases"]):
+        pytest.skip("no such case")
+    c = g["cases"][i]
+    t = O.Tree(O.from_state(c["state"]))
+    t.search(0 if c["player"] == "w" else 1, c["rr"], c["playouts"], c["net"])
+    sig = t.signature()
+    assert sig.shape[0] == c["n_nodes"]
+    assert sig[:40].tolist() == c["head"]
+    assert sha(sig.tobytes()) == c["sha_sig"], c["note"]
+    mv, N, W, P, Q = t.root_children()
+    got = [[O.move_str(m), int(n), int(w.view(np.uint32)), int(p.view(np.uint32)), int(q.view(np.uint32))]
+           for m, n, w, p, q in zip(mv, N, W, P, Q)]
+    assert got == c["root"]
+
+
+@pytest.mark.parametrize("i", range(6))
+def test_selfplay_tuples_against_reference(i):
+    g = load_golden("selfplay.json")["games"][i]
+    with np.errstate(all="ignore"):
+        r = O.selfplay_game(g["net"], g["playouts"], np.random.RandomState(g["seed"]))
+    assert len(r["states"]) == g["n"]
+    assert r["states"] == g["states"]
+    assert [float(v) for v in r["z"]] == g["z"]
+    assert sha(np.asarray(r["pis"], dtype=np.float64).tobytes()) == g["sha_pi"]
+    for p, sp in zip(r["pis"], g["pi_sparse"]):
+        assert [[int(k), float(p[k]).hex()] for k in np.nonzero(p)[0]] == sp
