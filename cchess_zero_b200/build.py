@@ -1,0 +1,36 @@
+"""Builds libcchess_b200.so (the C-ABI engine library) in-tree with nvcc for sm_100a."""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = [os.path.join(HERE, "csrc", "cz_engine.cu")]
+DEPS = SRC + [os.path.join(HERE, "csrc", "cz_rules.cuh"), os.path.join(os.path.dirname(HERE), "include", "cchess_b200.h")]
+LIB = os.path.join(HERE, "libcchess_b200.so")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--fmad=false",
+         "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v"]
+
+
+def needs_build():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(p) > t for p in DEPS)
+
+
+def build(force=False, verbose=False):
+    if not force and not needs_build():
+        return LIB
+    cmd = [NVCC] + FLAGS + ["-o", LIB] + SRC
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or r.returncode:
+        sys.stderr.write(r.stdout + r.stderr)
+    if r.returncode:
+        raise RuntimeError("nvcc failed: " + " ".join(cmd))
+    return LIB
+
+
+if __name__ == "__main__":
+    build(force=True, verbose=True)
+    print(LIB)

@@ -1,0 +1,982 @@
+// cz_engine.cu -- batched MCTS self-play engine for sm_100a (one warp per game) + its C ABI.
+//
+// Replaces, for thousands of concurrent games, the reference's leaf_node / MCTS_tree /
+// GameBoard hot path (main.py:93-206, 234-577, 579-1109) with search_threads = 1 semantics
+// (SURVEY Appendix A.4).  Results are bit-exact: every float op below is an explicit
+// round-to-nearest IEEE intrinsic in the width numpy uses (f32 for P/W/Q, f64 for U and Q+U).
+//
+// HBM layout (SoA over games; B = n_games, A = arena words per half):
+//   root_board  u8  [B][96]     90-byte mailbox + pad, 24 coalesced u32 per game
+//   arena       u32 [B][2][A]   per-game bump arena of node blocks, two halves (ping-pong
+//                               compaction when the root moves, MCTS_tree.update_tree)
+//   node block  = 8-word header {n_children,...} followed by five arrays of stride
+//                 cs = roundup8(n_children):  P f32 | W f32 | N i32 | META u32 | CHILD u32
+//                 META = move | n_grandchildren << 16, CHILD = base of the child's block or NONE.
+//                 One node = one contiguous run, each array sector-aligned, so a warp reads
+//                 all PUCT inputs of a node with coalesced loads in a single round trip.
+//   path        uint2 [B][MAXD] (slot of P[idx], cs) of the edges of the current playout
+//   leaf_board  u8  [B][96]     board at the pending leaf (+ side in byte 90)
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/cchess_b200.h"
+#include "cz_rules.cuh"
+
+#define MAXD 256
+#define NONE 0xFFFFFFFFu
+#define HDR 8
+#define WARPS_PER_BLOCK 4
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const char *what, cudaError_t ce = cudaSuccess) {
+    g_err = what;
+    if (ce != cudaSuccess) { g_err += ": "; g_err += cudaGetErrorString(ce); }
+    return code;
+}
+#define CUDA_TRY(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) return fail(CZ_ECUDA, #x, _e); } while (0)
+
+// ------------------------------------------------------------------------------------------
+// host-side label table (create_uci_labels, main.py:30-65): same enumeration order
+// ------------------------------------------------------------------------------------------
+struct Labels {
+    char text[CZ_NLABEL][4];
+    int16_t of[CZ_NSQ * CZ_NSQ];
+    int32_t unflipped[CZ_NLABEL];
+    Labels() {
+        int n = 0;
+        auto put = [&](int l1, int n1, int l2, int n2) {
+            text[n][0] = char('a' + l1); text[n][1] = char('0' + n1);
+            text[n][2] = char('a' + l2); text[n][3] = char('0' + n2);
+            n++;
+        };
+        const int kdx[8] = {-2, -1, -2, 1, 2, -1, 2, 1}, kdy[8] = {-1, -2, 1, -2, -1, 2, 1, 2};
+        for (int l1 = 0; l1 < 9; l1++)
+            for (int n1 = 0; n1 < 10; n1++) {
+                for (int t = 0; t < 9; t++) if (t != l1) put(l1, n1, t, n1);       // along the rank
+                for (int t = 0; t < 10; t++) if (t != n1) put(l1, n1, l1, t);      // along the file
+                for (int k = 0; k < 8; k++) {                                      // knight jumps
+                    int l2 = l1 + kdx[k], n2 = n1 + kdy[k];
+                    if (l2 >= 0 && l2 < 9 && n2 >= 0 && n2 < 10) put(l1, n1, l2, n2);
+                }
+            }
+        const char *adv = "d7e8e8d7e8f9f9e8d0e1e1d0e1f2f2e1d2e1e1d2e1f0f0e1d9e8e8d9e8f7f7e8";
+        const char *bis = "a2c4c4a2c0e2e2c0e2g4g4e2g0i2i2g0a7c9c9a7c5e7e7c5e7g9g9e7g5i7i7g5"
+                          "a2c0c0a2c4e2e2c4e2g0g0e2g4i2i2g4a7c5c5a7c9e7e7c9e7g5g5e7g9i7i7g9";
+        for (int i = 0; i < 16; i++) { memcpy(text[n], adv + 4 * i, 4); n++; }
+        for (int i = 0; i < 32; i++) { memcpy(text[n], bis + 4 * i, 4); n++; }
+        for (auto &v : of) v = -1;
+        for (int i = 0; i < CZ_NLABEL; i++) {
+            int s = (text[i][1] - '0') * 9 + (text[i][0] - 'a'), d = (text[i][3] - '0') * 9 + (text[i][2] - 'a');
+            if (of[s * CZ_NSQ + d] < 0) of[s * CZ_NSQ + d] = (int16_t)i;
+        }
+        for (int i = 0; i < CZ_NLABEL; i++) {  // flipped_uci_labels (main.py:23-27): rank digit d -> 9-d
+            int s = (9 - (text[i][1] - '0')) * 9 + (text[i][0] - 'a'), d = (9 - (text[i][3] - '0')) * 9 + (text[i][2] - 'a');
+            unflipped[i] = of[s * CZ_NSQ + d];
+        }
+    }
+};
+const Labels &labels() { static Labels L; return L; }
+
+// ------------------------------------------------------------------------------------------
+// device state
+// ------------------------------------------------------------------------------------------
+struct Dev {
+    int B;
+    long long A;
+    uint8_t *root_board;
+    uint8_t *side;
+    int32_t *rr, *ply;
+    int32_t *root_N, *root_cnt;
+    uint32_t *root_base;
+    int32_t *done, *target;
+    uint8_t *pending, *active;
+    int32_t *path_len;
+    uint2 *path;
+    uint8_t *leaf_board;
+    uint32_t *arena;
+    uint8_t *cur;
+    uint32_t *alloc, *max_alloc;
+    unsigned long long *cnt_expand, *cnt_playout, *cnt_L, *cnt_c;
+    uint32_t *err;
+    int32_t *max_depth;
+    uint8_t *terminal;
+    int8_t *winner;
+    const int16_t *label_of;
+    // staging
+    int32_t *st_n, *st_visits, *st_choice;
+    uint16_t *st_moves;
+    float *st_w, *st_p, *st_q;
+    int32_t *st_count;
+};
+
+__device__ __forceinline__ uint32_t *arena_of(const Dev &E, int g) {
+    return E.arena + ((size_t)g * 2 + E.cur[g]) * (size_t)E.A;
+}
+
+struct WarpSmem {
+    uint8_t board[96];
+    uint16_t moves[136];
+    float ps[128];
+};
+
+// order-preserving map of a double onto uint64 (NaN must be removed by the caller, -0 canonicalised)
+__device__ __forceinline__ unsigned long long dkey(double s) {
+    long long b = __double_as_longlong(s);
+    return (unsigned long long)(b ^ ((b >> 63) | (long long)0x8000000000000000ULL));
+}
+
+// VL undo + back_up_value along the recorded path (main.py:426-435, 189-194).
+// val = value handed to the deepest edge; sign alternates going up.
+__device__ void warp_backup(const Dev &E, int g, uint32_t *ar, int depth, float val, int lane) {
+    const uint2 *path = E.path + (size_t)g * MAXD;
+    for (int d = lane; d < depth; d += 32) {
+        const uint2 pe = path[d];
+        const uint32_t slot = pe.x, cs = pe.y;
+        float W = __uint_as_float(ar[slot + cs]);
+        int N = (int)ar[slot + 2 * cs];
+        const float v = ((depth - 1 - d) & 1) ? -val : val;
+        N = N - 3 + 1;
+        W = __fadd_rn(__fadd_rn(W, 3.0f), v);
+        ar[slot + cs] = __float_as_uint(W);
+        ar[slot + 2 * cs] = (uint32_t)N;
+    }
+    __syncwarp();
+}
+
+// leaf_node.expand (main.py:175-187) for the pending leaf of game g; returns false on error
+__device__ bool warp_expand(const Dev &E, int g, uint32_t *ar, WarpSmem &S, const float *logits, int pend, int depth, int lane) {
+    const uint32_t *lb = reinterpret_cast<const uint32_t *>(E.leaf_board + (size_t)g * 96);
+    if (lane < 24) reinterpret_cast<uint32_t *>(S.board)[lane] = lb[lane];
+    __syncwarp();
+    const int lside = S.board[90];
+    int n = cz::warp_legal_moves(S.board, lside, S.moves, lane);
+    uint32_t errf = 0;
+    if (n == 0) errf |= CZ_ERR_NOMOVES;
+    if (n > CZ_MAXCHILD) { errf |= CZ_ERR_CHILDREN; n = CZ_MAXCHILD; }
+    const uint32_t cs = (uint32_t)((n + 7) & ~7), size = HDR + 5 * cs;
+    const uint32_t base = E.alloc[g];
+    if ((long long)base + size > E.A) errf |= CZ_ERR_ARENA;
+    const float *lg = logits + (size_t)g * CZ_NLABEL;
+    for (int i = lane; i < n; i += 32) {
+        const int mv = S.moves[i];
+        int src = mv & 127, dst = mv >> 7;
+        if (lside == 1) {  // flip_policy (main.py:1152-1155) folded into the index: rank y -> 9-y
+            src = (9 - src / 9) * 9 + src % 9;
+            dst = (9 - dst / 9) * 9 + dst % 9;
+        }
+        int li = E.label_of[src * CZ_NSQ + dst];
+        if (li < 0) { errf |= CZ_ERR_NOLABEL; li = 0; }
+        S.ps[i] = __ldg(lg + li);
+    }
+    errf = __reduce_or_sync(CZ_FULL, errf);
+    __syncwarp();
+    if (errf) {
+        if (lane == 0) atomicOr(E.err + g, errf);
+        if (errf & (CZ_ERR_ARENA | CZ_ERR_NOMOVES)) return false;
+    }
+    float tot = 1e-8f;  // tot_p = 1e-8 accumulated in float32, in move order (main.py:176, 184)
+    for (int i = 0; i < n; i++) tot = __fadd_rn(tot, S.ps[i]);
+    uint32_t *blk = ar + base;
+    if (lane < HDR) blk[lane] = lane == 0 ? (uint32_t)n : 0u;
+    for (int i = lane; i < (int)cs; i += 32) {
+        const bool live = i < n;
+        blk[HDR + i] = live ? __float_as_uint(__fdiv_rn(S.ps[i], tot)) : 0u;   // n.P /= tot_p (main.py:187)
+        blk[HDR + cs + i] = 0u;                                                // W = 0
+        blk[HDR + 2 * cs + i] = 0u;                                            // N = 0
+        blk[HDR + 3 * cs + i] = live ? (uint32_t)S.moves[i] : 0u;              // META: move, no grandchildren yet
+        blk[HDR + 4 * cs + i] = NONE;
+    }
+    if (lane == 0) {
+        E.alloc[g] = base + size;
+        if (base + size > E.max_alloc[g]) E.max_alloc[g] = base + size;
+        if (pend == 2) {
+            E.root_base[g] = base;
+            E.root_cnt[g] = n;
+        } else {
+            const uint2 pe = E.path[(size_t)g * MAXD + depth - 1];
+            ar[pe.x + 3 * pe.y] = (ar[pe.x + 3 * pe.y] & 0xFFFFu) | ((uint32_t)n << 16);
+            ar[pe.x + 4 * pe.y] = base;
+        }
+        E.cnt_expand[g] += 1;
+    }
+    __syncwarp();
+    return true;
+}
+
+template <typename T>
+__device__ void store_leaf(const Dev &E, int g, WarpSmem &S, int side, T *nn_in, int lane) {
+    if (lane == 0) S.board[90] = (uint8_t)side;
+    __syncwarp();
+    uint32_t *lb = reinterpret_cast<uint32_t *>(E.leaf_board + (size_t)g * 96);
+    if (lane < 24) lb[lane] = reinterpret_cast<const uint32_t *>(S.board)[lane];
+    cz::warp_encode<T>(S.board, side, nn_in + (size_t)g * CZ_ENC_LEN, lane);
+}
+
+// One wave for one game (one warp).  DO_EXPAND: consume the previous evaluation; DO_SELECT: run playouts
+// until the next leaf.
+template <typename T, bool DO_EXPAND, bool DO_SELECT>
+__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_wave(Dev E, T *nn_in, const float *logits, const float *value) {
+    __shared__ WarpSmem smem[WARPS_PER_BLOCK];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int g = blockIdx.x * WARPS_PER_BLOCK + w;
+    if (g >= E.B) return;
+    if (!E.active[g]) return;
+    WarpSmem &S = smem[w];
+    uint32_t *ar = arena_of(E, g);
+    int pend = E.pending[g];
+    int done = E.done[g];
+
+    if (DO_EXPAND && pend) {
+        const int depth = E.path_len[g];
+        const bool ok = warp_expand(E, g, ar, S, logits, pend, depth, lane);
+        if (pend == 1) {
+            // leaf returns -v (main.py:384); on an engine error the playout is closed with 0
+            const float v = ok ? -value[g] : 0.0f;
+            warp_backup(E, g, ar, depth, v, lane);
+            done++;
+            if (lane == 0) E.cnt_playout[g] += 1;
+        }
+        if (!ok && pend == 2) { if (lane == 0) { E.active[g] = 0; E.pending[g] = 0; } return; }
+        pend = 0;
+        if (lane == 0) { E.pending[g] = 0; E.done[g] = done; }
+    }
+    if (!DO_SELECT || pend) return;
+
+    const int target = E.target[g];
+    const int side0 = E.side[g], rr0 = E.rr[g];
+    const uint32_t *rb = reinterpret_cast<const uint32_t *>(E.root_board + (size_t)g * 96);
+
+    if (E.root_cnt[g] < 0) {
+        // MCTS_tree.main: expand the root first (main.py:475-487); not a playout
+        if (lane < 24) reinterpret_cast<uint32_t *>(S.board)[lane] = rb[lane];
+        __syncwarp();
+        store_leaf<T>(E, g, S, side0, nn_in, lane);
+        if (lane == 0) { E.pending[g] = 2; E.path_len[g] = 0; }
+        return;
+    }
+    unsigned long long accL = 0, accC = 0;
+    int maxdep = 0;
+    while (done < target) {
+        // ---- one playout of start_tree_search (main.py:350-440) ----
+        if (lane < 24) reinterpret_cast<uint32_t *>(S.board)[lane] = rb[lane];
+        __syncwarp();
+        int side = side0, rr = rr0, depth = 0;
+        uint32_t base = E.root_base[g];
+        int cnt = E.root_cnt[g];
+        int parentN = E.root_N[g];
+        bool leaf = false, fault = false;
+        float tval = 0.0f;
+        for (;;) {
+            if (cnt <= 0 || depth >= MAXD) {
+                if (lane == 0) atomicOr(E.err + g, cnt <= 0 ? CZ_ERR_NOMOVES : CZ_ERR_DEPTH);
+                fault = true;
+                break;
+            }
+            const uint32_t cs = (uint32_t)((cnt + 7) & ~7);
+            const uint32_t *blk = ar + base + HDR;
+            // select_new (main.py:158-159) over get_Q_plus_U_new (108-116)
+            const double sq = __dsqrt_rn((double)parentN);
+            double bs = 0.0;
+            uint32_t bi = NONE, bmeta = 0, bchild = NONE;
+            float bW = 0.f;
+            int bN = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int i = lane + 32 * k;
+                if (i < cnt) {
+                    const float P = __uint_as_float(blk[i]);
+                    const float W = __uint_as_float(blk[cs + i]);
+                    const int N = (int)blk[2 * cs + i];
+                    const uint32_t meta = blk[3 * cs + i], child = blk[4 * cs + i];
+                    const float Q = N > 0 ? __fdiv_rn(W, (float)N) : 0.0f;           // Q = W / N in float32
+                    const float p5 = __fmul_rn(5.0f, P);                              // c_puct * P in float32
+                    const double U = __ddiv_rn(__dmul_rn((double)p5, sq), (double)(1 + N));
+                    double s = __dadd_rn((double)Q, U);
+                    if (i > 0 && s != s) s = -INFINITY;   // a NaN score never displaces an earlier candidate
+                    if (k == 0 || s > bs) { bs = s; bi = (uint32_t)i; bmeta = meta; bchild = child; bW = W; bN = N; }
+                }
+            }
+            // warp arg-max, first maximum wins (python max(): strict >)
+            const bool nan0 = __shfl_sync(CZ_FULL, (int)(bs != bs), 0) != 0;   // only lane 0 (i == 0) can hold a NaN
+            uint32_t e;
+            if (nan0) e = 0;
+            else {
+                const unsigned long long key = bi == NONE ? 0ull : dkey(__dadd_rn(bs, 0.0));
+                const uint32_t hi = (uint32_t)(key >> 32), lo = (uint32_t)key;
+                const uint32_t mhi = __reduce_max_sync(CZ_FULL, hi);
+                const uint32_t mlo = __reduce_max_sync(CZ_FULL, hi == mhi ? lo : 0u);
+                e = __reduce_min_sync(CZ_FULL, (bi != NONE && hi == mhi && lo == mlo) ? bi : NONE);
+            }
+            const int owner = e & 31;
+            const uint32_t meta = __shfl_sync(CZ_FULL, bmeta, owner);
+            const uint32_t child = __shfl_sync(CZ_FULL, bchild, owner);
+            const int eN = __shfl_sync(CZ_FULL, bN, owner);
+            if (lane == owner) {  // virtual loss (main.py:403-404)
+                const_cast<uint32_t *>(blk)[cs + e] = __float_as_uint(__fadd_rn(bW, -3.0f));
+                const_cast<uint32_t *>(blk)[2 * cs + e] = (uint32_t)(bN + 3);
+            }
+            if (lane == 0) E.path[(size_t)g * MAXD + depth] = make_uint2(base + HDR + e, cs);
+            depth++;
+            accL += 1; accC += (unsigned)cnt;
+            const int src = meta & 127, dst = (meta >> 7) & 127;
+            const int cap = S.board[dst];
+            __syncwarp();
+            if (lane == 0) { S.board[dst] = S.board[src]; S.board[src] = 0; }
+            __syncwarp();
+            side ^= 1;                                   // main.py:392
+            rr = cap == 0 ? rr + 1 : 0;                  // is_kill_move, main.py:393-396
+            if (cap == 1 || cap == 8) {                  // king captured: main.py:409-414
+                float v = cap == 1 ? (side == 1 ? 1.0f : -1.0f) : (side == 1 ? -1.0f : 1.0f);
+                tval = -v;
+                break;
+            }
+            if (rr >= 60) { tval = 0.0f; break; }        // main.py:415-416
+            if (child == NONE) { leaf = true; break; }   // main.py:357: not expanded -> evaluate
+            base = child;
+            cnt = (int)(meta >> 16);
+            parentN = eN + 3;                            // the child's N carries the virtual loss just added
+        }
+        if (depth > maxdep) maxdep = depth;
+        if (leaf) {
+            store_leaf<T>(E, g, S, side, nn_in, lane);
+            if (lane == 0) { E.pending[g] = 1; E.path_len[g] = depth; }
+            break;
+        }
+        __syncwarp();
+        warp_backup(E, g, ar, depth, tval, lane);       // also unwinds the VL of a faulted path
+        done++;
+        if (lane == 0) E.cnt_playout[g] += 1;
+        if (fault) break;
+    }
+    if (lane == 0) {
+        E.done[g] = done;
+        E.cnt_L[g] += accL;
+        E.cnt_c[g] += accC;
+        if (maxdep > E.max_depth[g]) E.max_depth[g] = maxdep;
+    }
+}
+
+__constant__ uint8_t c_start[96];   // start position, uploaded by cz_engine_create
+
+// ---- GameBoard.reload + MCTS_tree.reload -------------------------------------------------
+__global__ void k_reset(Dev E, const uint8_t *mask, const uint8_t *boards, const uint8_t *sides, const int32_t *rr) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= E.B || (mask && !mask[g])) return;
+    uint8_t *b = E.root_board + (size_t)g * 96;
+    for (int i = 0; i < 90; i++) b[i] = boards ? boards[(size_t)g * 90 + i] : c_start[i];
+    for (int i = 90; i < 96; i++) b[i] = 0;
+    E.side[g] = sides ? sides[g] : 0;
+    E.rr[g] = rr ? rr[g] : 0;
+    E.ply[g] = 0;
+    E.root_N[g] = 0;
+    E.root_cnt[g] = -1;
+    E.root_base[g] = 0;
+    E.done[g] = 0;
+    E.target[g] = 0;
+    E.pending[g] = 0;
+    E.active[g] = 0;
+    E.path_len[g] = 0;
+    E.alloc[g] = 0;
+    E.terminal[g] = 0;
+    E.winner[g] = -1;
+}
+
+__global__ void k_begin(Dev E, const uint8_t *mask, int playouts) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= E.B) return;
+    if (mask ? !mask[g] : E.terminal[g] != 0) return;
+    E.done[g] = 0;
+    E.target[g] = playouts;
+    E.active[g] = 1;
+}
+
+__global__ void k_unfinished(Dev E, int32_t *out) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    int u = 0;
+    if (g < E.B && E.active[g]) u = (E.pending[g] || E.root_cnt[g] < 0 || E.done[g] < E.target[g]) ? 1 : 0;
+    u = __reduce_add_sync(CZ_FULL, u);
+    if ((threadIdx.x & 31) == 0 && u) atomicAdd(out, u);
+}
+
+// ---- root statistics -> dense staging ---------------------------------------------------
+__global__ void k_root_children(Dev E) {
+    const int lane = threadIdx.x & 31, g = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    if (g >= E.B) return;
+    const int cnt = E.root_cnt[g];
+    if (lane == 0) E.st_n[g] = cnt;
+    if (cnt <= 0) return;
+    const uint32_t cs = (uint32_t)((cnt + 7) & ~7);
+    const uint32_t *blk = arena_of(E, g) + E.root_base[g] + HDR;
+    for (int i = lane; i < cnt; i += 32) {
+        const float W = __uint_as_float(blk[cs + i]);
+        const int N = (int)blk[2 * cs + i];
+        const size_t o = (size_t)g * CZ_MAXCHILD + i;
+        E.st_p[o] = __uint_as_float(blk[i]);
+        E.st_w[o] = W;
+        E.st_visits[o] = N;
+        E.st_q[o] = N > 0 ? __fdiv_rn(W, (float)N) : 0.0f;
+        E.st_moves[o] = (uint16_t)(blk[3 * cs + i] & 0xFFFFu);
+    }
+}
+
+// ---- play a move: board update + MCTS_tree.update_tree with subtree compaction ------------
+// Cheney-style breadth-first copy of the chosen child's subtree into the other arena half.
+__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_play(Dev E) {
+    const int lane = threadIdx.x & 31, g = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    if (g >= E.B) return;
+    const int choice = E.st_choice[g];
+    if (choice < 0) return;
+    const int rcnt = E.root_cnt[g];
+    if (rcnt <= 0 || choice >= rcnt) { if (lane == 0) atomicOr(E.err + g, CZ_ERR_NOMOVES); return; }
+    const uint32_t *old = arena_of(E, g);
+    uint32_t *neu = E.arena + ((size_t)g * 2 + (E.cur[g] ^ 1)) * (size_t)E.A;
+    const uint32_t rcs = (uint32_t)((rcnt + 7) & ~7);
+    const uint32_t *rblk = old + E.root_base[g] + HDR;
+    const uint32_t meta = rblk[3 * rcs + choice], child = rblk[4 * rcs + choice];
+    const int N = (int)rblk[2 * rcs + choice];
+    uint8_t *b = E.root_board + (size_t)g * 96;
+    const int src = meta & 127, dst = (meta >> 7) & 127;
+    const int cap = b[dst];
+    __syncwarp();
+    uint32_t alloc = 0;
+    int ncnt = -1;
+    if (child != NONE) {
+        ncnt = (int)(meta >> 16);
+        uint32_t size = HDR + 5 * (uint32_t)((ncnt + 7) & ~7);
+        for (uint32_t i = lane; i < size; i += 32) neu[i] = old[child + i];
+        alloc = size;
+        __syncwarp();
+        uint32_t scan = 0;
+        while (scan < alloc) {
+            const int c = (int)neu[scan];
+            const uint32_t cs = (uint32_t)((c + 7) & ~7);
+            uint32_t *blk = neu + scan + HDR;
+            for (int i0 = 0; i0 < c; i0 += 32) {
+                const int i = i0 + lane;
+                uint32_t oc = NONE, sz = 0;
+                if (i < c) {
+                    oc = blk[4 * cs + i];
+                    if (oc != NONE) sz = HDR + 5 * (((blk[3 * cs + i] >> 16) + 7) & ~7u);
+                }
+                int tot;
+                const uint32_t off = alloc + (uint32_t)cz::warp_excl_scan((int)sz, lane, tot);
+                if (oc != NONE) blk[4 * cs + i] = off;
+                unsigned m = __ballot_sync(CZ_FULL, oc != NONE);
+                while (m) {
+                    const int l = __ffs(m) - 1;
+                    m &= m - 1;
+                    const uint32_t so = __shfl_sync(CZ_FULL, oc, l), dn = __shfl_sync(CZ_FULL, off, l), n = __shfl_sync(CZ_FULL, sz, l);
+                    for (uint32_t j = lane; j < n; j += 32) neu[dn + j] = old[so + j];
+                }
+                alloc += (uint32_t)tot;
+                __syncwarp();
+            }
+            scan += HDR + 5 * cs;
+        }
+    }
+    if (lane == 0) {
+        b[dst] = b[src];
+        b[src] = 0;
+        const int side = E.side[g] ^ 1;
+        const int rr = cap == 0 ? E.rr[g] + 1 : 0;
+        E.side[g] = (uint8_t)side;
+        E.rr[g] = rr;
+        E.ply[g] += 1;
+        E.root_N[g] = N;
+        E.root_cnt[g] = ncnt;
+        E.root_base[g] = 0;
+        E.cur[g] ^= 1;
+        E.alloc[g] = alloc;
+        E.done[g] = 0;
+        E.target[g] = 0;
+        E.pending[g] = 0;
+        E.active[g] = 0;
+        // main.py:1532-1545: king missing -> winner, else restrict_round >= 60 -> tie
+        if (cap == 1) { E.terminal[g] = 1; E.winner[g] = 1; }
+        else if (cap == 8) { E.terminal[g] = 1; E.winner[g] = 0; }
+        else if (rr >= 60) { E.terminal[g] = 2; E.winner[g] = -1; }
+    }
+}
+
+// ---- stateless batched rules ------------------------------------------------------------
+__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_legal_moves(const uint8_t *boards, const uint8_t *sides, int n, uint16_t *moves, int32_t *counts) {
+    __shared__ WarpSmem smem[WARPS_PER_BLOCK];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = blockIdx.x * WARPS_PER_BLOCK + w;
+    if (g >= n) return;
+    WarpSmem &S = smem[w];
+    for (int i = lane; i < 90; i += 32) S.board[i] = boards[(size_t)g * 90 + i];
+    __syncwarp();
+    int c = cz::warp_legal_moves(S.board, sides[g], S.moves, lane);
+    if (lane == 0) counts[g] = c;
+    if (c > CZ_MAXCHILD) c = CZ_MAXCHILD;
+    for (int i = lane; i < CZ_MAXCHILD; i += 32) moves[(size_t)g * CZ_MAXCHILD + i] = i < c ? S.moves[i] : (uint16_t)0;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_encode(const uint8_t *boards, const uint8_t *sides, int n, T *out) {
+    __shared__ WarpSmem smem[WARPS_PER_BLOCK];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = blockIdx.x * WARPS_PER_BLOCK + w;
+    if (g >= n) return;
+    WarpSmem &S = smem[w];
+    for (int i = lane; i < 90; i += 32) S.board[i] = boards[(size_t)g * 90 + i];
+    __syncwarp();
+    cz::warp_encode<T>(S.board, sides[g], out + (size_t)g * CZ_ENC_LEN, lane);
+}
+
+__global__ void k_apply(uint8_t *boards, const uint16_t *moves, int n, uint8_t *captured) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n) return;
+    uint8_t *b = boards + (size_t)g * 90;
+    const int src = moves[g] & 127, dst = (moves[g] >> 7) & 127;
+    captured[g] = b[dst];
+    b[dst] = b[src];
+    b[src] = 0;
+}
+
+const int16_t *device_label_table(int device) {
+    static const int16_t *tab[64] = {nullptr};
+    if (device < 0 || device >= 64) return nullptr;
+    if (!tab[device]) {
+        int16_t *p = nullptr;
+        if (cudaMalloc(&p, sizeof(labels().of)) != cudaSuccess) return nullptr;
+        if (cudaMemcpy(p, labels().of, sizeof(labels().of), cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
+        tab[device] = p;
+    }
+    return tab[device];
+}
+
+inline int nblk(int n, int per) { return (n + per - 1) / per; }
+
+}  // namespace
+
+struct cz_engine {
+    Dev d;
+    int device;
+    std::vector<void *> allocs;
+    // pinned host staging
+    int32_t *h_n = nullptr, *h_visits = nullptr, *h_choice = nullptr, *h_i32 = nullptr;
+    uint16_t *h_moves = nullptr;
+    float *h_f = nullptr;
+    uint8_t *h_u8 = nullptr;
+    uint8_t *d_mask = nullptr, *d_boards = nullptr, *d_sides = nullptr;
+    int32_t *d_rr = nullptr;
+};
+
+extern "C" {
+
+const char *cz_last_error(void) { return g_err.c_str(); }
+int cz_version(void) { return 1; }
+
+int cz_labels(char *out) {
+    if (!out) return fail(CZ_EINVAL, "cz_labels: null");
+    memcpy(out, labels().text, sizeof(labels().text));
+    return CZ_OK;
+}
+int cz_label_index(int s, int d) {
+    if (s < 0 || s >= CZ_NSQ || d < 0 || d >= CZ_NSQ) return -1;
+    return labels().of[s * CZ_NSQ + d];
+}
+int cz_unflipped_index(int32_t *out) {
+    if (!out) return fail(CZ_EINVAL, "cz_unflipped_index: null");
+    memcpy(out, labels().unflipped, sizeof(labels().unflipped));
+    return CZ_OK;
+}
+
+int cz_from_state(const char *s, uint8_t *board) {
+    if (!s || !board) return fail(CZ_EINVAL, "cz_from_state: null");
+    static const char *pc = ".KARBNPCkarbnpc";
+    int sq = 0;
+    for (; *s; s++) {
+        const char c = *s;
+        if (c == '/') continue;
+        if (c >= '1' && c <= '9') {
+            for (int k = 0; k < c - '0'; k++) { if (sq >= CZ_NSQ) return fail(CZ_EINVAL, "cz_from_state: too many squares"); board[sq++] = 0; }
+            continue;
+        }
+        char cc = c;  // aliases accepted by the reference's move generator (main.py:835, 846, 857, 873)
+        if (cc == 'h') cc = 'n'; else if (cc == 'H') cc = 'N'; else if (cc == 'e') cc = 'b'; else if (cc == 'E') cc = 'B';
+        const char *f = strchr(pc + 1, cc);
+        if (!f || sq >= CZ_NSQ) return fail(CZ_EINVAL, "cz_from_state: bad character");
+        board[sq++] = (uint8_t)(f - pc);
+    }
+    return sq == CZ_NSQ ? CZ_OK : fail(CZ_EINVAL, "cz_from_state: not 90 squares");
+}
+
+int cz_to_state(const uint8_t *board, char *out) {
+    if (!out || !board) return fail(CZ_EINVAL, "cz_to_state: null");
+    static const char *pc = ".KARBNPCkarbnpc";
+    int n = 0;
+    for (int y = 0; y < 10; y++) {
+        int run = 0;
+        for (int x = 0; x < 9; x++) {
+            const int p = board[y * 9 + x];
+            if (p > 14) return fail(CZ_EINVAL, "cz_to_state: bad piece code");
+            if (!p) { run++; continue; }
+            if (run) { out[n++] = char('0' + run); run = 0; }
+            out[n++] = pc[p];
+        }
+        if (run) out[n++] = char('0' + run);
+        if (y < 9) out[n++] = '/';
+    }
+    out[n] = 0;
+    return CZ_OK;
+}
+
+int cz_legal_moves_dev(const uint8_t *boards, const uint8_t *sides, int n, uint16_t *moves, int32_t *counts, void *stream) {
+    if (n <= 0) return CZ_OK;
+    k_legal_moves<<<nblk(n, WARPS_PER_BLOCK), 32 * WARPS_PER_BLOCK, 0, (cudaStream_t)stream>>>(boards, sides, n, moves, counts);
+    CUDA_TRY(cudaGetLastError());
+    return CZ_OK;
+}
+
+int cz_encode_dev(const uint8_t *boards, const uint8_t *sides, int n, void *out, int dtype, void *stream) {
+    if (n <= 0) return CZ_OK;
+    dim3 gr(nblk(n, WARPS_PER_BLOCK)), bl(32 * WARPS_PER_BLOCK);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == CZ_F32) k_encode<float><<<gr, bl, 0, st>>>(boards, sides, n, (float *)out);
+    else if (dtype == CZ_BF16) k_encode<__nv_bfloat16><<<gr, bl, 0, st>>>(boards, sides, n, (__nv_bfloat16 *)out);
+    else if (dtype == CZ_F16) k_encode<__half><<<gr, bl, 0, st>>>(boards, sides, n, (__half *)out);
+    else return fail(CZ_EINVAL, "cz_encode_dev: dtype");
+    CUDA_TRY(cudaGetLastError());
+    return CZ_OK;
+}
+
+static int batch_io(int device, const uint8_t *boards, const uint8_t *sides, int n, uint8_t **db, uint8_t **ds) {
+    CUDA_TRY(cudaSetDevice(device));
+    CUDA_TRY(cudaMalloc(db, (size_t)n * 90));
+    CUDA_TRY(cudaMemcpy(*db, boards, (size_t)n * 90, cudaMemcpyHostToDevice));
+    if (sides) {
+        CUDA_TRY(cudaMalloc(ds, (size_t)n));
+        CUDA_TRY(cudaMemcpy(*ds, sides, (size_t)n, cudaMemcpyHostToDevice));
+    }
+    return CZ_OK;
+}
+
+int cz_legal_moves_batch(int device, const uint8_t *boards, const uint8_t *sides, int n, uint16_t *moves, int32_t *counts) {
+    if (n < 0 || (n && (!boards || !sides || !moves || !counts))) return fail(CZ_EINVAL, "cz_legal_moves_batch: null");
+    if (n == 0) return CZ_OK;
+    uint8_t *db = nullptr, *ds = nullptr;
+    uint16_t *dm = nullptr;
+    int32_t *dc = nullptr;
+    int rc = batch_io(device, boards, sides, n, &db, &ds);
+    if (rc) return rc;
+    CUDA_TRY(cudaMalloc(&dm, (size_t)n * CZ_MAXCHILD * 2));
+    CUDA_TRY(cudaMalloc(&dc, (size_t)n * 4));
+    rc = cz_legal_moves_dev(db, ds, n, dm, dc, nullptr);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpy(moves, dm, (size_t)n * CZ_MAXCHILD * 2, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(counts, dc, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    cudaFree(db); cudaFree(ds); cudaFree(dm); cudaFree(dc);
+    return CZ_OK;
+}
+
+int cz_apply_moves_batch(int device, uint8_t *boards, const uint16_t *moves, int n, uint8_t *captured) {
+    if (n < 0 || (n && (!boards || !moves || !captured))) return fail(CZ_EINVAL, "cz_apply_moves_batch: null");
+    if (n == 0) return CZ_OK;
+    uint8_t *db = nullptr, *ds = nullptr, *dcap = nullptr;
+    uint16_t *dm = nullptr;
+    int rc = batch_io(device, boards, nullptr, n, &db, &ds);
+    if (rc) return rc;
+    CUDA_TRY(cudaMalloc(&dm, (size_t)n * 2));
+    CUDA_TRY(cudaMalloc(&dcap, (size_t)n));
+    CUDA_TRY(cudaMemcpy(dm, moves, (size_t)n * 2, cudaMemcpyHostToDevice));
+    k_apply<<<nblk(n, 128), 128>>>(db, dm, n, dcap);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpy(boards, db, (size_t)n * 90, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(captured, dcap, (size_t)n, cudaMemcpyDeviceToHost));
+    cudaFree(db); cudaFree(dm); cudaFree(dcap);
+    return CZ_OK;
+}
+
+int cz_encode_batch(int device, const uint8_t *boards, const uint8_t *sides, int n, float *out) {
+    if (n < 0 || (n && (!boards || !sides || !out))) return fail(CZ_EINVAL, "cz_encode_batch: null");
+    if (n == 0) return CZ_OK;
+    uint8_t *db = nullptr, *ds = nullptr;
+    float *dout = nullptr;
+    int rc = batch_io(device, boards, sides, n, &db, &ds);
+    if (rc) return rc;
+    CUDA_TRY(cudaMalloc(&dout, (size_t)n * CZ_ENC_LEN * 4));
+    rc = cz_encode_dev(db, ds, n, dout, CZ_F32, nullptr);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpy(out, dout, (size_t)n * CZ_ENC_LEN * 4, cudaMemcpyDeviceToHost));
+    cudaFree(db); cudaFree(ds); cudaFree(dout);
+    return CZ_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+extern "C++" {
+template <typename T>
+static int dalloc(cz_engine *e, T **p, size_t count, bool zero = true) {
+    void *q = nullptr;
+    cudaError_t ce = cudaMalloc(&q, count * sizeof(T));
+    if (ce != cudaSuccess) return fail(CZ_ENOMEM, "cudaMalloc", ce);
+    if (zero) cudaMemset(q, 0, count * sizeof(T));
+    e->allocs.push_back(q);
+    *p = (T *)q;
+    return CZ_OK;
+}
+}  // extern "C++"
+
+int cz_engine_create(int n_games, int64_t arena_words, int device, cz_engine **out) {
+    if (n_games <= 0 || !out) return fail(CZ_EINVAL, "cz_engine_create: bad arguments");
+    if (arena_words <= 0) arena_words = 2ll << 20;
+    if (arena_words < 4096 || arena_words >= (1ll << 31)) return fail(CZ_EINVAL, "cz_engine_create: arena_words out of range");
+    arena_words = (arena_words + 31) & ~31ll;
+    CUDA_TRY(cudaSetDevice(device));
+    cz_engine *e = new cz_engine();
+    e->device = device;
+    Dev &d = e->d;
+    d.B = n_games;
+    d.A = arena_words;
+    const size_t B = (size_t)n_games;
+    int rc = 0;
+#define AL(ptr, cnt) if (!rc) rc = dalloc(e, &ptr, cnt)
+    AL(d.root_board, B * 96); AL(d.side, B); AL(d.rr, B); AL(d.ply, B); AL(d.root_N, B); AL(d.root_cnt, B);
+    AL(d.root_base, B); AL(d.done, B); AL(d.target, B); AL(d.pending, B); AL(d.active, B); AL(d.path_len, B);
+    AL(d.path, B * MAXD); AL(d.leaf_board, B * 96); AL(d.cur, B); AL(d.alloc, B); AL(d.max_alloc, B);
+    AL(d.cnt_expand, B); AL(d.cnt_playout, B); AL(d.cnt_L, B); AL(d.cnt_c, B); AL(d.err, B); AL(d.max_depth, B);
+    AL(d.terminal, B); AL(d.winner, B);
+    AL(d.st_n, B); AL(d.st_visits, B * CZ_MAXCHILD); AL(d.st_choice, B); AL(d.st_moves, B * CZ_MAXCHILD);
+    AL(d.st_w, B * CZ_MAXCHILD); AL(d.st_p, B * CZ_MAXCHILD); AL(d.st_q, B * CZ_MAXCHILD); AL(d.st_count, 8);
+    AL(e->d_mask, B); AL(e->d_boards, B * 90); AL(e->d_sides, B); AL(e->d_rr, B);
+    if (!rc) { uint32_t *a = nullptr; rc = dalloc(e, &a, B * 2 * (size_t)arena_words, false); d.arena = a; }
+#undef AL
+    if (rc) { cz_engine_destroy(e); return rc; }
+    d.label_of = device_label_table(device);
+    if (!d.label_of) { cz_engine_destroy(e); return fail(CZ_ECUDA, "label table upload"); }
+    const size_t hb = B * CZ_MAXCHILD;
+    if (cudaMallocHost(&e->h_n, B * 4) || cudaMallocHost(&e->h_visits, hb * 4) || cudaMallocHost(&e->h_choice, B * 4) ||
+        cudaMallocHost(&e->h_moves, hb * 2) || cudaMallocHost(&e->h_f, hb * 4 * 3) || cudaMallocHost(&e->h_u8, B * 96 + 64) ||
+        cudaMallocHost(&e->h_i32, B * 4 * 4 + 64)) {
+        cz_engine_destroy(e);
+        return fail(CZ_ENOMEM, "cudaMallocHost");
+    }
+    {
+        uint8_t sb[96] = {0};
+        if (cz_from_state("RNBAKABNR/9/1C5C1/P1P1P1P1P/9/9/p1p1p1p1p/1c5c1/9/rnbakabnr", sb) != CZ_OK) { cz_engine_destroy(e); return CZ_EINVAL; }
+        CUDA_TRY(cudaMemcpyToSymbol(c_start, sb, 96));   // GameBoard.__init__ state, main.py:585
+    }
+    k_reset<<<nblk(n_games, 128), 128>>>(d, nullptr, nullptr, nullptr, nullptr);
+    CUDA_TRY(cudaDeviceSynchronize());
+    *out = e;
+    return CZ_OK;
+}
+
+int cz_engine_destroy(cz_engine *e) {
+    if (!e) return CZ_OK;
+    cudaSetDevice(e->device);
+    cudaDeviceSynchronize();
+    for (void *p : e->allocs) cudaFree(p);
+    cudaFreeHost(e->h_n); cudaFreeHost(e->h_visits); cudaFreeHost(e->h_choice); cudaFreeHost(e->h_moves);
+    cudaFreeHost(e->h_f); cudaFreeHost(e->h_u8); cudaFreeHost(e->h_i32);
+    delete e;
+    return CZ_OK;
+}
+
+int cz_engine_n_games(const cz_engine *e) { return e ? e->d.B : CZ_EINVAL; }
+
+int cz_engine_reset(cz_engine *e, void *stream, const uint8_t *mask, const uint8_t *boards, const uint8_t *sides, const int32_t *rr) {
+    if (!e) return fail(CZ_EINVAL, "null engine");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t B = (size_t)e->d.B;
+    CUDA_TRY(cudaSetDevice(e->device));
+    if (mask) CUDA_TRY(cudaMemcpyAsync(e->d_mask, mask, B, cudaMemcpyHostToDevice, st));
+    if (boards) CUDA_TRY(cudaMemcpyAsync(e->d_boards, boards, B * 90, cudaMemcpyHostToDevice, st));
+    if (sides) CUDA_TRY(cudaMemcpyAsync(e->d_sides, sides, B, cudaMemcpyHostToDevice, st));
+    if (rr) CUDA_TRY(cudaMemcpyAsync(e->d_rr, rr, B * 4, cudaMemcpyHostToDevice, st));
+    k_reset<<<nblk(e->d.B, 128), 128, 0, st>>>(e->d, mask ? e->d_mask : nullptr, boards ? e->d_boards : nullptr,
+                                               sides ? e->d_sides : nullptr, rr ? e->d_rr : nullptr);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(st));   // host buffers may be pageable: do not return before they are consumed
+    return CZ_OK;
+}
+
+int cz_engine_begin_search(cz_engine *e, void *stream, const uint8_t *mask, int playouts) {
+    if (!e || playouts < 0) return fail(CZ_EINVAL, "cz_engine_begin_search: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaSetDevice(e->device));
+    if (mask) CUDA_TRY(cudaMemcpyAsync(e->d_mask, mask, (size_t)e->d.B, cudaMemcpyHostToDevice, st));
+    k_begin<<<nblk(e->d.B, 128), 128, 0, st>>>(e->d, mask ? e->d_mask : nullptr, playouts);
+    CUDA_TRY(cudaGetLastError());
+    if (mask) CUDA_TRY(cudaStreamSynchronize(st));
+    return CZ_OK;
+}
+
+extern "C++" {
+template <bool X, bool S>
+static int launch_wave(cz_engine *e, void *stream, void *nn_in, int dt, const float *logits, const float *value) {
+    dim3 gr(nblk(e->d.B, WARPS_PER_BLOCK)), bl(32 * WARPS_PER_BLOCK);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dt == CZ_F32) k_wave<float, X, S><<<gr, bl, 0, st>>>(e->d, (float *)nn_in, logits, value);
+    else if (dt == CZ_BF16) k_wave<__nv_bfloat16, X, S><<<gr, bl, 0, st>>>(e->d, (__nv_bfloat16 *)nn_in, logits, value);
+    else if (dt == CZ_F16) k_wave<__half, X, S><<<gr, bl, 0, st>>>(e->d, (__half *)nn_in, logits, value);
+    else return fail(CZ_EINVAL, "wave: nn_dtype");
+    CUDA_TRY(cudaGetLastError());
+    return CZ_OK;
+}
+}  // extern "C++"
+
+int cz_engine_wave(cz_engine *e, void *stream, void *nn_in, int nn_dtype, const float *logits, const float *value) {
+    if (!e || !nn_in || !logits || !value) return fail(CZ_EINVAL, "cz_engine_wave: null");
+    return launch_wave<true, true>(e, stream, nn_in, nn_dtype, logits, value);
+}
+int cz_engine_select(cz_engine *e, void *stream, void *nn_in, int nn_dtype) {
+    if (!e || !nn_in) return fail(CZ_EINVAL, "cz_engine_select: null");
+    return launch_wave<false, true>(e, stream, nn_in, nn_dtype, nullptr, nullptr);
+}
+int cz_engine_expand_backup(cz_engine *e, void *stream, const float *logits, const float *value) {
+    if (!e || !logits || !value) return fail(CZ_EINVAL, "cz_engine_expand_backup: null");
+    return launch_wave<true, false>(e, stream, (void *)logits, CZ_F32, logits, value);
+}
+
+int cz_engine_unfinished_async(cz_engine *e, void *stream, int32_t *dev_count) {
+    if (!e || !dev_count) return fail(CZ_EINVAL, "cz_engine_unfinished_async: null");
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaMemsetAsync(dev_count, 0, 4, st));
+    k_unfinished<<<nblk(e->d.B, 128), 128, 0, st>>>(e->d, dev_count);
+    CUDA_TRY(cudaGetLastError());
+    return CZ_OK;
+}
+
+int cz_engine_unfinished(cz_engine *e, void *stream, int32_t *out_count) {
+    if (!e || !out_count) return fail(CZ_EINVAL, "cz_engine_unfinished: null");
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaSetDevice(e->device));
+    int rc = cz_engine_unfinished_async(e, stream, e->d.st_count);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(e->h_i32, e->d.st_count, 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    *out_count = e->h_i32[0];
+    return CZ_OK;
+}
+
+int cz_engine_root_children(cz_engine *e, void *stream, int32_t *n_children, uint16_t *moves, int32_t *visits, float *w, float *p, float *q) {
+    if (!e) return fail(CZ_EINVAL, "null engine");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t B = (size_t)e->d.B, hb = B * CZ_MAXCHILD;
+    CUDA_TRY(cudaSetDevice(e->device));
+    k_root_children<<<nblk(e->d.B, WARPS_PER_BLOCK), 32 * WARPS_PER_BLOCK, 0, st>>>(e->d);
+    CUDA_TRY(cudaGetLastError());
+    if (n_children) CUDA_TRY(cudaMemcpyAsync(e->h_n, e->d.st_n, B * 4, cudaMemcpyDeviceToHost, st));
+    if (moves) CUDA_TRY(cudaMemcpyAsync(e->h_moves, e->d.st_moves, hb * 2, cudaMemcpyDeviceToHost, st));
+    if (visits) CUDA_TRY(cudaMemcpyAsync(e->h_visits, e->d.st_visits, hb * 4, cudaMemcpyDeviceToHost, st));
+    if (w) CUDA_TRY(cudaMemcpyAsync(e->h_f, e->d.st_w, hb * 4, cudaMemcpyDeviceToHost, st));
+    if (p) CUDA_TRY(cudaMemcpyAsync(e->h_f + hb, e->d.st_p, hb * 4, cudaMemcpyDeviceToHost, st));
+    if (q) CUDA_TRY(cudaMemcpyAsync(e->h_f + 2 * hb, e->d.st_q, hb * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (n_children) memcpy(n_children, e->h_n, B * 4);
+    if (moves) memcpy(moves, e->h_moves, hb * 2);
+    if (visits) memcpy(visits, e->h_visits, hb * 4);
+    if (w) memcpy(w, e->h_f, hb * 4);
+    if (p) memcpy(p, e->h_f + hb, hb * 4);
+    if (q) memcpy(q, e->h_f + 2 * hb, hb * 4);
+    return CZ_OK;
+}
+
+int cz_engine_play(cz_engine *e, void *stream, const int32_t *child_index) {
+    if (!e || !child_index) return fail(CZ_EINVAL, "cz_engine_play: null");
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaSetDevice(e->device));
+    memcpy(e->h_choice, child_index, (size_t)e->d.B * 4);
+    CUDA_TRY(cudaMemcpyAsync(e->d.st_choice, e->h_choice, (size_t)e->d.B * 4, cudaMemcpyHostToDevice, st));
+    k_play<<<nblk(e->d.B, WARPS_PER_BLOCK), 32 * WARPS_PER_BLOCK, 0, st>>>(e->d);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(st));   // h_choice is reused by the next call
+    return CZ_OK;
+}
+
+int cz_engine_status(cz_engine *e, void *stream, uint8_t *terminal, int8_t *winner, int32_t *ply, int32_t *rr, uint8_t *side, uint8_t *boards) {
+    if (!e) return fail(CZ_EINVAL, "null engine");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t B = (size_t)e->d.B;
+    CUDA_TRY(cudaSetDevice(e->device));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (terminal) CUDA_TRY(cudaMemcpy(terminal, e->d.terminal, B, cudaMemcpyDeviceToHost));
+    if (winner) CUDA_TRY(cudaMemcpy(winner, e->d.winner, B, cudaMemcpyDeviceToHost));
+    if (ply) CUDA_TRY(cudaMemcpy(ply, e->d.ply, B * 4, cudaMemcpyDeviceToHost));
+    if (rr) CUDA_TRY(cudaMemcpy(rr, e->d.rr, B * 4, cudaMemcpyDeviceToHost));
+    if (side) CUDA_TRY(cudaMemcpy(side, e->d.side, B, cudaMemcpyDeviceToHost));
+    if (boards) CUDA_TRY(cudaMemcpy2D(boards, 90, e->d.root_board, 96, 90, B, cudaMemcpyDeviceToHost));
+    return CZ_OK;
+}
+
+int cz_engine_counters(cz_engine *e, void *stream, int64_t *out) {
+    if (!e || !out) return fail(CZ_EINVAL, "cz_engine_counters: null");
+    const size_t B = (size_t)e->d.B;
+    CUDA_TRY(cudaSetDevice(e->device));
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    std::vector<unsigned long long> a(B), b(B), c(B), d(B);
+    std::vector<uint32_t> er(B), ma(B);
+    std::vector<int32_t> md(B);
+    CUDA_TRY(cudaMemcpy(a.data(), e->d.cnt_expand, B * 8, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(b.data(), e->d.cnt_playout, B * 8, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(c.data(), e->d.cnt_L, B * 8, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(d.data(), e->d.cnt_c, B * 8, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(er.data(), e->d.err, B * 4, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(ma.data(), e->d.max_alloc, B * 4, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(md.data(), e->d.max_depth, B * 4, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 8; i++) out[i] = 0;
+    out[6] = -1;
+    for (size_t g = 0; g < B; g++) {
+        out[0] += (int64_t)a[g]; out[1] += (int64_t)b[g]; out[2] += (int64_t)c[g]; out[3] += (int64_t)d[g];
+        out[4] |= er[g];
+        if (ma[g] > out[5]) out[5] = ma[g];
+        if (er[g] && out[6] < 0) out[6] = (int64_t)g;
+        if (md[g] > out[7]) out[7] = md[g];
+    }
+    return CZ_OK;
+}
+
+int cz_engine_tree_signature(cz_engine *e, void *stream, int game, int64_t *out, int64_t cap, int64_t *n) {
+    if (!e || !n || game < 0 || game >= e->d.B) return fail(CZ_EINVAL, "cz_engine_tree_signature: bad arguments");
+    CUDA_TRY(cudaSetDevice(e->device));
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    uint8_t cur;
+    uint32_t alloc, rbase;
+    int32_t rcnt;
+    CUDA_TRY(cudaMemcpy(&cur, e->d.cur + game, 1, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(&alloc, e->d.alloc + game, 4, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(&rbase, e->d.root_base + game, 4, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(&rcnt, e->d.root_cnt + game, 4, cudaMemcpyDeviceToHost));
+    std::vector<uint32_t> ar(alloc);
+    if (alloc) CUDA_TRY(cudaMemcpy(ar.data(), e->d.arena + ((size_t)game * 2 + cur) * (size_t)e->d.A, (size_t)alloc * 4, cudaMemcpyDeviceToHost));
+    int64_t k = 0;
+    struct Fr { uint32_t base; int cnt; int i; };
+    std::vector<Fr> stack;
+    if (rcnt > 0) stack.push_back({rbase, rcnt, 0});
+    const Labels &L = labels();
+    while (!stack.empty()) {
+        Fr &f = stack.back();
+        if (f.i >= f.cnt) { stack.pop_back(); continue; }
+        const uint32_t cs = (uint32_t)((f.cnt + 7) & ~7);
+        const uint32_t *blk = ar.data() + f.base + HDR;
+        const int i = f.i++;
+        const uint32_t meta = blk[3 * cs + i], child = blk[4 * cs + i];
+        const int N = (int)blk[2 * cs + i];
+        float W, Q;
+        memcpy(&W, &blk[cs + i], 4);
+        Q = N > 0 ? W / (float)N : 0.0f;
+        uint32_t qb;
+        memcpy(&qb, &Q, 4);
+        const int nch = child != NONE ? (int)(meta >> 16) : 0;
+        if (k < cap && out) {
+            int64_t *r = out + 6 * k;
+            r[0] = L.of[(meta & 127) * CZ_NSQ + ((meta >> 7) & 127)];
+            r[1] = N; r[2] = blk[cs + i]; r[3] = blk[i]; r[4] = qb; r[5] = nch;
+        }
+        k++;
+        if (nch > 0) stack.push_back({child, nch, 0});
+    }
+    *n = k;
+    return CZ_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,143 @@
+"""Python handle on the batched device engine (cz_engine_* in include/cchess_b200.h).
+
+torch is used for device buffers and streams only; all tree / rules work happens in the
+sm_100a kernels of csrc/cz_engine.cu."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import BF16, F16, F32, MAXCHILD, NLABEL, EngineError, check, lib
+
+_DT = {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16}
+
+
+def _hp(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class Engine:
+    def __init__(self, n_games, arena_words=0, device=None):
+        if not torch.cuda.is_available():
+            raise EngineError("cchess_zero_b200 needs a CUDA device (no CPU fallback exists)")
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self.B = int(n_games)
+        h = C.c_void_p()
+        check(lib().cz_engine_create(self.B, int(arena_words), self.device, C.byref(h)), "cz_engine_create")
+        self.h = h
+        self._count = torch.zeros(1, dtype=torch.int32, device="cuda:%d" % self.device)
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().cz_engine_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- game state -------------------------------------------------------------------
+    def reset(self, mask=None, boards=None, sides=None, rr=None):
+        m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+        b = None if boards is None else np.ascontiguousarray(boards, dtype=np.uint8).reshape(self.B, 90)
+        s = None if sides is None else np.ascontiguousarray(sides, dtype=np.uint8)
+        r = None if rr is None else np.ascontiguousarray(rr, dtype=np.int32)
+        check(lib().cz_engine_reset(self.h, _stream(), _hp(m), _hp(b), _hp(s), _hp(r)), "cz_engine_reset")
+
+    def begin_search(self, playouts, mask=None):
+        m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+        check(lib().cz_engine_begin_search(self.h, _stream(), _hp(m), int(playouts)), "cz_engine_begin_search")
+
+    # ---- waves (device tensors) ---------------------------------------------------------
+    def wave(self, nn_in, logits, value):
+        check(lib().cz_engine_wave(self.h, _stream(), nn_in.data_ptr(), _DT[nn_in.dtype], logits.data_ptr(), value.data_ptr()),
+              "cz_engine_wave")
+
+    def select(self, nn_in):
+        check(lib().cz_engine_select(self.h, _stream(), nn_in.data_ptr(), _DT[nn_in.dtype]), "cz_engine_select")
+
+    def expand_backup(self, logits, value):
+        check(lib().cz_engine_expand_backup(self.h, _stream(), logits.data_ptr(), value.data_ptr()), "cz_engine_expand_backup")
+
+    def unfinished(self):
+        out = C.c_int32(0)
+        check(lib().cz_engine_unfinished(self.h, _stream(), C.byref(out)), "cz_engine_unfinished")
+        return out.value
+
+    def unfinished_async(self):
+        check(lib().cz_engine_unfinished_async(self.h, _stream(), self._count.data_ptr()), "cz_engine_unfinished_async")
+        return self._count
+
+    # ---- root statistics / moves ----------------------------------------------------------
+    def root_children(self, want_wpq=True):
+        B = self.B
+        n = np.zeros(B, dtype=np.int32)
+        mv = np.zeros((B, MAXCHILD), dtype=np.uint16)
+        vis = np.zeros((B, MAXCHILD), dtype=np.int32)
+        w = np.zeros((B, MAXCHILD), dtype=np.float32) if want_wpq else None
+        p = np.zeros((B, MAXCHILD), dtype=np.float32) if want_wpq else None
+        q = np.zeros((B, MAXCHILD), dtype=np.float32) if want_wpq else None
+        check(lib().cz_engine_root_children(self.h, _stream(), _hp(n), _hp(mv), _hp(vis), _hp(w), _hp(p), _hp(q)),
+              "cz_engine_root_children")
+        return dict(n=n, moves=mv, visits=vis, w=w, p=p, q=q)
+
+    def play(self, child_index):
+        ci = np.ascontiguousarray(child_index, dtype=np.int32)
+        assert ci.shape == (self.B,)
+        check(lib().cz_engine_play(self.h, _stream(), _hp(ci)), "cz_engine_play")
+
+    def status(self, boards=True):
+        B = self.B
+        t = np.zeros(B, dtype=np.uint8)
+        w = np.zeros(B, dtype=np.int8)
+        ply = np.zeros(B, dtype=np.int32)
+        rr = np.zeros(B, dtype=np.int32)
+        side = np.zeros(B, dtype=np.uint8)
+        bd = np.zeros((B, 90), dtype=np.uint8) if boards else None
+        check(lib().cz_engine_status(self.h, _stream(), _hp(t), _hp(w), _hp(ply), _hp(rr), _hp(side), _hp(bd)), "cz_engine_status")
+        return dict(terminal=t, winner=w, ply=ply, rr=rr, side=side, boards=bd)
+
+    def counters(self):
+        out = np.zeros(8, dtype=np.int64)
+        check(lib().cz_engine_counters(self.h, _stream(), _hp(out)), "cz_engine_counters")
+        return dict(n_expand=int(out[0]), n_playout=int(out[1]), sum_L=int(out[2]), sum_c=int(out[3]), error=int(out[4]),
+                    max_arena_words=int(out[5]), first_error_game=int(out[6]), max_depth=int(out[7]))
+
+    def raise_on_error(self):
+        c = self.counters()
+        if c["error"]:
+            names = [v for k, v in _lib.ERR_NAMES.items() if c["error"] & k]
+            raise EngineError("engine error flags %s (first game %d)" % ("|".join(names), c["first_error_game"]))
+        return c
+
+    def tree_signature(self, game, cap=1 << 16):
+        out = np.zeros((cap, 6), dtype=np.int64)
+        n = C.c_int64(0)
+        check(lib().cz_engine_tree_signature(self.h, _stream(), int(game), _hp(out), cap, C.byref(n)), "cz_engine_tree_signature")
+        if n.value > cap:
+            return self.tree_signature(game, int(n.value))
+        return out[: n.value].copy()
+
+    # ---- a whole search: MCTS_tree.main for every selected game ---------------------------
+    def search(self, forward_dev, playouts, nn_in, logits, value, mask=None, check_every=1):
+        """forward_dev(nn_in) must fill `logits` [B,2086] f32 and `value` [B] (or [B,1]) f32 in place
+        (device tensors).  Runs waves until every selected game has finished `playouts` playouts."""
+        self.begin_search(playouts, mask)
+        waves = 0
+        while True:
+            self.wave(nn_in, logits, value)
+            waves += 1
+            if waves > playouts and (waves - playouts) % check_every == 0 and self.unfinished() == 0:
+                break
+            forward_dev(nn_in)
+            if waves > 4 * playouts + 64:
+                self.raise_on_error()
+                raise EngineError("search did not converge after %d waves" % waves)
+        return waves

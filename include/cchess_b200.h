@@ -1,0 +1,148 @@
+/*
+ * cchess_b200.h -- C ABI of the B200-native batched MCTS self-play engine.
+ *
+ * The reference (chengstone/cchess-zero) is pure Python and has no FFI; this header is
+ * the boundary a maintainer would bind from the reference's Python (ctypes stub in
+ * INTEGRATION.md).  Each entry point names the reference code it replaces
+ * (file:line relative to the reference tree).
+ *
+ * Conventions
+ *   - every function returns an int status: CZ_OK (0) or a negative CZ_E* code; nothing
+ *     throws across the boundary; cz_last_error() gives a thread-local message.
+ *   - plain pointers and sizes only.  "host" buffers are ordinary (ideally pinned) host
+ *     memory owned by the caller; "dev" pointers are CUDA device pointers owned by the
+ *     caller (e.g. torch tensors' data_ptr()).  `stream` is a cudaStream_t passed as void*
+ *     (NULL = default stream); asynchronous work is ordered on it.
+ *   - boards are 90 bytes, row-major sq = y*9 + x (y = rank 0..9 = row of the reference's
+ *     state string, x = file a..i), piece codes 0 = empty, 1..7 = K A R B N P C (red /
+ *     upper-case / 'w'), 8..14 = k a r b n p c (black / 'b')  [pieces_order, main.py:208].
+ *   - a move is uint16: src_sq | dst_sq << 7.   side: 0 = 'w' (red), 1 = 'b'.
+ *   - a handle is bound to one GPU; calls on one handle are not thread-safe.
+ */
+#ifndef CCHESS_B200_H
+#define CCHESS_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CZ_OK 0
+#define CZ_EINVAL (-1)   /* bad argument */
+#define CZ_ECUDA (-2)    /* CUDA runtime error (see cz_last_error) */
+#define CZ_ENOMEM (-3)   /* allocation failed */
+#define CZ_EENGINE (-4)  /* a game raised an engine error flag (see cz_engine_counters) */
+
+#define CZ_NSQ 90
+#define CZ_NLABEL 2086       /* labels_len, main.py:212 */
+#define CZ_MAXCHILD 128      /* upper bound on pseudo-legal moves of one position */
+#define CZ_ENC_LEN 1260      /* 9*10*14, main.py:550 */
+
+/* nn input element types accepted by encode / wave */
+#define CZ_F32 0
+#define CZ_BF16 1
+#define CZ_F16 2
+
+/* per-game error flags (cz_engine_counters) */
+#define CZ_ERR_NOMOVES 1     /* expanded node with zero legal moves (reference: ValueError from max(), main.py:159) */
+#define CZ_ERR_NOLABEL 2     /* move outside the 2086-label table (reference: KeyError, main.py:181) */
+#define CZ_ERR_DEPTH 4       /* search path deeper than the path stack */
+#define CZ_ERR_ARENA 8       /* tree arena exhausted */
+#define CZ_ERR_CHILDREN 16   /* more than CZ_MAXCHILD moves */
+
+const char *cz_last_error(void);
+int cz_version(void);
+
+/* ---- move-label codec: create_uci_labels main.py:30-65, label2i 217, unflipped_index 213-214 ---- */
+int cz_labels(char *out /* [2086*4] host, no terminators */);
+int cz_label_index(int src_sq, int dst_sq);           /* >= 0 label index, -1 if not a label */
+int cz_unflipped_index(int32_t *out /* [2086] host */);
+
+/* ---- state strings: GameBoard.board_to_pos_name main.py:705-714, re-compression 691-699 ---- */
+int cz_from_state(const char *state, uint8_t *board /* [90] */);
+int cz_to_state(const uint8_t *board, char *out /* >= 100 bytes */);
+
+/* ---- stateless, batched rules; HOST buffers, computed on the GPU (copies included) ----
+ * cz_legal_moves_batch  replaces GameBoard.get_legal_moves            main.py:743-1109 (same ORDER)
+ * cz_apply_moves_batch  replaces GameBoard.sim_do_action + is_kill_move  main.py:647-702, 219-227
+ * cz_encode_batch       replaces MCTS_tree.generate_inputs (try_flip + state_to_positions, incl. the
+ *                       rank*9+file indexing of the [9][10][14] tensor) main.py:531-574            */
+int cz_legal_moves_batch(int device, const uint8_t *boards /* [n][90] */, const uint8_t *sides /* [n] */, int n,
+                         uint16_t *moves /* [n][128] */, int32_t *counts /* [n] */);
+int cz_apply_moves_batch(int device, uint8_t *boards /* [n][90] in/out */, const uint16_t *moves /* [n] */, int n,
+                         uint8_t *captured /* [n] piece code captured or 0 */);
+int cz_encode_batch(int device, const uint8_t *boards, const uint8_t *sides, int n, float *out /* [n][9][10][14] */);
+/* device-pointer variants (no copies; async on stream) */
+int cz_legal_moves_dev(const uint8_t *boards, const uint8_t *sides, int n, uint16_t *moves, int32_t *counts, void *stream);
+int cz_encode_dev(const uint8_t *boards, const uint8_t *sides, int n, void *out, int dtype, void *stream);
+
+/* ---- the batched engine: n_games independent (GameBoard, MCTS_tree) pairs resident in HBM ---- */
+typedef struct cz_engine cz_engine;
+
+/* arena_words: uint32 words of tree storage per game per half (two halves, ping-pong re-rooting);
+ * 0 selects the default (2 Mi words = 8 MiB per half). */
+int cz_engine_create(int n_games, int64_t arena_words, int device, cz_engine **out);
+int cz_engine_destroy(cz_engine *e);
+int cz_engine_n_games(const cz_engine *e);
+
+/* GameBoard.reload (main.py:604-608) + MCTS_tree.reload (255-258) for the games with mask[g] != 0
+ * (mask NULL = all).  boards/sides/rr NULL = the start position, 'w', 0. All host pointers. */
+int cz_engine_reset(cz_engine *e, void *stream, const uint8_t *mask, const uint8_t *boards, const uint8_t *sides,
+                    const int32_t *rr);
+
+/* Start a search of `playouts` playouts (MCTS_tree.main's loop count, main.py:490) on the games with
+ * mask[g] != 0 (NULL = every non-terminal game). */
+int cz_engine_begin_search(cz_engine *e, void *stream, const uint8_t *mask, int playouts);
+
+/* One wave = one kernel launch (capturable in a CUDA graph; no host sync, no allocation):
+ *   1. for every game with a pending leaf: expand it from logits/value of the previous wave
+ *      (leaf_node.expand main.py:175-187 incl. flip_policy 1152-1155 and the legal-move generation),
+ *      undo the virtual loss and back the value up (main.py:426-435, 189-194);
+ *   2. run playouts of start_tree_search (main.py:350-440, search_threads = 1 semantics) until the
+ *      game needs a network evaluation: PUCT selection (108-116, 158-159), virtual loss (403-404),
+ *      terminal / 60-ply rule (409-416); terminal playouts are backed up in-kernel and the game
+ *      continues with its next playout;
+ *   3. encode the leaf (main.py:531-557) into row g of nn_in.
+ * nn_in: dev [n_games][9][10][14] of `nn_dtype`; logits: dev f32 [n_games][2086]; value: dev f32 [n_games].
+ * A game's row of logits/value is only read if that game has a pending leaf.                              */
+int cz_engine_wave(cz_engine *e, void *stream, void *nn_in, int nn_dtype, const float *logits, const float *value);
+/* the two halves of a wave as separate launches */
+int cz_engine_select(cz_engine *e, void *stream, void *nn_in, int nn_dtype);
+int cz_engine_expand_backup(cz_engine *e, void *stream, const float *logits, const float *value);
+
+/* Number of games that still have playouts to run or a leaf pending (device->host, synchronises stream). */
+int cz_engine_unfinished(cz_engine *e, void *stream, int32_t *out_count);
+/* Asynchronous form: writes the count to *dev_count (device int32) without synchronising. */
+int cz_engine_unfinished_async(cz_engine *e, void *stream, int32_t *dev_count);
+
+/* Root statistics in child (= move generation) order: what get_action reads from root.child
+ * (main.py:1339) and MCTS_tree.Q (261-270).  HOST buffers; synchronises stream.
+ * q = f32(W/N) (0 when N == 0).  Any pointer may be NULL. */
+int cz_engine_root_children(cz_engine *e, void *stream, int32_t *n_children /* [B] (-1: root not expanded) */,
+                            uint16_t *moves /* [B][128] */, int32_t *visits /* [B][128] */,
+                            float *w /* [B][128] */, float *p /* [B][128] */, float *q /* [B][128] */);
+
+/* Play child_index[g] (index into the root's children; < 0 = leave game g alone):
+ * GameBoard state update (main.py:1522-1528) + MCTS_tree.update_tree (272-276): the chosen child's
+ * subtree is compacted into the other arena half and becomes the root; terminal flags are updated
+ * (main.py:1532-1545).  child_index is a HOST buffer. */
+int cz_engine_play(cz_engine *e, void *stream, const int32_t *child_index /* [B] */);
+
+/* Game status (cchess_main.check_end main.py:1380-1392): HOST buffers, any may be NULL; synchronises.
+ * terminal: 0 running, 1 king captured, 2 draw (restrict_round >= 60); winner: 0 'w', 1 'b', -1 none. */
+int cz_engine_status(cz_engine *e, void *stream, uint8_t *terminal, int8_t *winner, int32_t *ply, int32_t *rr,
+                     uint8_t *side, uint8_t *boards /* [B][90] */);
+
+/* Counters since creation, summed over games: out[0] expansions (calls of expand), out[1] playouts,
+ * out[2] sum of path lengths L, out[3] sum of scanned children c_l, out[4] OR of per-game error flags,
+ * out[5] max arena words in use, out[6] index of first game with an error (or -1), out[7] max path length. */
+int cz_engine_counters(cz_engine *e, void *stream, int64_t *out /* [8] */);
+
+/* Test hook: flat DFS signature of game g's tree, records of 6 int64
+ * (label index, N, W bits, P bits, Q bits, n_children), children in order. Returns record count via *n. */
+int cz_engine_tree_signature(cz_engine *e, void *stream, int game, int64_t *out, int64_t cap, int64_t *n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,226 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the golden vectors produced by the
+reference and against the CPU oracle on seeded inputs.  Bit-exact everywhere (integer / f32-bit compares)."""
+import hashlib
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def sha(b):
+    return hashlib.sha256(b).hexdigest()[:16]
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import oracle
+    return oracle
+
+
+@pytest.fixture(scope="module")
+def R():
+    from cchess_zero_b200 import rules
+    rules._init_tables()
+    return rules
+
+
+def test_rules_against_reference_vectors(R):
+    g = load_golden("movegen.json.gz")["records"]
+    boards = np.stack([R.state_to_board(r["state"]) for r in g])
+    sides = np.array([0 if r["player"] == "w" else 1 for r in g], dtype=np.uint8)
+    mv, cnt = R.legal_moves_batch(boards, sides)
+    enc = R.encode_batch(boards, sides)
+    for i, r in enumerate(g):
+        assert " ".join(R.move_to_label(m) for m in mv[i, : cnt[i]]) == r["moves"], r["state"]
+        assert [int(k) for k in np.nonzero(enc[i].reshape(-1))[0]] == r["enc"]
+    assert set(np.unique(enc)) <= {0.0, 1.0}
+    have = [i for i, r in enumerate(g) if "move" in r]
+    nb, cap = R.apply_moves_batch(boards[have], [R.label_to_move(g[i]["move"]) for i in have])
+    for k, i in enumerate(have):
+        assert R.board_to_state(nb[k]) == g[i]["next"]
+        assert int(cap[k] != 0) == g[i]["kill"]
+
+
+def test_gameboard_surface(R):
+    gb = R.GameBoard()
+    mv = R.GameBoard.get_legal_moves(gb.state, "w")
+    assert len(mv) == 44 and mv[:4] == ["a0a1", "a0a2", "b0a2", "b0c2"]
+    assert R.GameBoard.sim_do_action("h2e2", gb.state) == "RNBAKABNR/9/1C2C4/P1P1P1P1P/9/9/p1p1p1p1p/1c5c1/9/rnbakabnr"
+    assert R.GameBoard.sim_do_action("b7b0", gb.state) == "RcBAKABNR/9/1C5C1/P1P1P1P1P/9/9/p1p1p1p1p/7c1/9/rnbakabnr"
+    with pytest.raises(KeyError):
+        R.label2i["a0a0"]
+
+
+def _random_positions(O, n_games, seed, max_plies=160):
+    rng = np.random.RandomState(seed)
+    boards, sides = [], []
+    for _ in range(n_games):
+        b, side = O.from_state(O.START), 0
+        for _ply in range(max_plies):
+            boards.append(b.copy()); sides.append(side)
+            mv = O.legal_moves(b, side)
+            if len(mv) == 0:
+                break
+            b, cap = O.apply_move(b, mv[rng.randint(len(mv))])
+            side ^= 1
+            if cap in (1, 8):
+                boards.append(b.copy()); sides.append(side)
+                break
+    return np.stack(boards), np.array(sides, dtype=np.uint8)
+
+
+def test_rules_random_play_vs_oracle(O, R):
+    boards, sides = _random_positions(O, 400, 123)
+    assert len(boards) > 30000
+    mv, cnt = R.legal_moves_batch(boards, sides)
+    enc = R.encode_batch(boards, sides)
+    for i in range(len(boards)):
+        om = O.legal_moves(boards[i], int(sides[i]))
+        assert cnt[i] == len(om) and np.array_equal(mv[i, : cnt[i]], om), i
+    for i in range(0, len(boards), 7):
+        assert np.array_equal(enc[i], O.encode(boards[i], int(sides[i])))
+
+
+def test_encode_dtypes(O, R):
+    from cchess_zero_b200._lib import lib, check, BF16, F16, F32
+    boards, sides = _random_positions(O, 10, 5)
+    n = len(boards)
+    db = torch.from_numpy(boards).cuda()
+    ds = torch.from_numpy(sides).cuda()
+    ref = torch.from_numpy(R.encode_batch(boards, sides)).cuda()
+    for dt, code in ((torch.float32, F32), (torch.bfloat16, BF16), (torch.float16, F16)):
+        out = torch.full((n, 9, 10, 14), 7.0, dtype=dt, device="cuda")
+        check(lib().cz_encode_dev(db.data_ptr(), ds.data_ptr(), n, out.data_ptr(), code, None))
+        torch.cuda.synchronize()
+        assert torch.equal(out.float(), ref)
+
+
+def test_fakenets_match_oracle(O, R):
+    from cchess_zero_b200.fakenet import FakeNet
+    boards, sides = _random_positions(O, 6, 9)
+    enc = R.encode_batch(boards, sides)
+    x = torch.from_numpy(enc).cuda()
+    for kind in ("hash_signed", "hash_pos", "mod17"):
+        lo, v = FakeNet(kind)(x)
+        olo, ov = O.fake_forward(kind, enc)
+        assert np.array_equal(lo.cpu().numpy(), olo), kind
+        assert np.array_equal(v.cpu().numpy(), ov.reshape(-1)), kind
+
+
+def _run_cases(cases, net, R, split=False, graph=False):
+    """cases: list of dict(board, side, rr, playouts).  Returns the engine after searching."""
+    from cchess_zero_b200.engine import Engine
+    from cchess_zero_b200.fakenet import FakeNet
+    B = len(cases)
+    e = Engine(B, arena_words=1 << 20)
+    e.reset(None, np.stack([c["board"] for c in cases]), [c["side"] for c in cases], [c["rr"] for c in cases])
+    fn = FakeNet(net)
+    nn_in = torch.zeros((B, 9, 10, 14), device="cuda")
+    logits = torch.zeros((B, 2086), device="cuda")
+    value = torch.zeros((B,), device="cuda")
+    pl = np.array([c["playouts"] for c in cases])
+    for p in np.unique(pl):
+        e.begin_search(int(p), (pl == p).astype(np.uint8))
+
+    def fwd():
+        lo, v = fn(nn_in)
+        logits.copy_(lo); value.copy_(v)
+
+    waves = 0
+    while True:
+        if split:
+            e.expand_backup(logits, value)
+            e.select(nn_in)
+        else:
+            e.wave(nn_in, logits, value)
+        waves += 1
+        if e.unfinished() == 0:
+            break
+        fwd()
+        assert waves < 5 * pl.max() + 50
+    e.raise_on_error()
+    return e
+
+
+@pytest.mark.parametrize("net", ["mod17", "hash_signed", "hash_pos"])
+def test_tree_against_reference_vectors(net, R):
+    cases = [c for c in load_golden("tree.json")["cases"] if c["net"] == net]
+    e = _run_cases([dict(board=R.state_to_board(c["state"]), side=0 if c["player"] == "w" else 1, rr=c["rr"],
+                         playouts=c["playouts"]) for c in cases], net, R)
+    rc = e.root_children()
+    for g, c in enumerate(cases):
+        sig = e.tree_signature(g)
+        assert sig.shape[0] == c["n_nodes"], c["note"]
+        assert sig[:40].tolist() == c["head"], c["note"]
+        assert sha(sig.tobytes()) == c["sha_sig"], c["note"]
+        n = rc["n"][g]
+        got = [[R.move_to_label(rc["moves"][g, i]), int(rc["visits"][g, i]), int(rc["w"][g, i].view(np.uint32)),
+                int(rc["p"][g, i].view(np.uint32)), int(rc["q"][g, i].view(np.uint32))] for i in range(n)]
+        assert got == c["root"], c["note"]
+
+
+@pytest.mark.parametrize("net,split", [("hash_signed", False), ("hash_pos", True)])
+def test_tree_many_positions_vs_oracle(net, split, O, R):
+    boards, sides = _random_positions(O, 3, 77)
+    sel = np.arange(0, len(boards), max(1, len(boards) // 96))[:96]
+    rng = np.random.RandomState(1)
+    cases = [dict(board=boards[i], side=int(sides[i]), rr=int(rng.choice([0, 5, 56, 58])), playouts=int(rng.choice([50, 150, 250])))
+             for i in sel if (boards[i] == 1).any() and (boards[i] == 8).any()]
+    e = _run_cases(cases, net, R, split=split)
+    cnt = e.counters()
+    tot = dict(n_expand=0, n_playout=0, sum_L=0, sum_c=0)
+    for g, c in enumerate(cases):
+        t = O.Tree(c["board"])
+        assert t.search(c["side"], c["rr"], c["playouts"], net) == 0
+        assert np.array_equal(t.signature(), e.tree_signature(g)), g
+        s = t.stats()
+        for k in tot:
+            tot[k] += s[k]
+    for k in tot:
+        assert cnt[k] == tot[k], k
+
+
+def _golden_selfplay_games(net):
+    return [g for g in load_golden("selfplay.json")["games"] if g["net"] == net]
+
+
+@pytest.mark.parametrize("net", ["hash_pos", "hash_signed", "mod17"])
+def test_selfplay_tuples_against_reference_vectors(net, R):
+    from cchess_zero_b200.fakenet import FakeNet
+    from cchess_zero_b200.selfplay import SelfPlay
+    games = _golden_selfplay_games(net)
+    sp = SelfPlay(len(games), FakeNet(net), [g["playouts"] for g in games], seeds=[g["seed"] for g in games],
+                  arena_words=1 << 20, auto_reset=False)
+    out = sp.play_games()
+    assert len(out) == len(games)
+    for (slot, rec), g in zip(out, games):
+        assert len(rec) == g["n"]
+        assert rec.states == g["states"]
+        assert [float(z) for z in rec.z] == g["z"]
+        pis = rec.dense_pi()
+        assert sha(pis.tobytes()) == g["sha_pi"]
+        for p, spv in zip(pis, g["pi_sparse"]):
+            assert [[int(k), float(p[k]).hex()] for k in np.nonzero(p)[0]] == spv
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_selfplay_many_games_vs_oracle(graph, O, R):
+    from cchess_zero_b200.fakenet import FakeNet
+    from cchess_zero_b200.selfplay import SelfPlay
+    B, playouts, net = 48, 40, "hash_pos"
+    sp = SelfPlay(B, FakeNet(net), playouts, seeds=[1000 + i for i in range(B)], arena_words=1 << 20, auto_reset=False)
+    if graph:
+        sp.capture_graph()
+    out = sp.play_games()
+    assert len(out) == B
+    for slot, rec in out:
+        with np.errstate(all="ignore"):
+            r = O.selfplay_game(net, playouts, np.random.RandomState(1000 + slot))
+        assert rec.states == r["states"], slot
+        assert np.array_equal(rec.z, r["z"])
+        assert np.array_equal(rec.dense_pi(), r["pis"])
+        assert rec.actions == r["actions"]
