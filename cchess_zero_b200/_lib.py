@@ -34,6 +34,7 @@ def _sig(L):
     L.cz_engine_destroy.argtypes = [vp]
     L.cz_engine_n_games.argtypes = [vp]
     L.cz_engine_reset.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.cz_engine_set_root_meta.argtypes = [vp, vp, vp, vp, vp]
     L.cz_engine_begin_search.argtypes = [vp, vp, vp, i32]
     L.cz_engine_wave.argtypes = [vp, vp, vp, i32, vp, vp]
     L.cz_engine_select.argtypes = [vp, vp, vp, i32]

@@ -125,6 +125,7 @@ struct WarpSmem {
     uint8_t board[96];
     uint16_t moves[136];
     float ps[128];
+    cz::MoveScratch scratch;
 };
 
 // order-preserving map of a double onto uint64 (NaN must be removed by the caller, -0 canonicalised)
@@ -157,7 +158,7 @@ __device__ bool warp_expand(const Dev &E, int g, uint32_t *ar, WarpSmem &S, cons
     if (lane < 24) reinterpret_cast<uint32_t *>(S.board)[lane] = lb[lane];
     __syncwarp();
     const int lside = S.board[90];
-    int n = cz::warp_legal_moves(S.board, lside, S.moves, lane);
+    int n = cz::warp_legal_moves(S.board, lside, S.moves, S.scratch, lane);
     uint32_t errf = 0;
     if (n == 0) errf |= CZ_ERR_NOMOVES;
     if (n > CZ_MAXCHILD) { errf |= CZ_ERR_CHILDREN; n = CZ_MAXCHILD; }
@@ -389,6 +390,13 @@ __global__ void k_reset(Dev E, const uint8_t *mask, const uint8_t *boards, const
     E.winner[g] = -1;
 }
 
+__global__ void k_set_meta(Dev E, const uint8_t *mask, const uint8_t *sides, const int32_t *rr) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= E.B || (mask && !mask[g])) return;
+    if (sides) E.side[g] = sides[g];
+    if (rr) E.rr[g] = rr[g];
+}
+
 __global__ void k_begin(Dev E, const uint8_t *mask, int playouts) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= E.B) return;
@@ -514,7 +522,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_legal_moves(const uint
     WarpSmem &S = smem[w];
     for (int i = lane; i < 90; i += 32) S.board[i] = boards[(size_t)g * 90 + i];
     __syncwarp();
-    int c = cz::warp_legal_moves(S.board, sides[g], S.moves, lane);
+    int c = cz::warp_legal_moves(S.board, sides[g], S.moves, S.scratch, lane);
     if (lane == 0) counts[g] = c;
     if (c > CZ_MAXCHILD) c = CZ_MAXCHILD;
     for (int i = lane; i < CZ_MAXCHILD; i += 32) moves[(size_t)g * CZ_MAXCHILD + i] = i < c ? S.moves[i] : (uint16_t)0;
@@ -799,6 +807,20 @@ int cz_engine_reset(cz_engine *e, void *stream, const uint8_t *mask, const uint8
     return CZ_OK;
 }
 
+int cz_engine_set_root_meta(cz_engine *e, void *stream, const uint8_t *mask, const uint8_t *sides, const int32_t *rr) {
+    if (!e) return fail(CZ_EINVAL, "null engine");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t B = (size_t)e->d.B;
+    CUDA_TRY(cudaSetDevice(e->device));
+    if (mask) CUDA_TRY(cudaMemcpyAsync(e->d_mask, mask, B, cudaMemcpyHostToDevice, st));
+    if (sides) CUDA_TRY(cudaMemcpyAsync(e->d_sides, sides, B, cudaMemcpyHostToDevice, st));
+    if (rr) CUDA_TRY(cudaMemcpyAsync(e->d_rr, rr, B * 4, cudaMemcpyHostToDevice, st));
+    k_set_meta<<<nblk(e->d.B, 128), 128, 0, st>>>(e->d, mask ? e->d_mask : nullptr, sides ? e->d_sides : nullptr, rr ? e->d_rr : nullptr);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return CZ_OK;
+}
+
 int cz_engine_begin_search(cz_engine *e, void *stream, const uint8_t *mask, int playouts) {
     if (!e || playouts < 0) return fail(CZ_EINVAL, "cz_engine_begin_search: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
@@ -970,7 +992,13 @@ int cz_engine_tree_signature(cz_engine *e, void *stream, int game, int64_t *out,
         if (k < cap && out) {
             int64_t *r = out + 6 * k;
             r[0] = L.of[(meta & 127) * CZ_NSQ + ((meta >> 7) & 127)];
-            r[1] = N; r[2] = blk[cs + i]; r[3] = blk[i]; r[4] = qb; r[5] = nch;
+            float P;
+            memcpy(&P, &blk[i], 4);
+            r[1] = N;
+            r[2] = W != W ? 0x7FC00000u : blk[cs + i];   // NaN payloads are not part of parity
+            r[3] = P != P ? 0x7FC00000u : blk[i];
+            r[4] = Q != Q ? 0x7FC00000u : qb;
+            r[5] = nch;
         }
         k++;
         if (nch > 0) stack.push_back({child, nch, 0});

@@ -51,6 +51,12 @@ class Engine:
         r = None if rr is None else np.ascontiguousarray(rr, dtype=np.int32)
         check(lib().cz_engine_reset(self.h, _stream(), _hp(m), _hp(b), _hp(s), _hp(r)), "cz_engine_reset")
 
+    def set_root_meta(self, sides=None, rr=None, mask=None):
+        m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+        s = None if sides is None else np.ascontiguousarray(sides, dtype=np.uint8)
+        r = None if rr is None else np.ascontiguousarray(rr, dtype=np.int32)
+        check(lib().cz_engine_set_root_meta(self.h, _stream(), _hp(m), _hp(s), _hp(r)), "cz_engine_set_root_meta")
+
     def begin_search(self, playouts, mask=None):
         m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
         check(lib().cz_engine_begin_search(self.h, _stream(), _hp(m), int(playouts)), "cz_engine_begin_search")

@@ -1,0 +1,155 @@
+"""Drop-in for the reference's MCTS_tree / leaf_node surface (main.py:93-206, 234-577) on top of a
+one-game device engine.  Same constructor, same methods, same attribute names that main.py's callers
+touch (`root.child[label].N/.Q`, `Q(move)`, `update_tree`, `reload`, `forward`, `generate_inputs`,
+`try_flip`, `state_to_positions`, `is_black_turn`).
+
+Semantics: search_threads = 1 of the reference whatever `search_threads`
+is passed -- one playout at a time per tree is the deterministic schedule; concurrency comes from
+running thousands of trees per GPU (selfplay.SelfPlay), not from coroutines inside one tree."""
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import rules
+from ._lib import NLABEL
+from .engine import Engine
+
+
+class leaf_node(object):
+    """Read-only view of one root child (the fields get_action / get_hint / Q read, main.py:1286, 1339)."""
+
+    __slots__ = ("P", "Q", "N", "W", "U", "v", "parent", "child", "state")
+
+    def __init__(self, P, Q, N, W):
+        self.P, self.Q, self.N, self.W = P, Q, N, W
+        self.U = 0
+        self.v = 0
+        self.parent = None
+        self.child = {}
+        self.state = None
+
+
+class _Root(object):
+    def __init__(self, tree):
+        self._t = tree
+
+    @property
+    def state(self):
+        return self._t._state
+
+    @property
+    def N(self):
+        return self._t._root_N
+
+    @property
+    def child(self):
+        return self._t._children()
+
+    def is_leaf(self):
+        return len(self.child) == 0
+
+
+class MCTS_tree(object):
+    def __init__(self, in_state, in_forward, search_threads, arena_words=1 << 21):
+        self.noise_eps = 0.25
+        self.dirichlet_alpha = 0.3
+        # main.py:238 draws from np.random here (a 1-element Dirichlet is always [1.]); kept so that the
+        # global RNG stream is consumed exactly like the reference's constructor does.
+        self.p_ = (1 - self.noise_eps) * 1 + self.noise_eps * np.random.dirichlet([self.dirichlet_alpha])
+        self.c_puct = 5
+        self.forward = in_forward
+        self.virtual_loss = 3
+        self.search_threads = search_threads
+        self.engine = Engine(1, arena_words)
+        dev = torch.device("cuda", self.engine.device)
+        self._dev_forward = getattr(getattr(in_forward, "__self__", None), "forward_device", None)
+        dt = getattr(getattr(in_forward, "__self__", None), "nn_dtype", torch.float32) if self._dev_forward else torch.float32
+        self._nn_in = torch.zeros((1, 9, 10, 14), dtype=dt, device=dev)
+        self._logits = torch.zeros((1, NLABEL), dtype=torch.float32, device=dev)
+        self._value = torch.zeros((1,), dtype=torch.float32, device=dev)
+        self._h_in = torch.zeros((1, 9, 10, 14), dtype=torch.float32).pin_memory()
+        self._h_logits = torch.zeros((1, NLABEL), dtype=torch.float32).pin_memory()
+        self._h_value = torch.zeros((1,), dtype=torch.float32).pin_memory()
+        self.root = _Root(self)
+        self._set_position(in_state, "w", 0)
+        rules._init_tables()
+
+    # ---- internals -------------------------------------------------------------------------------
+    def _set_position(self, state, player, rr):
+        self.engine.reset(None, rules.state_to_board(state)[None], [rules.side_of(player)], [rr])
+        self._state, self._side, self._rr, self._root_N = state, rules.side_of(player), rr, 0
+        self._cache = None
+
+    def _eval(self, nn_in):
+        if self._dev_forward is not None:
+            self._dev_forward(nn_in, self._logits, self._value)
+            return
+        self._h_in.copy_(nn_in.float(), non_blocking=False)
+        probs, value = self.forward(self._h_in.numpy())
+        self._h_logits.copy_(torch.as_tensor(np.asarray(probs, dtype=np.float32).reshape(1, NLABEL)))
+        self._h_value[0] = float(np.asarray(value).reshape(-1)[0])
+        self._logits.copy_(self._h_logits, non_blocking=True)
+        self._value.copy_(self._h_value, non_blocking=True)
+
+    def _children(self):
+        if self._cache is None:
+            rc = self.engine.root_children()
+            n = int(rc["n"][0])
+            d = OrderedDict()
+            for i in range(max(n, 0)):
+                N = int(rc["visits"][0, i])
+                d[rules.move_to_label(rc["moves"][0, i])] = leaf_node(rc["p"][0, i], rc["q"][0, i] if N else 0, N, rc["w"][0, i])
+            self._cache = d
+        return self._cache
+
+    # ---- reference surface ---------------------------------------------------------------------
+    def reload(self):  # main.py:255-258
+        self._set_position(rules.START_STATE, "w", 0)
+
+    def Q(self, move) -> float:  # main.py:261-270
+        ch = self._children()
+        if move in ch:
+            return ch[move].Q
+        print("{} not exist in the child".format(move))
+        return 0.0
+
+    def update_tree(self, act):  # main.py:272-276
+        ch = self._children()
+        idx = list(ch.keys()).index(act)   # KeyError/ValueError like root.child[act]
+        self._root_N = ch[act].N
+        self.engine.play(np.array([idx], dtype=np.int32))
+        st = self.engine.status()
+        self._state = rules.board_to_state(st["boards"][0])
+        self._side, self._rr = int(st["side"][0]), int(st["rr"][0])
+        self._cache = None
+
+    def is_expanded(self, key) -> bool:  # main.py:333-335
+        return len(self._children()) > 0
+
+    def main(self, state, current_player, restrict_round, playouts):  # main.py:473-493
+        side = rules.side_of(current_player)
+        if side != self._side or restrict_round != self._rr:
+            self.engine.set_root_meta([side], [restrict_round])
+            self._side, self._rr = side, restrict_round
+        self.engine.search(self._eval, playouts, self._nn_in, self._logits, self._value)
+        self.engine.raise_on_error()
+        self._cache = None
+
+    def generate_inputs(self, in_state, current_player):  # main.py:531-533
+        return rules.encode_batch(rules.state_to_board(in_state)[None], [rules.side_of(current_player)])[0]
+
+    def state_to_positions(self, state):  # main.py:547-557 (no flip)
+        return rules.encode_batch(rules.state_to_board(state)[None], [0])[0]
+
+    def replace_board_tags(self, board):  # main.py:535-544
+        return "".join(rules.GameBoard.board_to_pos_name(board))
+
+    def try_flip(self, state, current_player, flip=False):  # main.py:560-574
+        if not flip:
+            return state, current_player
+        rows = state.split("/")
+        return "/".join(r.swapcase() for r in reversed(rows)), ("w" if current_player == "b" else "b")
+
+    def is_black_turn(self, current_player):  # main.py:576-577
+        return current_player == "b"

@@ -1,0 +1,299 @@
+"""The policy-value ResNet of the reference (policy_value_network.py:9-214), re-implemented in PyTorch.
+
+Architecture (policy_value_network.py:45-74, 151-162), NHWC input [B,9,10,14]:
+  conv3x3(14->128)+bias -> BN(no gamma/beta, eps 1e-5) -> ReLU
+  res_block_nums x [conv3x3 -> BN -> ReLU -> conv3x3 -> BN -> +skip -> ReLU]
+  policy: conv1x1(128->2) -> BN -> ReLU -> flatten (h, w, c) 180 -> FC 2086   (raw LOGITS, no softmax: line 64/210)
+  value : conv1x1(128->1) -> BN -> ReLU -> flatten 90 -> FC 256 ReLU -> FC 1 tanh
+Reference quirk kept by default: the TF1 graph never runs the batch-norm UPDATE_OPS
+(policy_value_network.py:104-106), so inference statistics stay at (mean 0, var 1) forever;
+`update_moving_stats=True` gives conventional behaviour.
+
+The tensor-core work (residual convolutions) goes through cuDNN/cuBLAS; this module is plumbing for the
+engine, which hands it a device-resident [B,9,10,14] batch and reads back logits/value on the device."""
+import os
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+NLABEL = 2086
+
+
+class RefBatchNorm(nn.Module):
+    """tf.contrib.layers.batch_norm(center=False, scale=False, epsilon=1e-5, decay=0.999)."""
+
+    def __init__(self, ch, eps=1e-5, decay=0.999, update_moving_stats=False):
+        super().__init__()
+        self.eps, self.decay, self.update = eps, decay, update_moving_stats
+        self.register_buffer("running_mean", torch.zeros(ch))
+        self.register_buffer("running_var", torch.ones(ch))
+
+    def forward(self, x):
+        if self.training:
+            mean = x.mean(dim=(0, 2, 3))
+            var = x.var(dim=(0, 2, 3), unbiased=False)
+            if self.update:
+                n = x.numel() / x.shape[1]
+                with torch.no_grad():
+                    self.running_mean.mul_(self.decay).add_(mean.detach() * (1 - self.decay))
+                    self.running_var.mul_(self.decay).add_(var.detach() * (n / max(n - 1, 1)) * (1 - self.decay))
+        else:
+            mean, var = self.running_mean, self.running_var
+        return (x - mean[None, :, None, None]) * torch.rsqrt(var[None, :, None, None] + self.eps)
+
+
+class ResBlock(nn.Module):
+    def __init__(self, ch, **bn):
+        super().__init__()
+        self.c1 = nn.Conv2d(ch, ch, 3, padding=1)
+        self.b1 = RefBatchNorm(ch, **bn)
+        self.c2 = nn.Conv2d(ch, ch, 3, padding=1)
+        self.b2 = RefBatchNorm(ch, **bn)
+
+    def forward(self, x):
+        y = F.relu(self.b1(self.c1(x)))
+        y = self.b2(self.c2(y))
+        return F.relu(x + y)
+
+
+class PolicyValueNet(nn.Module):
+    def __init__(self, res_block_nums=7, filters=128, update_moving_stats=False):
+        super().__init__()
+        bn = dict(update_moving_stats=update_moving_stats)
+        self.conv_in = nn.Conv2d(14, filters, 3, padding=1)
+        self.bn_in = RefBatchNorm(filters, **bn)
+        self.blocks = nn.ModuleList([ResBlock(filters, **bn) for _ in range(res_block_nums)])
+        self.p_conv = nn.Conv2d(filters, 2, 1)
+        self.p_bn = RefBatchNorm(2, **bn)
+        self.p_fc = nn.Linear(180, NLABEL)
+        self.v_conv = nn.Conv2d(filters, 1, 1)
+        self.v_bn = RefBatchNorm(1, **bn)
+        self.v_fc1 = nn.Linear(90, 256)
+        self.v_fc2 = nn.Linear(256, 1)
+        for m in self.modules():  # tf.layers / contrib defaults: glorot-uniform kernels, zero biases
+            if isinstance(m, (nn.Conv2d, nn.Linear)):
+                nn.init.xavier_uniform_(m.weight)
+                nn.init.zeros_(m.bias)
+
+    def forward(self, x_nhwc):
+        """x_nhwc: [B,9,10,14] -> (logits [B,2086], value [B,1])"""
+        x = x_nhwc.permute(0, 3, 1, 2)
+        x = F.relu(self.bn_in(self.conv_in(x)))
+        for b in self.blocks:
+            x = b(x)
+        p = F.relu(self.p_bn(self.p_conv(x))).permute(0, 2, 3, 1).reshape(x.shape[0], 180)
+        v = F.relu(self.v_bn(self.v_conv(x))).permute(0, 2, 3, 1).reshape(x.shape[0], 90)
+        logits = self.p_fc(p)
+        value = torch.tanh(self.v_fc2(F.relu(self.v_fc1(v))))
+        return logits, value
+
+
+_DT = {"fp32": torch.float32, "tf32": torch.float32, "bf16": torch.bfloat16, "fp16": torch.float16}
+
+
+class InferencePlan:
+    """Eval-mode forward with batch norm folded into the convolutions, channels-last, in one of
+    fp32 / tf32 / bf16 / fp16.  Takes the engine's NHWC batch as-is (its NCHW view is already
+    channels_last) and returns float32 logits / value on the device."""
+
+    def __init__(self, net, precision="fp32", fused=True):
+        assert precision in _DT
+        self.precision = precision
+        self.dtype = _DT[precision]
+        dt = self.dtype
+
+        def fold(conv, bn):
+            s = torch.rsqrt(bn.running_var + bn.eps)
+            w = (conv.weight * s[:, None, None, None]).detach()
+            b = ((conv.bias - bn.running_mean) * s).detach()
+            return w.to(dt).contiguous(memory_format=torch.channels_last), b.to(dt).contiguous()
+
+        with torch.no_grad():
+            self.w_in = fold(net.conv_in, net.bn_in)
+            self.blocks = [(fold(b.c1, b.b1), fold(b.c2, b.b2)) for b in net.blocks]
+            wp, bp = fold(net.p_conv, net.p_bn)
+            wv, bv = fold(net.v_conv, net.v_bn)
+            self.w_head = (torch.cat([wp, wv], 0).contiguous(memory_format=torch.channels_last), torch.cat([bp, bv], 0).contiguous())
+            self.p_fc = (net.p_fc.weight.detach().to(dt).contiguous(), net.p_fc.bias.detach().to(dt).contiguous())
+            self.v_fc1 = (net.v_fc1.weight.detach().float().contiguous(), net.v_fc1.bias.detach().float().contiguous())
+            self.v_fc2 = (net.v_fc2.weight.detach().float().contiguous(), net.v_fc2.bias.detach().float().contiguous())
+        self.fused = bool(fused) and self._probe_fused()
+
+    def _probe_fused(self):
+        try:
+            x = torch.randn(4, 128, 9, 10, device=self.w_in[0].device, dtype=self.dtype).contiguous(memory_format=torch.channels_last)
+            (w, b) = self.blocks[0][0] if self.blocks else self.w_in
+            if w.shape[1] != 128:
+                return False
+            with self._ctx():
+                a = torch.cudnn_convolution_relu(x, w, b, (1, 1), (1, 1), (1, 1), 1)
+                r = F.relu(F.conv2d(x, w, b, padding=1))
+                a2 = torch.cudnn_convolution_add_relu(x, w, x, 1.0, b, (1, 1), (1, 1), (1, 1), 1)
+                r2 = F.relu(F.conv2d(x, w, b, padding=1) + x)
+            tol = 1e-4 if self.dtype == torch.float32 else 5e-2
+            return bool(torch.allclose(a.float(), r.float(), atol=tol, rtol=tol) and torch.allclose(a2.float(), r2.float(), atol=tol, rtol=tol))
+        except Exception:
+            return False
+
+    def _ctx(self):
+        return _Tf32(self.precision == "tf32")
+
+    def _conv_relu(self, x, wb, pad):
+        w, b = wb
+        if self.fused and pad == 1:
+            return torch.cudnn_convolution_relu(x, w, b, (1, 1), (pad, pad), (1, 1), 1)
+        return F.relu_(F.conv2d(x, w, b, padding=pad))
+
+    def _conv_add_relu(self, x, wb, skip):
+        w, b = wb
+        if self.fused:
+            return torch.cudnn_convolution_add_relu(x, w, skip, 1.0, b, (1, 1), (1, 1), (1, 1), 1)
+        return F.relu_(F.conv2d(x, w, b, padding=1).add_(skip))
+
+    @torch.no_grad()
+    def __call__(self, nn_in, logits_out=None, value_out=None):
+        """nn_in: [B,9,10,14] of self.dtype on the device."""
+        B = nn_in.shape[0]
+        with self._ctx():
+            x = nn_in.permute(0, 3, 1, 2)
+            if x.dtype != self.dtype:
+                x = x.to(self.dtype)
+            x = self._conv_relu(x, self.w_in, 1)
+            for c1, c2 in self.blocks:
+                y = self._conv_relu(x, c1, 1)
+                x = self._conv_add_relu(y, c2, x)
+            h = F.relu_(F.conv2d(x, self.w_head[0], self.w_head[1]))      # [B,3,9,10] channels_last
+            h = h.permute(0, 2, 3, 1)                                      # [B,9,10,3]
+            p = h[..., :2].reshape(B, 180)
+            v = h[..., 2].reshape(B, 90).float()
+            logits = F.linear(p, self.p_fc[0], self.p_fc[1]).float()
+            value = torch.tanh(F.linear(F.relu_(F.linear(v, self.v_fc1[0], self.v_fc1[1])), self.v_fc2[0], self.v_fc2[1]))
+        if logits_out is not None:
+            logits_out.copy_(logits)
+            value_out.copy_(value.reshape(value_out.shape))
+            return None
+        return logits, value
+
+
+class _Tf32:
+    def __init__(self, on):
+        self.on = on
+
+    def __enter__(self):
+        self.prev = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+        torch.backends.cudnn.allow_tf32 = self.on
+        torch.backends.cuda.matmul.allow_tf32 = self.on
+
+    def __exit__(self, *a):
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = self.prev
+
+
+class policy_value_network(object):
+    """Drop-in for the reference class of the same name (policy_value_network.py:8-214):
+    forward(positions) -> (logits np [B,2086] f32, value np [B,1] f32); train_step; save; restore."""
+
+    def __init__(self, res_block_nums=7, precision=None, device=None, seed=0, update_moving_stats=False):
+        if not torch.cuda.is_available():
+            raise RuntimeError("policy_value_network needs a CUDA device")
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        self.save_dir = "./models"
+        self.filters_size = 128
+        self.prob_size = NLABEL
+        self.c_l2 = 0.0001
+        self.momentum = 0.9
+        self.global_norm = 100
+        self.global_step = 0
+        self.precision = precision or os.environ.get("CCHESS_NN_PRECISION", "fp32")
+        g = torch.Generator(device="cpu")
+        if seed is not None:
+            torch.manual_seed(seed)
+        self.net = PolicyValueNet(res_block_nums, self.filters_size, update_moving_stats).to(self.device)
+        self.net = self.net.to(memory_format=torch.channels_last)
+        self.opt = torch.optim.SGD(self.net.parameters(), lr=1e-3, momentum=self.momentum, nesterov=True)
+        self._plan = None
+        self.train_restore()
+
+    # -- inference -------------------------------------------------------------------------------
+    def plan(self):
+        if self._plan is None:
+            self.net.eval()
+            self._plan = InferencePlan(self.net, self.precision)
+        return self._plan
+
+    @property
+    def nn_dtype(self):
+        return _DT[self.precision]
+
+    def forward_device(self, nn_in, logits_out=None, value_out=None):
+        return self.plan()(nn_in, logits_out, value_out)
+
+    def forward(self, positions):
+        """policy_value_network.py:202-214: host arrays in, host arrays out."""
+        x = torch.as_tensor(np.asarray(positions, dtype=np.float32)).reshape(-1, 9, 10, 14)
+        x = x.to(self.device, non_blocking=True).to(self.nn_dtype)
+        logits, value = self.plan()(x)
+        return logits.cpu().numpy(), value.reshape(-1, 1).cpu().numpy()
+
+    # -- training (policy_value_network.py:76-126, 186-199) ---------------------------------------
+    def train_step(self, positions, probs, winners, learning_rate):
+        self._plan = None
+        self.net.train()
+        x = torch.as_tensor(np.asarray(positions, dtype=np.float32)).reshape(-1, 9, 10, 14).to(self.device)
+        pi = torch.as_tensor(np.asarray(probs, dtype=np.float32)).to(self.device)
+        z = torch.as_tensor(np.asarray(winners, dtype=np.float32)).reshape(-1, 1).to(self.device)
+        for gp in self.opt.param_groups:
+            gp["lr"] = float(learning_rate)
+        logits, value = self.net(x)
+        policy_loss = (-(pi * F.log_softmax(logits, dim=1)).sum(dim=1)).mean()
+        value_loss = F.mse_loss(value, z)
+        l2 = sum((p * p).sum() for p in self.net.parameters()) * (0.5 * self.c_l2)
+        loss = value_loss + policy_loss + l2
+        self.opt.zero_grad(set_to_none=True)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(self.net.parameters(), self.global_norm)
+        if not all(torch.isfinite(p.grad).all() for p in self.net.parameters()):
+            raise FloatingPointError("NaN Found!")   # tf.check_numerics, policy_value_network.py:122
+        self.opt.step()
+        self.global_step += 1
+        accuracy = (logits.argmax(1) == pi.argmax(1)).float().mean().item()
+        return accuracy, loss.item(), self.global_step
+
+    # -- checkpoints (policy_value_network.py:164-184) -------------------------------------------
+    def save(self, in_global_step):
+        os.makedirs(self.save_dir, exist_ok=True)
+        path = os.path.join(self.save_dir, "best_model.ckpt-%d" % int(in_global_step))
+        torch.save(dict(model=self.net.state_dict(), opt=self.opt.state_dict(), global_step=int(in_global_step)), path)
+        with open(os.path.join(self.save_dir, "checkpoint"), "w") as f:
+            f.write(os.path.basename(path) + "\n")
+        print("Model saved in file: {}".format(path))
+        return path
+
+    def restore(self, file):
+        print("Restoring from {0}".format(file))
+        ck = torch.load(file, map_location=self.device)
+        self.net.load_state_dict(ck["model"])
+        self.opt.load_state_dict(ck["opt"])
+        self.global_step = ck.get("global_step", 0)
+        self._plan = None
+
+    def train_restore(self):
+        idx = os.path.join(self.save_dir, "checkpoint")
+        if os.path.isfile(idx):
+            name = open(idx).read().strip()
+            if name and os.path.isfile(os.path.join(self.save_dir, name)):
+                self.restore(os.path.join(self.save_dir, name))
+                print("Successfully loaded:", name)
+                return
+        print("Could not find old network weights")
+
+
+class policy_value_network_gpus(policy_value_network):
+    """policy_value_network_gpus.py:9-379 replaced the batch split over in-graph towers; here every rank
+    owns one replica (one process per GPU), so the multi-GPU class is the single-GPU one per rank."""
+
+    def __init__(self, num_gpus=1, res_block_nums=7, **kw):
+        super().__init__(res_block_nums, **kw)
+        self.num_gpus = num_gpus
+        self.save_dir = "./gpu_models"

@@ -90,6 +90,10 @@ int cz_engine_n_games(const cz_engine *e);
 int cz_engine_reset(cz_engine *e, void *stream, const uint8_t *mask, const uint8_t *boards, const uint8_t *sides,
                     const int32_t *rr);
 
+/* Override side-to-move / restrict_round of the root without touching the tree: MCTS_tree.main takes
+ * current_player and restrict_round as call arguments (main.py:473).  Host pointers, any may be NULL. */
+int cz_engine_set_root_meta(cz_engine *e, void *stream, const uint8_t *mask, const uint8_t *sides, const int32_t *rr);
+
 /* Start a search of `playouts` playouts (MCTS_tree.main's loop count, main.py:490) on the games with
  * mask[g] != 0 (NULL = every non-terminal game). */
 int cz_engine_begin_search(cz_engine *e, void *stream, const uint8_t *mask, int playouts);

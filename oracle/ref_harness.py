@@ -169,7 +169,10 @@ NET_IDS = {"hash_signed": 0, "hash_pos": 1, "mod17": 2}
 
 
 def f32_bits(v):
-    return int(np.float32(v).view(np.uint32))
+    """Bit pattern of float32(v); every NaN is reported as 0x7FC00000 (x86 produces 0xFFC00000 for
+    0/0, the GPU 0x7FFFFFFF -- the payload carries no meaning and the reference never inspects it)."""
+    v = np.float32(v)
+    return 0x7FC00000 if np.isnan(v) else int(v.view(np.uint32))
 
 
 def tree_signature(node, ref=None):

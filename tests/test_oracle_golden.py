@@ -13,6 +13,12 @@ def sha(b):
     return hashlib.sha256(b).hexdigest()[:16]
 
 
+def bits(v):
+    """float32 bit pattern with NaN canonicalised (see oracle/ref_harness.py:f32_bits)"""
+    v = np.float32(v)
+    return 0x7FC00000 if np.isnan(v) else int(v.view(np.uint32))
+
+
 def test_labels():
     g = load_golden("labels.json")
     assert O.labels() == g["labels"]
@@ -69,7 +75,7 @@ def test_tree_against_reference(i):
     assert sig[:40].tolist() == c["head"]
     assert sha(sig.tobytes()) == c["sha_sig"], c["note"]
     mv, N, W, P, Q = t.root_children()
-    got = [[O.move_str(m), int(n), int(w.view(np.uint32)), int(p.view(np.uint32)), int(q.view(np.uint32))]
+    got = [[O.move_str(m), int(n), bits(w), bits(p), bits(q)]
            for m, n, w, p, q in zip(mv, N, W, P, Q)]
     assert got == c["root"]
 
