@@ -1,0 +1,390 @@
+#!/usr/bin/env python
+"""bench.py -- MCTS node-expansions/sec of batched self-play (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W          our arm (one rank per GPU under torchrun)
+  python bench.py --impl reference ...                    CPU arm: the oracle port of the reference's path
+
+A "step" is one ply of EVERY concurrent game: a full MCTS_tree.main of `--playouts` playouts per game
+(select / encode / network / expand / backup waves), then get_action's host-side move choice and the
+re-root.  Workload = BASELINE.json configs[1]: 1024 concurrent games x 1200 playouts, res_block_nums=7,
+per GPU (weak scaling).  Expansions are counted by the engine (calls of expand), not inferred.
+
+value : expansions / device time of the search waves (CUDA events, state resident in HBM)
+e2e   : expansions / time of the whole SelfPlay.step() loop through the public API, including the
+        per-ply device->host read of root statistics / status and host->device write of the chosen
+        moves, host move sampling and tuple recording.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "mcts_node_expansions_per_sec"
+FLOPS_PER_EVAL = {7: 375.4e6, 19: 1012.4e6}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--games", type=int, default=1024, help="concurrent games per GPU")
+    ap.add_argument("--playouts", type=int, default=1200)
+    ap.add_argument("--res-blocks", type=int, default=7)
+    ap.add_argument("--precision", default=os.environ.get("CCHESS_NN_PRECISION", "tf32"))
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--profile-waves", type=int, default=200, help="waves timed individually for the roofline line")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    samples=len(sm), reasons=sorted(reasons))
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)", d
+    return 6650.0, "fallback (B200_PROFILING.md)", {}
+
+
+def algorithmic_bytes(c0, c1, enc_bytes):
+    """per playout sum_l 12*c_l + 36*L; per expansion 90 + encode + 4C+4 + 14C."""
+    d = {k: c1[k] - c0[k] for k in ("n_expand", "n_playout", "sum_L", "sum_c", "sum_C")}
+    return 12 * d["sum_c"] + 36 * d["sum_L"] + d["n_expand"] * (90 + enc_bytes + 4) + 18 * d["sum_C"], d
+
+
+# ---------------------------------------------------------------------------------------------
+def cpu_reference(n_games, playouts, res_blocks, seconds, threads, warm_waves=1, fixed_waves=None):
+    """The reference's path on the host cores: the C oracle port (oracle/cchess_oracle.c) drives
+    n_games trees in lock-step (one leaf per game per wave, search_threads=1 semantics) and the same
+    network (same seed-0 weights) is evaluated by PyTorch on the CPU with all host threads."""
+    import ctypes as C
+    from cchess_zero_b200.net import PolicyValueNet
+    from oracle import oracle as O
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    net = PolicyValueNet(res_blocks).eval().to(memory_format=torch.channels_last)
+    L = O.lib()
+    trees = [O.Tree() for _ in range(n_games)]
+    arr = (C.c_void_p * n_games)(*[t.h for t in trees])
+    side = np.zeros(n_games, dtype=np.int32)
+    rr = np.zeros(n_games, dtype=np.int32)
+    nn_in = np.zeros((n_games, 9, 10, 14), dtype=np.float32)
+    pending = np.zeros(n_games, dtype=np.uint8)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+
+    def wave():
+        L.co_batch_select(arr, p(side), p(rr), n_games, playouts, p(nn_in), p(pending), threads)
+        with torch.no_grad():
+            lo, v = net(torch.from_numpy(nn_in))
+        lo = np.ascontiguousarray(lo.numpy(), dtype=np.float32)
+        v = np.ascontiguousarray(v.numpy().reshape(-1), dtype=np.float32)
+        L.co_batch_finish(arr, n_games, p(lo), p(v), p(pending), threads)
+
+    def expansions():
+        return sum(t.stats()["n_expand"] for t in trees)
+
+    for _ in range(warm_waves):
+        wave()
+    e0, t0, n = expansions(), time.perf_counter(), 0
+    while True:
+        wave(); n += 1
+        if fixed_waves is not None:
+            if n >= fixed_waves:
+                break
+        elif time.perf_counter() - t0 >= seconds:
+            break
+    dt = time.perf_counter() - t0
+    ex = expansions() - e0
+    return dict(value=ex / dt, seconds=dt, waves=n, expansions=ex)
+
+
+def run_reference(a, rank, world):
+    """--impl reference: rank 0 times the CPU arm, other ranks exit 0."""
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    waves_per_step = max(1, int(os.environ.get("CCHESS_REF_WAVES_PER_STEP", "4")))
+    r = None
+    t_steps = []
+    # one persistent set of trees: warm-up steps then timed steps, each step = waves_per_step waves
+    import ctypes as C
+    from cchess_zero_b200.net import PolicyValueNet
+    from oracle import oracle as O
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    net = PolicyValueNet(a.res_blocks).eval().to(memory_format=torch.channels_last)
+    L = O.lib()
+    B = a.games
+    trees = [O.Tree() for _ in range(B)]
+    arr = (C.c_void_p * B)(*[t.h for t in trees])
+    side = np.zeros(B, dtype=np.int32); rr = np.zeros(B, dtype=np.int32)
+    nn_in = np.zeros((B, 9, 10, 14), dtype=np.float32); pending = np.zeros(B, dtype=np.uint8)
+    p = lambda x: x.ctypes.data_as(C.c_void_p)  # noqa: E731
+
+    def wave():
+        L.co_batch_select(arr, p(side), p(rr), B, a.playouts, p(nn_in), p(pending), threads)
+        with torch.no_grad():
+            lo, v = net(torch.from_numpy(nn_in))
+        lo = np.ascontiguousarray(lo.numpy(), dtype=np.float32)
+        v = np.ascontiguousarray(v.numpy().reshape(-1), dtype=np.float32)
+        L.co_batch_finish(arr, B, p(lo), p(v), p(pending), threads)
+
+    def expansions():
+        return sum(t.stats()["n_expand"] for t in trees)
+
+    for _ in range(a.warmup * waves_per_step):
+        wave()
+    e0, t0 = expansions(), time.perf_counter()
+    for _ in range(a.steps * waves_per_step):
+        wave()
+    dt = time.perf_counter() - t0
+    ex = expansions() - e0
+    v = ex / dt
+    sample = "%d games x %d lock-step waves per step (first waves of the %d-playout search from the start position), oracle C port + torch CPU fp32 net" % (
+        B, waves_per_step, a.playouts)
+    line = dict(metric=METRIC, value=v, unit="expansions/s", n_gpus=a.gpus, steps=a.steps, warmup=a.warmup,
+                ms_per_step=dt / a.steps * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                data="synthetic", impl="reference",
+                config=dict(workload="%d concurrent self-play games x %d playouts, res_block_nums=%d" % (B, a.playouts, a.res_blocks),
+                            games_per_gpu=B, playouts=a.playouts, res_block_nums=a.res_blocks),
+                cpu_baseline=dict(value=v, unit="expansions/s", cores=threads, kind="port", sample=sample),
+                e2e=dict(value=v, unit="expansions/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+def run_ours(a, rank, world, local_rank):
+    from cchess_zero_b200.net import policy_value_network
+    from cchess_zero_b200.selfplay import SelfPlay
+    import torch.distributed as dist
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    B = a.games
+    pv = policy_value_network(a.res_blocks, precision=a.precision, device=local_rank, seed=0)
+    plan = pv.plan()
+    sp = SelfPlay(B, None, a.playouts, seeds=[rank * B + g for g in range(B)], nn_dtype=plan.dtype, device=local_rank,
+                  auto_reset=True, keep_records=True)
+    sp.forward = lambda x: plan(x, sp.logits, sp.value)
+    if not a.no_graph:
+        sp.capture_graph()
+    e = sp.engine
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    search_ms = []
+    orig_search = sp.search
+
+    def timed_search():
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        w = orig_search()
+        e1.record()
+        search_ms.append((e0, e1))
+        return w
+    sp.search = timed_search
+
+    gathered = 0
+    for _ in range(a.warmup):
+        sp.step()
+    barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    search_ms.clear()
+    c0 = e.counters()
+    l0 = e.launches
+    waves0, fin0 = sp.waves, len(sp.finished)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0 = time.perf_counter()
+    ev0.record()
+    for _ in range(a.steps):
+        out = sp.step()
+        if world > 1:
+            gathered += gather_tuples(out["finished"], dev, world)
+    ev1.record()
+    barrier()
+    wall = time.perf_counter() - t0
+    clk = clocks.stop() if rank == 0 else None
+    c1 = e.raise_on_error()
+    e2e_ms = ev0.elapsed_time(ev1)
+    dev_ms = sum(x.elapsed_time(y) for x, y in search_ms)
+    n_exp = c1["n_expand"] - c0["n_expand"]
+    launches = e.launches - l0
+    # max time over ranks, sum of expansions
+    t = torch.tensor([dev_ms, e2e_ms, wall * 1e3], dtype=torch.float64, device=dev)
+    n = torch.tensor([n_exp, launches, len(sp.finished) - fin0, sum(len(r) for _, r in sp.finished[fin0:])], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(n, op=dist.ReduceOp.SUM)
+    dev_ms, e2e_ms, wall_ms = [float(x) for x in t]
+    tot_exp, tot_launch, games_done, tuples_done = [float(x) for x in n]
+
+    # ---- roofline of the dominant kernel of OUR code (k_wave), timed live per launch ----
+    roof = None
+    cpu = None
+    if rank == 0:
+        hbm, peak_src, _ = measured_peaks()
+        enc_bytes = 1260 * (4 if plan.dtype == torch.float32 else 2)
+        sp.search = orig_search
+        e.begin_search(a.playouts)
+        k0 = e.counters()
+        evs = []
+        for _ in range(a.profile_waves):
+            x, y = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            x.record(); e.wave(sp.nn_in, sp.logits, sp.value); y.record()
+            evs.append((x, y))
+            sp.forward(sp.nn_in)
+        torch.cuda.synchronize()
+        k1 = e.counters()
+        kms = [x.elapsed_time(y) for x, y in evs]
+        ab, d = algorithmic_bytes(k0, k1, enc_bytes)
+        per_launch = ab / len(kms)
+        avg_ms = float(np.mean(kms))
+        achieved = per_launch / (avg_ms * 1e-3) / 1e9
+        roof = dict(kernel="k_wave (expand+backup+select+encode, one warp per game)", bound="hbm", achieved=achieved, peak=hbm, unit="GB/s",
+                    frac=achieved / hbm, traffic=None, peak_source=peak_src, avg_launch_ms=avg_ms, algorithmic_bytes_per_launch=per_launch,
+                    bytes_per_expansion=ab / max(1, d["n_expand"]), launches_timed=len(kms),
+                    note="latency-bound pointer-chasing kernel: HBM fraction is reported as required, the binding limits are per-warp dependent loads and the network")
+        if not a.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            r = cpu_reference(min(B, 256), a.playouts, a.res_blocks, a.cpu_seconds, threads)
+            cpu = dict(value=r["value"], unit="expansions/s", cores=threads, kind="port",
+                       sample="%d games x %d lock-step waves (%.1f s) from the start position, oracle C port + torch CPU fp32 net, %d threads" % (
+                           min(B, 256), r["waves"], r["seconds"], threads))
+
+    if rank == 0:
+        value = tot_exp / (dev_ms * 1e-3)
+        e2e_v = tot_exp / (e2e_ms * 1e-3)
+        plies_per_game = tuples_done / games_done if games_done else None
+        games_per_hour = (world * B * a.steps / (e2e_ms * 1e-3) * 3600.0 / plies_per_game) if plies_per_game else None
+        h2d = B * 4 + B          # chosen child indices + search mask
+        d2h = B * 4 + B * 128 * (2 + 4 + 4 + 4 + 4) + B * (1 + 1 + 4 + 4 + 1 + 90) + 4 * (sp.waves - waves0) // max(1, a.steps) // max(1, a.playouts)
+        line = dict(metric=METRIC, value=value, unit="expansions/s", n_gpus=world, steps=a.steps, warmup=a.warmup,
+                    ms_per_step=e2e_ms / a.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                    dtype=a.precision, data="synthetic (seed-0 xavier-initialised network, all games from the start position)",
+                    config=dict(workload="%d concurrent self-play games x %d playouts per move, res_block_nums=%d, per GPU" % (B, a.playouts, a.res_blocks),
+                                games_per_gpu=B, playouts=a.playouts, res_block_nums=a.res_blocks, search_threads=1, exploration=True,
+                                cuda_graph=not a.no_graph, fused_conv_epilogue=plan.fused,
+                                l2_policy="working set (trees %.1f GB + activations) exceeds the 126 MB L2" % (c1["max_arena_words"] * 4 * B / 1e9)),
+                    e2e=dict(value=e2e_v, unit="expansions/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, wall_ms=wall_ms),
+                    gpu_launches=int(tot_launch), clocks=clk, roofline=roof, cpu_baseline=cpu,
+                    extra=dict(expansions=tot_exp, waves_per_step=(sp.waves - waves0) / a.steps, games_finished=games_done,
+                               plies_per_finished_game=plies_per_game, games_per_hour=games_per_hour, tuples_all_gathered=gathered,
+                               nn_tflops=tot_exp * FLOPS_PER_EVAL.get(a.res_blocks, 0) / (dev_ms * 1e-3) / 1e12 / world,
+                               max_arena_words=c1["max_arena_words"], max_depth=c1["max_depth"],
+                               mean_L=(c1["sum_L"] - c0["sum_L"]) / max(1, c1["n_playout"] - c0["n_playout"]),
+                               mean_children=(c1["sum_C"] - c0["sum_C"]) / max(1, n_exp)))
+        print(json.dumps(line), flush=True)
+
+
+def gather_tuples(finished, dev, world, cap=2048):
+    """NCCL all_gather of the (s, pi, z) tuples of the games that ended this step (the only collective
+    on the path: games are independent).  Fixed-size records: 90 B board-string squares are
+    re-encodable from the canonical state, so a record is state (100 B text) + 128 x (int16 label, f64 prob) + z."""
+    import torch.distributed as dist
+    rec = np.zeros((cap, 100 + 4 + 128 * 2 + 128 * 8 + 8), dtype=np.uint8)
+    k = 0
+    for _, r in finished:
+        for s, ix, pv, z in zip(r.states, r.pi_idx, r.pi_val, r.z):
+            if k >= cap:
+                break
+            row = rec[k]
+            sb = s.encode()
+            row[: len(sb)] = np.frombuffer(sb, dtype=np.uint8)
+            row[100:104] = np.frombuffer(np.int32(len(ix)).tobytes(), dtype=np.uint8)
+            row[104:104 + 2 * len(ix)] = np.frombuffer(ix.astype(np.int16).tobytes(), dtype=np.uint8)
+            row[360:360 + 8 * len(pv)] = np.frombuffer(pv.astype(np.float64).tobytes(), dtype=np.uint8)
+            row[1384:1392] = np.frombuffer(np.float64(z).tobytes(), dtype=np.uint8)
+            k += 1
+    mine = torch.from_numpy(rec).to(dev)
+    cnt = torch.tensor([k], dtype=torch.int32, device=dev)
+    allr = torch.empty((world,) + tuple(mine.shape), dtype=torch.uint8, device=dev)
+    allc = torch.empty((world,), dtype=torch.int32, device=dev)
+    dist.all_gather_into_tensor(allr, mine)
+    dist.all_gather_into_tensor(allc, cnt)
+    return int(allc.sum().item())
+
+
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if a.impl == "reference":
+        run_reference(a, rank, world)
+        return
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    run_ours(a, rank, world, local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

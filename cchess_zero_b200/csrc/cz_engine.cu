@@ -104,7 +104,7 @@ struct Dev {
     uint32_t *arena;
     uint8_t *cur;
     uint32_t *alloc, *max_alloc;
-    unsigned long long *cnt_expand, *cnt_playout, *cnt_L, *cnt_c;
+    unsigned long long *cnt_expand, *cnt_playout, *cnt_L, *cnt_c, *cnt_C;
     uint32_t *err;
     int32_t *max_depth;
     uint8_t *terminal;
@@ -207,6 +207,7 @@ __device__ bool warp_expand(const Dev &E, int g, uint32_t *ar, WarpSmem &S, cons
             ar[pe.x + 4 * pe.y] = base;
         }
         E.cnt_expand[g] += 1;
+        E.cnt_C[g] += (unsigned)n;
     }
     __syncwarp();
     return true;
@@ -750,7 +751,7 @@ int cz_engine_create(int n_games, int64_t arena_words, int device, cz_engine **o
     AL(d.root_board, B * 96); AL(d.side, B); AL(d.rr, B); AL(d.ply, B); AL(d.root_N, B); AL(d.root_cnt, B);
     AL(d.root_base, B); AL(d.done, B); AL(d.target, B); AL(d.pending, B); AL(d.active, B); AL(d.path_len, B);
     AL(d.path, B * MAXD); AL(d.leaf_board, B * 96); AL(d.cur, B); AL(d.alloc, B); AL(d.max_alloc, B);
-    AL(d.cnt_expand, B); AL(d.cnt_playout, B); AL(d.cnt_L, B); AL(d.cnt_c, B); AL(d.err, B); AL(d.max_depth, B);
+    AL(d.cnt_expand, B); AL(d.cnt_playout, B); AL(d.cnt_L, B); AL(d.cnt_c, B); AL(d.cnt_C, B); AL(d.err, B); AL(d.max_depth, B);
     AL(d.terminal, B); AL(d.winner, B);
     AL(d.st_n, B); AL(d.st_visits, B * CZ_MAXCHILD); AL(d.st_choice, B); AL(d.st_moves, B * CZ_MAXCHILD);
     AL(d.st_w, B * CZ_MAXCHILD); AL(d.st_p, B * CZ_MAXCHILD); AL(d.st_q, B * CZ_MAXCHILD); AL(d.st_count, 8);
@@ -935,17 +936,18 @@ int cz_engine_counters(cz_engine *e, void *stream, int64_t *out) {
     const size_t B = (size_t)e->d.B;
     CUDA_TRY(cudaSetDevice(e->device));
     CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
-    std::vector<unsigned long long> a(B), b(B), c(B), d(B);
+    std::vector<unsigned long long> a(B), b(B), c(B), d(B), cc(B);
     std::vector<uint32_t> er(B), ma(B);
     std::vector<int32_t> md(B);
     CUDA_TRY(cudaMemcpy(a.data(), e->d.cnt_expand, B * 8, cudaMemcpyDeviceToHost));
     CUDA_TRY(cudaMemcpy(b.data(), e->d.cnt_playout, B * 8, cudaMemcpyDeviceToHost));
     CUDA_TRY(cudaMemcpy(c.data(), e->d.cnt_L, B * 8, cudaMemcpyDeviceToHost));
     CUDA_TRY(cudaMemcpy(d.data(), e->d.cnt_c, B * 8, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(cc.data(), e->d.cnt_C, B * 8, cudaMemcpyDeviceToHost));
     CUDA_TRY(cudaMemcpy(er.data(), e->d.err, B * 4, cudaMemcpyDeviceToHost));
     CUDA_TRY(cudaMemcpy(ma.data(), e->d.max_alloc, B * 4, cudaMemcpyDeviceToHost));
     CUDA_TRY(cudaMemcpy(md.data(), e->d.max_depth, B * 4, cudaMemcpyDeviceToHost));
-    for (int i = 0; i < 8; i++) out[i] = 0;
+    for (int i = 0; i < 9; i++) out[i] = 0;
     out[6] = -1;
     for (size_t g = 0; g < B; g++) {
         out[0] += (int64_t)a[g]; out[1] += (int64_t)b[g]; out[2] += (int64_t)c[g]; out[3] += (int64_t)d[g];
@@ -953,6 +955,7 @@ int cz_engine_counters(cz_engine *e, void *stream, int64_t *out) {
         if (ma[g] > out[5]) out[5] = ma[g];
         if (er[g] && out[6] < 0) out[6] = (int64_t)g;
         if (md[g] > out[7]) out[7] = md[g];
+        out[8] += (int64_t)cc[g];
     }
     return CZ_OK;
 }

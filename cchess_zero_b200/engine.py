@@ -30,6 +30,7 @@ class Engine:
         h = C.c_void_p()
         check(lib().cz_engine_create(self.B, int(arena_words), self.device, C.byref(h)), "cz_engine_create")
         self.h = h
+        self.launches = 0   # kernels of csrc/cz_engine.cu launched through this handle
         self._count = torch.zeros(1, dtype=torch.int32, device="cuda:%d" % self.device)
 
     def close(self):
@@ -49,35 +50,43 @@ class Engine:
         b = None if boards is None else np.ascontiguousarray(boards, dtype=np.uint8).reshape(self.B, 90)
         s = None if sides is None else np.ascontiguousarray(sides, dtype=np.uint8)
         r = None if rr is None else np.ascontiguousarray(rr, dtype=np.int32)
+        self.launches += 1
         check(lib().cz_engine_reset(self.h, _stream(), _hp(m), _hp(b), _hp(s), _hp(r)), "cz_engine_reset")
 
     def set_root_meta(self, sides=None, rr=None, mask=None):
         m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
         s = None if sides is None else np.ascontiguousarray(sides, dtype=np.uint8)
         r = None if rr is None else np.ascontiguousarray(rr, dtype=np.int32)
+        self.launches += 1
         check(lib().cz_engine_set_root_meta(self.h, _stream(), _hp(m), _hp(s), _hp(r)), "cz_engine_set_root_meta")
 
     def begin_search(self, playouts, mask=None):
         m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+        self.launches += 1
         check(lib().cz_engine_begin_search(self.h, _stream(), _hp(m), int(playouts)), "cz_engine_begin_search")
 
     # ---- waves (device tensors) ---------------------------------------------------------
     def wave(self, nn_in, logits, value):
+        self.launches += 1
         check(lib().cz_engine_wave(self.h, _stream(), nn_in.data_ptr(), _DT[nn_in.dtype], logits.data_ptr(), value.data_ptr()),
               "cz_engine_wave")
 
     def select(self, nn_in):
+        self.launches += 1
         check(lib().cz_engine_select(self.h, _stream(), nn_in.data_ptr(), _DT[nn_in.dtype]), "cz_engine_select")
 
     def expand_backup(self, logits, value):
+        self.launches += 1
         check(lib().cz_engine_expand_backup(self.h, _stream(), logits.data_ptr(), value.data_ptr()), "cz_engine_expand_backup")
 
     def unfinished(self):
         out = C.c_int32(0)
+        self.launches += 1
         check(lib().cz_engine_unfinished(self.h, _stream(), C.byref(out)), "cz_engine_unfinished")
         return out.value
 
     def unfinished_async(self):
+        self.launches += 1
         check(lib().cz_engine_unfinished_async(self.h, _stream(), self._count.data_ptr()), "cz_engine_unfinished_async")
         return self._count
 
@@ -90,6 +99,7 @@ class Engine:
         w = np.zeros((B, MAXCHILD), dtype=np.float32) if want_wpq else None
         p = np.zeros((B, MAXCHILD), dtype=np.float32) if want_wpq else None
         q = np.zeros((B, MAXCHILD), dtype=np.float32) if want_wpq else None
+        self.launches += 1
         check(lib().cz_engine_root_children(self.h, _stream(), _hp(n), _hp(mv), _hp(vis), _hp(w), _hp(p), _hp(q)),
               "cz_engine_root_children")
         return dict(n=n, moves=mv, visits=vis, w=w, p=p, q=q)
@@ -97,6 +107,7 @@ class Engine:
     def play(self, child_index):
         ci = np.ascontiguousarray(child_index, dtype=np.int32)
         assert ci.shape == (self.B,)
+        self.launches += 1
         check(lib().cz_engine_play(self.h, _stream(), _hp(ci)), "cz_engine_play")
 
     def status(self, boards=True):
@@ -111,10 +122,10 @@ class Engine:
         return dict(terminal=t, winner=w, ply=ply, rr=rr, side=side, boards=bd)
 
     def counters(self):
-        out = np.zeros(8, dtype=np.int64)
+        out = np.zeros(9, dtype=np.int64)
         check(lib().cz_engine_counters(self.h, _stream(), _hp(out)), "cz_engine_counters")
         return dict(n_expand=int(out[0]), n_playout=int(out[1]), sum_L=int(out[2]), sum_c=int(out[3]), error=int(out[4]),
-                    max_arena_words=int(out[5]), first_error_game=int(out[6]), max_depth=int(out[7]))
+                    max_arena_words=int(out[5]), first_error_game=int(out[6]), max_depth=int(out[7]), sum_C=int(out[8]))
 
     def raise_on_error(self):
         c = self.counters()

@@ -119,6 +119,7 @@ class SelfPlay:
         while True:
             if self.graph is not None:
                 self.graph.replay()
+                e.launches += 1          # the captured k_wave launch
             else:
                 e.wave(self.nn_in, self.logits, self.value)
             waves += 1

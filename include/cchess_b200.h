@@ -139,8 +139,9 @@ int cz_engine_status(cz_engine *e, void *stream, uint8_t *terminal, int8_t *winn
 
 /* Counters since creation, summed over games: out[0] expansions (calls of expand), out[1] playouts,
  * out[2] sum of path lengths L, out[3] sum of scanned children c_l, out[4] OR of per-game error flags,
- * out[5] max arena words in use, out[6] index of first game with an error (or -1), out[7] max path length. */
-int cz_engine_counters(cz_engine *e, void *stream, int64_t *out /* [8] */);
+ * out[5] max arena words in use, out[6] index of first game with an error (or -1), out[7] max path length,
+ * out[8] sum over expansions of the number of children C. */
+int cz_engine_counters(cz_engine *e, void *stream, int64_t *out /* [9] */);
 
 /* Test hook: flat DFS signature of game g's tree, records of 6 int64
  * (label index, N, W bits, P bits, Q bits, n_children), children in order. Returns record count via *n. */
