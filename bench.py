@@ -41,7 +41,7 @@ def parse():
     ap.add_argument("--games", type=int, default=1024, help="concurrent games per GPU")
     ap.add_argument("--playouts", type=int, default=1200)
     ap.add_argument("--res-blocks", type=int, default=7)
-    ap.add_argument("--precision", default=os.environ.get("CCHESS_NN_PRECISION", "tf32"))
+    ap.add_argument("--precision", default=os.environ.get("CCHESS_NN_PRECISION", "fp16"))
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
@@ -340,31 +340,9 @@ def run_ours(a, rank, world, local_rank):
 
 
 def gather_tuples(finished, dev, world, cap=2048):
-    """NCCL all_gather of the (s, pi, z) tuples of the games that ended this step (the only collective
-    on the path: games are independent).  Fixed-size records: 90 B board-string squares are
-    re-encodable from the canonical state, so a record is state (100 B text) + 128 x (int16 label, f64 prob) + z."""
-    import torch.distributed as dist
-    rec = np.zeros((cap, 100 + 4 + 128 * 2 + 128 * 8 + 8), dtype=np.uint8)
-    k = 0
-    for _, r in finished:
-        for s, ix, pv, z in zip(r.states, r.pi_idx, r.pi_val, r.z):
-            if k >= cap:
-                break
-            row = rec[k]
-            sb = s.encode()
-            row[: len(sb)] = np.frombuffer(sb, dtype=np.uint8)
-            row[100:104] = np.frombuffer(np.int32(len(ix)).tobytes(), dtype=np.uint8)
-            row[104:104 + 2 * len(ix)] = np.frombuffer(ix.astype(np.int16).tobytes(), dtype=np.uint8)
-            row[360:360 + 8 * len(pv)] = np.frombuffer(pv.astype(np.float64).tobytes(), dtype=np.uint8)
-            row[1384:1392] = np.frombuffer(np.float64(z).tobytes(), dtype=np.uint8)
-            k += 1
-    mine = torch.from_numpy(rec).to(dev)
-    cnt = torch.tensor([k], dtype=torch.int32, device=dev)
-    allr = torch.empty((world,) + tuple(mine.shape), dtype=torch.uint8, device=dev)
-    allc = torch.empty((world,), dtype=torch.int32, device=dev)
-    dist.all_gather_into_tensor(allr, mine)
-    dist.all_gather_into_tensor(allc, cnt)
-    return int(allc.sum().item())
+    """NCCL all_gather of the (s, pi, z) tuples of the games that ended this step."""
+    from cchess_zero_b200.distributed import all_gather_tuples
+    return len(all_gather_tuples([r for _, r in finished], dev, cap))
 
 
 def main():

@@ -205,7 +205,7 @@ class policy_value_network(object):
         self.momentum = 0.9
         self.global_norm = 100
         self.global_step = 0
-        self.precision = precision or os.environ.get("CCHESS_NN_PRECISION", "fp32")
+        self.precision = precision or os.environ.get("CCHESS_NN_PRECISION", "fp16")
         g = torch.Generator(device="cpu")
         if seed is not None:
             torch.manual_seed(seed)

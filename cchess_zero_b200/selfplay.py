@@ -211,3 +211,261 @@ class SelfPlay:
             n += 1
         self.engine.raise_on_error()
         return sorted(self.finished, key=lambda t: t[0])
+
+
+# =================================================================================================
+# Reference-shaped facade: cchess_main (main.py:1118-1554).  One game at a time through MCTS_tree,
+# exactly the call sequence of the reference, so main.py's train loop runs unchanged on top of it.
+# For throughput use SelfPlay (thousands of games per GPU); `selfplay_many` bridges the two.
+# =================================================================================================
+import os
+import random
+import time
+from collections import defaultdict, deque
+
+
+class cchess_main(object):
+
+    def __init__(self, playout=400, in_batch_size=128, exploration=True, in_search_threads=16, processor="cpu",
+                 num_gpus=1, res_block_nums=7, human_color="b", network=None, log_file=True):
+        from .mcts import MCTS_tree
+        from .net import policy_value_network, policy_value_network_gpus
+        rules._init_tables()
+        self.epochs = 5
+        self.playout_counts = playout
+        self.temperature = 1
+        self.batch_size = in_batch_size
+        self.game_batch = 400
+        self.top_steps = 30
+        self.top_temperature = 1
+        self.eta = 0.03
+        self.learning_rate = 0.001
+        self.lr_multiplier = 1.0
+        self.buffer_size = 10000
+        self.data_buffer = deque(maxlen=self.buffer_size)
+        self.game_borad = rules.GameBoard()
+        if network is not None:
+            self.policy_value_netowrk = network
+        else:  # `processor` selected CPU/GPU TensorFlow in the reference (main.py:1142); both map to the CUDA net here
+            self.policy_value_netowrk = policy_value_network(res_block_nums) if processor == "cpu" else policy_value_network_gpus(num_gpus, res_block_nums)
+        self.search_threads = in_search_threads
+        self.mcts = MCTS_tree(self.game_borad.state, self.policy_value_netowrk.forward, self.search_threads)
+        self.exploration = exploration
+        self.resign_threshold = -0.8
+        self.global_step = 0
+        self.kl_targ = 0.025
+        self.log_file = open(os.path.join(os.getcwd(), "log_file.txt"), "w") if log_file else None
+        self.human_color = human_color
+
+    @staticmethod
+    def flip_policy(prob):  # main.py:1152-1155
+        prob = np.asarray(prob).flatten()
+        return np.asarray([prob[i] for i in rules.unflipped_index])
+
+    # ---- training (main.py:1157-1205) ------------------------------------------------------------
+    def policy_update(self):
+        mini_batch = random.sample(self.data_buffer, self.batch_size)
+        state_batch = [d[0] for d in mini_batch]
+        mcts_probs_batch = [d[1] for d in mini_batch]
+        winner_batch = np.expand_dims([d[2] for d in mini_batch], 1)
+        start_time = time.time()
+        old_probs, old_v = self.mcts.forward(state_batch)
+        kl, loss, accuracy, new_v = 0.0, 0.0, 0.0, old_v
+        for _ in range(self.epochs):
+            accuracy, loss, self.global_step = self.policy_value_netowrk.train_step(
+                state_batch, mcts_probs_batch, winner_batch, self.learning_rate * self.lr_multiplier)
+            new_probs, new_v = self.mcts.forward(state_batch)
+            with np.errstate(all="ignore"):
+                kl_tmp = old_probs * (np.log((old_probs + 1e-10) / (new_probs + 1e-10)))
+            kl = np.mean([np.sum(line[np.isfinite(line)]) for line in kl_tmp])   # rows without nan/inf terms, main.py:1178-1182
+            if kl > self.kl_targ * 4:
+                break
+        self.policy_value_netowrk.save(self.global_step)
+        print("train using time {} s".format(time.time() - start_time))
+        if kl > self.kl_targ * 2 and self.lr_multiplier > 0.1:
+            self.lr_multiplier /= 1.5
+        elif kl < self.kl_targ / 2 and self.lr_multiplier < 10:
+            self.lr_multiplier *= 1.5
+        wb = np.array(winner_batch)
+        explained_var_old = 1 - np.var(wb - old_v.flatten()) / np.var(wb)
+        explained_var_new = 1 - np.var(wb - new_v.flatten()) / np.var(wb)
+        msg = "kl:{:.5f},lr_multiplier:{:.3f},loss:{},accuracy:{},explained_var_old:{:.3f},explained_var_new:{:.3f}".format(
+            kl, self.lr_multiplier, loss, accuracy, explained_var_old, explained_var_new)
+        print(msg)
+        if self.log_file:
+            self.log_file.write(msg + "\n")
+            self.log_file.flush()
+
+    def run(self, max_batches=None):  # main.py:1224-1248
+        batch_iter = 0
+        try:
+            while max_batches is None or batch_iter < max_batches:
+                batch_iter += 1
+                play_data, episode_len = self.selfplay()
+                print("batch i:{}, episode_len:{}".format(batch_iter, episode_len))
+                extend_data = []
+                for state, mcts_prob, winner in play_data:
+                    extend_data.append((self.mcts.state_to_positions(state), mcts_prob, winner))
+                self.data_buffer.extend(extend_data)
+                if len(self.data_buffer) > self.batch_size:
+                    self.policy_update()
+        except KeyboardInterrupt:
+            if self.log_file:
+                self.log_file.close()
+            self.policy_value_netowrk.save(self.global_step)
+
+    # ---- move choice (main.py:1278-1358) -----------------------------------------------------------
+    def _visit_probs(self):
+        actions_visits = [(act, nod.N) for act, nod in self.mcts.root.child.items()]
+        actions, visits = zip(*actions_visits)
+        with np.errstate(divide="ignore"):
+            probs = rules.softmax(1.0 / self.temperature * np.log(visits))
+        return actions, probs
+
+    def get_hint(self, mcts_or_net, reverse, disp_mcts_msg_handler):
+        act_prob_dict = defaultdict(float)
+        if mcts_or_net == "mcts":
+            if self.mcts.root.child == {}:
+                disp_mcts_msg_handler()
+                self.mcts.main(self.game_borad.state, self.game_borad.current_player, self.game_borad.restrict_round, self.playout_counts)
+            actions, probs = self._visit_probs()
+            for i in range(len(actions)):
+                action = "".join(rules.flipped_uci_labels(actions[i])) if self.human_color == "w" else actions[i]
+                act_prob_dict[action] = probs[i]
+        elif mcts_or_net == "net":
+            moves, p, _ = self._net_priors()
+            for action, mov_p in zip(moves, p):
+                if self.human_color == "w":
+                    action = "".join(rules.flipped_uci_labels(action))
+                act_prob_dict[action] = mov_p
+        return sorted(act_prob_dict.items(), key=lambda item: item[1], reverse=reverse)
+
+    def _net_priors(self):
+        """The 'net' branches of get_hint / select_move (main.py:1300-1324, 1437-1459)."""
+        positions = self.mcts.generate_inputs(self.game_borad.state, self.game_borad.current_player)
+        action_probs, value = self.mcts.forward(np.expand_dims(positions, 0))
+        if self.mcts.is_black_turn(self.game_borad.current_player):
+            action_probs = cchess_main.flip_policy(action_probs)
+        moves = rules.GameBoard.get_legal_moves(self.game_borad.state, self.game_borad.current_player)
+        action_probs = np.asarray(action_probs).flatten()
+        tot_p = 1e-8
+        p = []
+        for action in moves:
+            mov_p = action_probs[rules.label2i[action]]
+            p.append(mov_p)
+            tot_p += mov_p
+        return moves, [x / tot_p for x in p], value
+
+    def get_action(self, state, temperature=1e-3):
+        self.mcts.main(state, self.game_borad.current_player, self.game_borad.restrict_round, self.playout_counts)
+        actions_visits = [(act, nod.N) for act, nod in self.mcts.root.child.items()]
+        actions, visits = zip(*actions_visits)
+        with np.errstate(divide="ignore"):
+            probs = rules.softmax(1.0 / temperature * np.log(visits))
+        move_probs = [[actions, probs]]
+        if self.exploration:
+            act = np.random.choice(actions, p=0.75 * probs + 0.25 * np.random.dirichlet(0.3 * np.ones(len(probs))))
+        else:
+            act = np.random.choice(actions, p=probs)
+        win_rate = self.mcts.Q(act)
+        self.mcts.update_tree(act)
+        return act, move_probs, win_rate
+
+    # ---- game flow (main.py:1380-1554) -------------------------------------------------------------
+    def check_end(self):
+        st = self.game_borad.state
+        if st.find("K") == -1 or st.find("k") == -1:
+            if st.find("K") == -1:
+                print("Green is Winner")
+                return True, "b"
+            print("Red is Winner")
+            return True, "w"
+        elif self.game_borad.restrict_round >= 60:
+            print("TIE! No Winners!")
+            return True, "t"
+        return False, ""
+
+    def _advance(self, action):
+        """state / round / player / restrict_round bookkeeping shared by human_move, select_move, selfplay."""
+        last_state = self.game_borad.state
+        self.game_borad.state = rules.GameBoard.sim_do_action(action, self.game_borad.state)
+        self.game_borad.round += 1
+        self.game_borad.current_player = "w" if self.game_borad.current_player == "b" else "b"
+        if rules.is_kill_move(last_state, self.game_borad.state) == 0:
+            self.game_borad.restrict_round += 1
+        else:
+            self.game_borad.restrict_round = 0
+
+    def human_move(self, coord, mcts_or_net):
+        win_rate = 0
+        action = "abcdefghi"[coord[0]] + str(coord[1]) + "abcdefghi"[coord[2]] + str(coord[3])
+        if self.human_color == "w":
+            action = "".join(rules.flipped_uci_labels(action))
+        if mcts_or_net == "mcts":
+            if self.mcts.root.child == {}:
+                self.mcts.main(self.game_borad.state, self.game_borad.current_player, self.game_borad.restrict_round, self.playout_counts)
+            win_rate = self.mcts.Q(action)
+            self.mcts.update_tree(action)
+        self._advance(action)
+        return win_rate
+
+    def select_move(self, mcts_or_net):
+        if mcts_or_net == "mcts":
+            action, probs, win_rate = self.get_action(self.game_borad.state, self.temperature)
+        else:
+            moves, p, value = self._net_priors()
+            win_rate = value[0, 0]
+            action = max(zip(moves, p), key=lambda t: t[1])[0]   # first maximum wins, main.py:1461
+        print("Win rate for player {} is {:.4f}".format(self.game_borad.current_player, win_rate))
+        print(self.game_borad.current_player, " now take a action : ", action, "[Step {}]".format(self.game_borad.round))
+        self._advance(action)
+        self.game_borad.print_borad(self.game_borad.state)
+        if self.human_color == "w":
+            action = "".join(rules.flipped_uci_labels(action))
+        sx, sy, dx, dy = ord(action[0]) - 97, int(action[1]), ord(action[2]) - 97, int(action[3])
+        return (sx, sy, dx - sx, dy - sy), win_rate
+
+    def selfplay(self):
+        self.game_borad.reload()
+        states, mcts_probs, current_players = [], [], []
+        z = None
+        game_over = False
+        start_time = time.time()
+        while not game_over:
+            action, probs, win_rate = self.get_action(self.game_borad.state, self.temperature)
+            black = self.mcts.is_black_turn(self.game_borad.current_player)
+            state, _ = self.mcts.try_flip(self.game_borad.state, self.game_borad.current_player, black)
+            states.append(state)
+            prob = np.zeros(rules.labels_len)
+            for a, pr in zip(probs[0][0], probs[0][1]):
+                prob[rules.label2i["".join(rules.flipped_uci_labels(a)) if black else a]] = pr
+            mcts_probs.append(prob)
+            current_players.append(self.game_borad.current_player)
+            self._advance(action)
+            st = self.game_borad.state
+            if st.find("K") == -1 or st.find("k") == -1:
+                winnner = "b" if st.find("K") == -1 else "w"
+                z = np.zeros(len(current_players))
+                z[np.array(current_players) == winnner] = 1.0
+                z[np.array(current_players) != winnner] = -1.0
+                game_over = True
+                print("Game end. Winner is player : ", winnner, " In {} steps".format(self.game_borad.round - 1))
+            elif self.game_borad.restrict_round >= 60:
+                z = np.zeros(len(current_players))
+                game_over = True
+                print("Game end. Tie in {} steps".format(self.game_borad.round - 1))
+            if game_over:
+                self.mcts.reload()
+        print("Using time {} s".format(time.time() - start_time))
+        return zip(states, mcts_probs, z), len(z)
+
+    # ---- batched bridge: many games at once on this rank's GPU ---------------------------------------
+    def selfplay_many(self, n_games, seeds=None, arena_words=0):
+        """Plays n_games concurrent games with the engine's lock-step waves and returns a list of
+        (zip(states, mcts_probs, z), n) -- the same tuples selfplay() yields, one entry per game."""
+        net = self.policy_value_netowrk
+        plan = net.plan()
+        sp = SelfPlay(n_games, None, self.playout_counts, seeds=seeds, exploration=self.exploration, temperature=self.temperature,
+                      nn_dtype=plan.dtype, arena_words=arena_words, auto_reset=False)
+        sp.forward = lambda x: plan(x, sp.logits, sp.value)
+        return [(rec.tuples(), len(rec)) for _, rec in sp.play_games()]

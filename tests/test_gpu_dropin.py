@@ -1,0 +1,140 @@
+"""GPU tests of the reference-shaped surface: policy_value_network (forward / train_step / save / restore),
+MCTS_tree and cchess_main drop-ins against the reference's golden vectors, and the real-network self-play path."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def sha(b):
+    return hashlib.sha256(b).hexdigest()[:16]
+
+
+def _positions(n, seed=0):
+    from oracle import oracle as O
+    rng = np.random.RandomState(seed)
+    xs, b, side = [], O.from_state(O.START), 0
+    while len(xs) < n:
+        xs.append(O.encode(b, side))
+        mv = O.legal_moves(b, side)
+        b, cap = O.apply_move(b, mv[rng.randint(len(mv))]); side ^= 1
+        if cap in (1, 8):
+            b, side = O.from_state(O.START), 0
+    return np.stack(xs)
+
+
+@pytest.mark.parametrize("blocks", [7, 19])
+def test_network_within_1e3_of_fp64(blocks):
+    """north_star: NN outputs match within 1e-3 of an fp32/fp64 evaluation.  Tolerance 1e-3 absolute on
+    logits and value; bf16 is measured too and is expected to miss it (that is why it is not the default)."""
+    from cchess_zero_b200.net import InferencePlan, PolicyValueNet
+    torch.manual_seed(0)
+    net = PolicyValueNet(blocks).eval()
+    x = torch.from_numpy(_positions(96))
+    with torch.no_grad():
+        rl, rv = net.double()(x.double())
+    net = net.float().cuda().to(memory_format=torch.channels_last)
+    err = {}
+    for prec in ("fp32", "tf32", "fp16", "bf16"):
+        plan = InferencePlan(net, prec)
+        l, v = plan(x.cuda().to(plan.dtype))
+        err[prec] = max((l.double().cpu() - rl).abs().max().item(), (v.double().cpu().reshape(-1) - rv.reshape(-1)).abs().max().item())
+    print("max abs error vs fp64:", err)
+    assert err["fp32"] < 1e-5
+    assert err["tf32"] < 1e-3
+    assert err["fp16"] < 1e-3      # the default inference precision
+
+
+def test_policy_value_network_surface(tmp_path, monkeypatch):
+    monkeypatch.chdir(tmp_path)
+    from cchess_zero_b200.net import policy_value_network
+    pv = policy_value_network(res_block_nums=2)
+    x = _positions(12)
+    lo, v = pv.forward(list(x))                      # the reference passes python lists (main.py:1170)
+    assert lo.shape == (12, 2086) and lo.dtype == np.float32 and v.shape == (12, 1) and v.dtype == np.float32
+    assert np.all(np.abs(v) <= 1)
+    lo1, v1 = pv.forward(x[:1])
+    assert np.allclose(lo1, lo[:1], atol=2e-3)
+    pi = np.zeros((12, 2086), dtype=np.float32)
+    pi[np.arange(12), np.arange(12) * 7] = 1
+    z = np.where(np.arange(12) % 2 == 0, 1.0, -1.0).reshape(12, 1)
+    losses = []
+    for _ in range(8):
+        acc, loss, step = pv.train_step(x, pi, z, 0.01)
+        losses.append(loss)
+    assert step == 8 and np.isfinite(losses).all() and losses[-1] < losses[0]
+    lo2, v2 = pv.forward(x)
+    path = pv.save(step)
+    assert os.path.exists(path)
+    pv2 = policy_value_network(res_block_nums=2)     # train_restore picks the checkpoint up (policy_value_network.py:164-174)
+    assert pv2.global_step == 8
+    lo3, v3 = pv2.forward(x)
+    assert np.array_equal(lo2, lo3) and np.array_equal(v2, v3)
+
+
+def test_mcts_tree_dropin_against_reference_vectors():
+    from cchess_zero_b200.mcts import MCTS_tree
+    from oracle.fakenets_np import FAKE_NETS
+    for c in load_golden("tree.json")["cases"]:
+        if c["playouts"] > 300:
+            continue
+        t = MCTS_tree(c["state"], FAKE_NETS[c["net"]], 16)
+        t._set_position(c["state"], c["player"], c["rr"])
+        t.main(c["state"], c["player"], c["rr"], c["playouts"])
+        got = [[a, n.N] for a, n in t.root.child.items()]
+        assert got == [[r[0], r[1]] for r in c["root"]], c["note"]
+        for (a, n), r in zip(t.root.child.items(), c["root"]):
+            q = np.float32(n.Q)
+            assert (0x7FC00000 if np.isnan(q) else int(q.view(np.uint32))) == r[4]
+        assert t.Q(c["root"][0][0]) == t.root.child[c["root"][0][0]].Q
+
+
+def test_cchess_main_selfplay_dropin_against_reference_vectors(tmp_path, monkeypatch):
+    monkeypatch.chdir(tmp_path)
+    from cchess_zero_b200.selfplay import cchess_main
+    from oracle.fakenets_np import FAKE_NETS
+
+    class Net:
+        def __init__(self, f):
+            self.forward = f
+
+    for g in load_golden("selfplay.json")["games"][:2]:
+        m = cchess_main(playout=g["playouts"], in_search_threads=16, network=Net(FAKE_NETS[g["net"]]), log_file=False)
+        np.random.seed(g["seed"])
+        import contextlib, io
+        with contextlib.redirect_stdout(io.StringIO()):
+            data, n = m.selfplay()
+        data = list(data)
+        assert n == g["n"]
+        assert [d[0] for d in data] == g["states"]
+        assert [float(d[2]) for d in data] == g["z"]
+        assert sha(np.asarray([d[1] for d in data], dtype=np.float64).tobytes()) == g["sha_pi"]
+        ended, who = m.check_end()
+        assert ended and who in ("w", "b", "t")
+
+
+@pytest.mark.parametrize("precision,graph", [("fp16", True), ("tf32", False)])
+def test_selfplay_with_real_network(precision, graph, tmp_path, monkeypatch):
+    monkeypatch.chdir(tmp_path)
+    from cchess_zero_b200.net import policy_value_network
+    from cchess_zero_b200.selfplay import SelfPlay
+    pv = policy_value_network(res_block_nums=2, precision=precision)
+    plan = pv.plan()
+    B, P = 64, 24
+    sp = SelfPlay(B, None, P, seeds=range(B), nn_dtype=plan.dtype, arena_words=1 << 18)
+    sp.forward = lambda x: plan(x, sp.logits, sp.value)
+    if graph:
+        sp.capture_graph()
+    for _ in range(6):
+        sp.step()
+    c = sp.engine.raise_on_error()
+    assert c["n_playout"] == 6 * B * P
+    assert 0 < c["n_expand"] <= c["n_playout"] + 6 * B
+    st = sp.engine.status()
+    assert (st["ply"] <= 6).all() and st["ply"].max() == 6

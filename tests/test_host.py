@@ -1,0 +1,141 @@
+"""CPU-only tests: the C-ABI library loads and exports every declared symbol, the host-only entry points
+work without a GPU, compute entry points fail loudly without one, and the host-side logic (tuple packing,
+flip helpers, multi-rank gather over gloo) is correct."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_abi_exports_every_declared_symbol():
+    from cchess_zero_b200 import _lib
+    L = _lib.lib()
+    hdr = open(os.path.join(ROOT, "include", "cchess_b200.h")).read()
+    names = sorted(set(re.findall(r"\b(cz_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(L, n), "missing symbol %s" % n
+    assert L.cz_version() >= 1
+
+
+def test_host_only_entry_points_match_oracle():
+    from cchess_zero_b200 import rules
+    from oracle import oracle as O
+    rules._init_tables()
+    assert rules.labels_array == O.labels()
+    assert rules.unflipped_index == O.unflipped_index()
+    assert rules.labels_len == 2086 and rules.label2i["e0e9"] == 916 and rules.i2label[2056] == "c0e2"
+    b = rules.state_to_board(rules.START_STATE)
+    assert np.array_equal(b, O.from_state(O.START))
+    assert rules.board_to_state(b) == rules.START_STATE
+    with pytest.raises(Exception):
+        rules.state_to_board("9/9/9")
+    assert rules.flipped_uci_labels(["a0b9"]) == ["a9b0"]
+    assert rules.is_kill_move("RNBAKABNR/9", "RNBAKABN1/9") == 1
+    assert rules.GameBoard.board_to_pos_name("4K4/9")[0] == "1111K1111"
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_compute_fails_loudly_without_gpu():
+    from cchess_zero_b200 import rules
+    from cchess_zero_b200._lib import EngineError
+    from cchess_zero_b200.engine import Engine
+    with pytest.raises(EngineError):
+        Engine(4)
+    with pytest.raises(EngineError):
+        rules.GameBoard.get_legal_moves(rules.START_STATE, "w")
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "cchess_zero_b200")
+    for dp, _, fns in os.walk(pkg):
+        for fn in fns:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dp, fn)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), fn
+                assert "liboracle" not in src and "cchess_oracle" not in src, fn
+
+
+def test_flip_helpers_and_record_packing():
+    from cchess_zero_b200 import rules
+    from cchess_zero_b200.distributed import pack_records, unpack_records, shard_seeds
+    from cchess_zero_b200.selfplay import GameRecord, _flip_board, _flip_move_label_index
+    from oracle import oracle as O
+    rules._init_tables()
+    b = O.from_state("R1BAKAB1R/9/1C2C1N2/P1P1P1P1P/2N6/6p2/p1p1p3p/1c2c1n2/9/rnbakab1r")
+    assert np.array_equal(_flip_board(b), O.flip_board(b))
+    for m in ("a0a1", "h9g7", "e9e0"):
+        mv = O.move_from_str(m)
+        assert _flip_move_label_index(mv) == rules.label2i[O.flip_label(m)]
+    with np.errstate(all="ignore"):
+        g = O.selfplay_game("hash_pos", 12, np.random.RandomState(4))
+    rec = GameRecord()
+    rec.states, rec.z = g["states"], g["z"]
+    for p in g["pis"]:
+        ix = np.nonzero(p)[0]
+        rec.pi_idx.append(ix); rec.pi_val.append(p[ix])
+    buf, k, left = pack_records([rec], 4096)
+    assert k == len(g["states"]) and not left
+    back = unpack_records(buf, k)
+    for (s, pi, z), s0, p0, z0 in zip(back, g["states"], g["pis"], g["z"]):
+        assert s == s0 and z == z0 and np.array_equal(pi, p0)
+    _, k2, left2 = pack_records([rec], 5)
+    assert k2 == 5 and len(left2) == len(g["states"]) - 5
+    assert shard_seeds(4, 0) == [0, 1, 2, 3] and shard_seeds(4, 2, 10) == [18, 19, 20, 21]
+
+
+_GLOO = r'''
+import os, sys
+sys.path.insert(0, %r)
+import numpy as np, torch, torch.distributed as dist
+from cchess_zero_b200.distributed import all_gather_tuples
+from cchess_zero_b200.selfplay import GameRecord
+from oracle import oracle as O
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+def game(seed):
+    with np.errstate(all="ignore"):
+        g = O.selfplay_game("hash_pos", 10, np.random.RandomState(seed))
+    r = GameRecord(); r.states, r.z = g["states"], g["z"]
+    for p in g["pis"]:
+        ix = np.nonzero(p)[0]; r.pi_idx.append(ix); r.pi_val.append(p[ix])
+    return g, r
+mine = [game(100 + rank * 2 + i) for i in range(2 if rank == 0 else 1)]     # ragged: rank 0 two games, rank 1 one
+out = all_gather_tuples([r for _, r in mine], torch.device("cpu"), cap=1024)
+exp = []
+for rk in range(world):
+    for i in range(2 if rk == 0 else 1):
+        g, _ = game(100 + rk * 2 + i)
+        exp += list(zip(g["states"], g["pis"], g["z"]))
+assert len(out) == len(exp), (len(out), len(exp))
+for (s, p, z), (s0, p0, z0) in zip(out, exp):
+    assert s == s0 and z == z0 and np.array_equal(p, p0)
+if rank == 0: print("GLOO_OK", len(out))
+dist.destroy_process_group()
+'''
+
+
+def test_all_gather_tuples_world_size_2_gloo(tmp_path):
+    script = tmp_path / "g.py"
+    script.write_text(_GLOO % ROOT)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29517", str(script)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "GLOO_OK" in r.stdout
+
+
+def test_bench_reference_arm_prints_contract_line():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--games", "8", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    import json
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "mcts_node_expansions_per_sec" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
