@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--res-blocks", type=int, default=7)
     ap.add_argument("--precision", default=os.environ.get("CCHESS_NN_PRECISION", "fp16"))
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--library-ends", action="store_true", help="use cuDNN/cuBLAS for the first conv and the heads instead of csrc/cz_net.cu")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--profile-waves", type=int, default=200, help="waves timed individually for the roofline line")
@@ -219,10 +220,9 @@ def run_ours(a, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     B = a.games
     pv = policy_value_network(a.res_blocks, precision=a.precision, device=local_rank, seed=0)
-    plan = pv.plan()
-    sp = SelfPlay(B, None, a.playouts, seeds=[rank * B + g for g in range(B)], nn_dtype=plan.dtype, device=local_rank,
-                  auto_reset=True, keep_records=True)
-    sp.forward = lambda x: plan(x, sp.logits, sp.value)
+    plan = pv.native_plan(B) if (a.precision == "fp16" and not a.library_ends) else pv.plan()
+    sp = SelfPlay(B, None, a.playouts, seeds=[rank * B + g for g in range(B)], device=local_rank,
+                  auto_reset=True, keep_records=True, plan=plan)
     if not a.no_graph:
         sp.capture_graph()
     e = sp.engine
@@ -286,7 +286,7 @@ def run_ours(a, rank, world, local_rank):
     cpu = None
     if rank == 0:
         hbm, peak_src, _ = measured_peaks()
-        enc_bytes = 1260 * (4 if plan.dtype == torch.float32 else 2)
+        enc_bytes = 96 if plan.dtype == torch.uint8 else 1260 * (4 if plan.dtype == torch.float32 else 2)
         sp.search = orig_search
         e.begin_search(a.playouts)
         k0 = e.counters()
@@ -327,6 +327,7 @@ def run_ours(a, rank, world, local_rank):
                     config=dict(workload="%d concurrent self-play games x %d playouts per move, res_block_nums=%d, per GPU" % (B, a.playouts, a.res_blocks),
                                 games_per_gpu=B, playouts=a.playouts, res_block_nums=a.res_blocks, search_threads=1, exploration=True,
                                 cuda_graph=not a.no_graph, fused_conv_epilogue=plan.fused,
+                                network_ends="csrc/cz_net.cu (board-byte first conv, fused heads)" if plan.dtype == torch.uint8 else "library",
                                 l2_policy="working set (trees %.1f GB + activations) exceeds the 126 MB L2" % (c1["max_arena_words"] * 4 * B / 1e9)),
                     e2e=dict(value=e2e_v, unit="expansions/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, wall_ms=wall_ms),
                     gpu_launches=int(tot_launch), clocks=clk, roofline=roof, cpu_baseline=cpu,

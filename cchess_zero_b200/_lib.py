@@ -7,7 +7,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcchess_b200.so")
 
 NSQ, NLABEL, MAXCHILD, ENC_LEN = 90, 2086, 128, 1260
-F32, BF16, F16 = 0, 1, 2
+F32, BF16, F16, BOARD = 0, 1, 2, 3
 ERR_NAMES = {1: "NOMOVES", 2: "NOLABEL", 4: "DEPTH", 8: "ARENA", 16: "CHILDREN"}
 
 _lib = None
@@ -46,6 +46,8 @@ def _sig(L):
     L.cz_engine_status.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
     L.cz_engine_counters.argtypes = [vp, vp, vp]
     L.cz_engine_tree_signature.argtypes = [vp, vp, i32, vp, i64, vp]
+    L.cz_net_first_conv.argtypes = [vp, i32, vp, vp, vp, vp]
+    L.cz_net_heads.argtypes = [vp, i32, vp, vp, vp, vp, vp, C.c_float, vp, vp, vp, vp, vp, vp]
 
 
 def lib():

@@ -219,7 +219,21 @@ __device__ void store_leaf(const Dev &E, int g, WarpSmem &S, int side, T *nn_in,
     __syncwarp();
     uint32_t *lb = reinterpret_cast<uint32_t *>(E.leaf_board + (size_t)g * 96);
     if (lane < 24) lb[lane] = reinterpret_cast<const uint32_t *>(S.board)[lane];
-    cz::warp_encode<T>(S.board, side, nn_in + (size_t)g * CZ_ENC_LEN, lane);
+    if constexpr (sizeof(T) == 1) {
+        // CZ_BOARD: the evaluator reads the side-to-move-canonical board itself (try_flip, main.py:560-574);
+        // cz_net_first_conv applies the reference's cell indexing, so no [9][10][14] tensor is written.
+        uint8_t *o = reinterpret_cast<uint8_t *>(nn_in) + (size_t)g * 96;
+        for (int i = lane; i < 96; i += 32) {
+            int p = 0;
+            if (i < 90) {
+                if (side == 0) p = S.board[i];
+                else { const int yy = i / 9, xx = i - yy * 9; p = cz::swap_colour(S.board[(9 - yy) * 9 + xx]); }
+            }
+            o[i] = (uint8_t)p;
+        }
+    } else {
+        cz::warp_encode<T>(S.board, side, nn_in + (size_t)g * CZ_ENC_LEN, lane);
+    }
 }
 
 // One wave for one game (one warp).  DO_EXPAND: consume the previous evaluation; DO_SELECT: run playouts
@@ -841,6 +855,7 @@ static int launch_wave(cz_engine *e, void *stream, void *nn_in, int dt, const fl
     if (dt == CZ_F32) k_wave<float, X, S><<<gr, bl, 0, st>>>(e->d, (float *)nn_in, logits, value);
     else if (dt == CZ_BF16) k_wave<__nv_bfloat16, X, S><<<gr, bl, 0, st>>>(e->d, (__nv_bfloat16 *)nn_in, logits, value);
     else if (dt == CZ_F16) k_wave<__half, X, S><<<gr, bl, 0, st>>>(e->d, (__half *)nn_in, logits, value);
+    else if (dt == CZ_BOARD) k_wave<uint8_t, X, S><<<gr, bl, 0, st>>>(e->d, (uint8_t *)nn_in, logits, value);
     else return fail(CZ_EINVAL, "wave: nn_dtype");
     CUDA_TRY(cudaGetLastError());
     return CZ_OK;

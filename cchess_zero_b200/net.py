@@ -140,6 +140,9 @@ class InferencePlan:
     def _ctx(self):
         return _Tf32(self.precision == "tf32")
 
+    def make_input(self, B):
+        return torch.zeros((B, 9, 10, 14), dtype=self.dtype, device=self.w_in[0].device)
+
     def _conv_relu(self, x, wb, pad):
         w, b = wb
         if self.fused and pad == 1:
@@ -175,6 +178,67 @@ class InferencePlan:
             value_out.copy_(value.reshape(value_out.shape))
             return None
         return logits, value
+
+
+class NativePlan:
+    """fp16 inference plan whose ends are the hand-written kernels of csrc/cz_net.cu:
+         board bytes --cz_net_first_conv--> [B,90,128] --library tcgen05 convs (residual tower)--> --cz_net_heads--> logits, value
+    Input is the engine's CZ_BOARD output (uint8 [B,96], the side-to-move-canonical board); the one-hot
+    [9,10,14] tensor is never built.  Outputs are written straight into the float32 buffers the engine reads."""
+
+    precision = "fp16"
+    dtype = torch.uint8
+
+    def __init__(self, net, max_batch):
+        import ctypes as C
+        from ._lib import lib
+        self._C, self._lib = C, lib()
+        base = InferencePlan(net, "fp16")
+        self.blocks, self.fused, self._base = base.blocks, base.fused, base
+        dev = base.w_in[0].device
+        with torch.no_grad():
+            w, b = base.w_in                                                    # folded conv_in: [128,14,3,3] fp16
+            self.w1 = w.float().permute(2, 3, 1, 0).reshape(9, 14, 128).to(torch.float16).contiguous()
+            self.b1 = b.float().contiguous()
+            wh, bh = base.w_head                                                 # [3,128,1,1]
+            self.wh = wh.float().reshape(3, 128).contiguous()
+            self.bh = bh.float().contiguous()
+            self.w1t = net.v_fc1.weight.detach().float().t().contiguous()        # [90,256]
+            self.bv1 = net.v_fc1.bias.detach().float().contiguous()
+            self.w2 = net.v_fc2.weight.detach().float().reshape(256).contiguous()
+            self.b2 = float(net.v_fc2.bias.detach().float().item())
+            self.wp = torch.zeros((2112, 192), dtype=torch.float16, device=dev)
+            self.wp[:NLABEL, :180] = net.p_fc.weight.detach().to(torch.float16)
+            self.bp = torch.zeros((2112,), dtype=torch.float32, device=dev)
+            self.bp[:NLABEL] = net.p_fc.bias.detach().float()
+        self.max_batch = max_batch
+        self.x1 = torch.empty((max_batch, 9, 10, 128), dtype=torch.float16, device=dev)
+        self.hp = torch.zeros((max_batch, 192), dtype=torch.float16, device=dev)
+
+    def make_input(self, B):
+        return torch.zeros((B, 96), dtype=torch.uint8, device=self.x1.device)
+
+    @torch.no_grad()
+    def __call__(self, boards, logits_out, value_out):
+        B = boards.shape[0]
+        assert B <= self.max_batch and boards.dtype == torch.uint8 and logits_out.dtype == torch.float32
+        st = self._C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        rc = self._lib.cz_net_first_conv(boards.data_ptr(), B, self.w1.data_ptr(), self.b1.data_ptr(), self.x1.data_ptr(), st)
+        if rc:
+            raise RuntimeError("cz_net_first_conv failed (%d)" % rc)
+        x = self.x1[:B].permute(0, 3, 1, 2)                                     # NCHW view of NHWC memory = channels_last
+        for c1, c2 in self.blocks:
+            y = self._base._conv_relu(x, c1, 1)
+            x = self._base._conv_add_relu(y, c2, x)
+        if not x.is_contiguous(memory_format=torch.channels_last):
+            x = x.contiguous(memory_format=torch.channels_last)
+        rc = self._lib.cz_net_heads(x.data_ptr(), B, self.wh.data_ptr(), self.bh.data_ptr(), self.w1t.data_ptr(), self.bv1.data_ptr(),
+                                    self.w2.data_ptr(), self.b2, self.wp.data_ptr(), self.bp.data_ptr(), self.hp.data_ptr(),
+                                    logits_out.data_ptr(), value_out.data_ptr(), st)
+        if rc:
+            raise RuntimeError("cz_net_heads failed (%d)" % rc)
+        self._keep = x
+        return None
 
 
 class _Tf32:
@@ -221,6 +285,11 @@ class policy_value_network(object):
             self.net.eval()
             self._plan = InferencePlan(self.net, self.precision)
         return self._plan
+
+    def native_plan(self, max_batch):
+        """fp16 plan with the hand-written first-conv / head kernels (engine path); see NativePlan."""
+        self.net.eval()
+        return NativePlan(self.net, max_batch)
 
     @property
     def nn_dtype(self):

@@ -61,11 +61,15 @@ class SelfPlay:
     device tensors (they are copied into the static buffers)."""
 
     def __init__(self, n_games, forward, playouts, seeds=None, exploration=True, temperature=1,
-                 nn_dtype=torch.float32, arena_words=0, auto_reset=True, device=None, keep_records=True):
+                 nn_dtype=torch.float32, arena_words=0, auto_reset=True, device=None, keep_records=True, plan=None):
         self.engine = Engine(n_games, arena_words, device)
         self.B = n_games
         dev = torch.device("cuda", self.engine.device)
-        self.nn_in = torch.zeros((n_games, 9, 10, 14), dtype=nn_dtype, device=dev)
+        if plan is not None:     # an InferencePlan / NativePlan: it defines the input buffer and writes logits/value in place
+            self.nn_in = plan.make_input(n_games)
+            forward = lambda x: plan(x, self.logits, self.value)  # noqa: E731
+        else:
+            self.nn_in = torch.zeros((n_games, 9, 10, 14), dtype=nn_dtype, device=dev)
         self.logits = torch.zeros((n_games, NLABEL), dtype=torch.float32, device=dev)
         self.value = torch.zeros((n_games,), dtype=torch.float32, device=dev)
         self.forward = forward
@@ -466,6 +470,5 @@ class cchess_main(object):
         net = self.policy_value_netowrk
         plan = net.plan()
         sp = SelfPlay(n_games, None, self.playout_counts, seeds=seeds, exploration=self.exploration, temperature=self.temperature,
-                      nn_dtype=plan.dtype, arena_words=arena_words, auto_reset=False)
-        sp.forward = lambda x: plan(x, sp.logits, sp.value)
+                      arena_words=arena_words, auto_reset=False, plan=plan)
         return [(rec.tuples(), len(rec)) for _, rec in sp.play_games()]

@@ -42,6 +42,7 @@ extern "C" {
 #define CZ_F32 0
 #define CZ_BF16 1
 #define CZ_F16 2
+#define CZ_BOARD 3           /* wave only: row g = 96 bytes, the side-to-move-canonical board (for cz_net_first_conv) */
 
 /* per-game error flags (cz_engine_counters) */
 #define CZ_ERR_NOMOVES 1     /* expanded node with zero legal moves (reference: ValueError from max(), main.py:159) */
@@ -146,6 +147,17 @@ int cz_engine_counters(cz_engine *e, void *stream, int64_t *out /* [9] */);
 /* Test hook: flat DFS signature of game g's tree, records of 6 int64
  * (label index, N, W bits, P bits, Q bits, n_children), children in order. Returns record count via *n. */
 int cz_engine_tree_signature(cz_engine *e, void *stream, int game, int64_t *out, int64_t cap, int64_t *n);
+
+/* ---- network ends (policy_value_network.py:45-48 and 55-74), hand-written; the residual tower is library code ----
+ * cz_net_first_conv: canonical boards (dev u8 [B][96], from cz_engine_wave with CZ_BOARD) ->
+ *     ReLU(conv3x3(14->128) + bias) as fp16 NHWC [B][90][128].  w1: dev fp16 [9 taps][14 pieces][128], b1: dev f32 [128]
+ *     (batch norm already folded in).  The one-hot [9][10][14] tensor of main.py:547-557 is never materialised.
+ * cz_net_heads: x fp16 [B][90][128] -> logits f32 [B][2086] (raw, no softmax) and value f32 [B] (tanh).
+ *     wh f32 [3][128] / bh [3]: 1x1 convs of the policy (2) and value (1) heads with BN folded; w1t f32 [90][256], b1 [256],
+ *     w2 [256], b2: value MLP; wp fp16 [2112][192] / bp f32 [2112]: policy FC zero-padded; hp_scratch fp16 [B][192]. */
+int cz_net_first_conv(const uint8_t *canon_boards, int B, const void *w1, const float *b1, void *out, void *stream);
+int cz_net_heads(const void *x, int B, const float *wh, const float *bh, const float *w1t, const float *b1, const float *w2, float b2,
+                 const void *wp, const float *bp, void *hp_scratch, float *logits, float *value, void *stream);
 
 #ifdef __cplusplus
 }

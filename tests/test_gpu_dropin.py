@@ -138,3 +138,67 @@ def test_selfplay_with_real_network(precision, graph, tmp_path, monkeypatch):
     assert 0 < c["n_expand"] <= c["n_playout"] + 6 * B
     st = sp.engine.status()
     assert (st["ply"] <= 6).all() and st["ply"].max() == 6
+
+
+@pytest.mark.parametrize("blocks", [2, 7])
+def test_native_network_ends_match_library_plan(blocks):
+    """csrc/cz_net.cu (first conv from board bytes, fused heads) against the cuDNN/cuBLAS plan and against fp64."""
+    from cchess_zero_b200 import rules
+    from cchess_zero_b200.net import InferencePlan, NativePlan, PolicyValueNet
+    from cchess_zero_b200.selfplay import _flip_board
+    from oracle import oracle as O
+    torch.manual_seed(1)
+    net = PolicyValueNet(blocks).eval()
+    with torch.no_grad():   # non-trivial biases / BN statistics so that every folded term is exercised
+        for m in net.modules():
+            if isinstance(m, (torch.nn.Conv2d, torch.nn.Linear)):
+                m.bias.uniform_(-0.1, 0.1)
+            if hasattr(m, "running_var"):
+                m.running_var.uniform_(0.5, 1.5); m.running_mean.uniform_(-0.2, 0.2)
+    rng = np.random.RandomState(3)
+    boards, sides = [], []
+    b, side = O.from_state(O.START), 0
+    while len(boards) < 203:     # odd batch: exercises the tails of every kernel
+        boards.append(b.copy()); sides.append(side)
+        mv = O.legal_moves(b, side)
+        b, cap = O.apply_move(b, mv[rng.randint(len(mv))]); side ^= 1
+        if cap in (1, 8):
+            b, side = O.from_state(O.START), 0
+    enc = rules.encode_batch(np.stack(boards), sides)
+    canon = np.zeros((len(boards), 96), dtype=np.uint8)
+    for i, (bb, s) in enumerate(zip(boards, sides)):
+        canon[i, :90] = _flip_board(bb) if s == 1 else bb
+    with torch.no_grad():
+        rl, rv = net.double()(torch.from_numpy(enc).double())
+    net = net.float().cuda().to(memory_format=torch.channels_last)
+    B = len(boards)
+    lib_l, lib_v = InferencePlan(net, "fp16")(torch.from_numpy(enc).cuda().half())
+    nat = NativePlan(net, 256)
+    lo = torch.zeros((B, 2086), device="cuda"); vo = torch.zeros((B,), device="cuda")
+    nat(torch.from_numpy(canon).cuda(), lo, vo)
+    torch.cuda.synchronize()
+    e_nat = max((lo.double().cpu() - rl).abs().max().item(), (vo.double().cpu() - rv.reshape(-1)).abs().max().item())
+    e_lib = max((lib_l.double().cpu() - rl).abs().max().item(), (lib_v.double().cpu().reshape(-1) - rv.reshape(-1)).abs().max().item())
+    print("max abs err vs fp64: native %.3g library %.3g" % (e_nat, e_lib))
+    assert e_nat < 1e-3
+    assert (lo - lib_l).abs().max().item() < 2e-3
+
+
+def test_selfplay_native_plan_board_mode(tmp_path, monkeypatch):
+    monkeypatch.chdir(tmp_path)
+    from cchess_zero_b200.net import policy_value_network
+    from cchess_zero_b200.selfplay import SelfPlay
+    pv = policy_value_network(res_block_nums=2, precision="fp16")
+    B, P = 96, 20
+    sp = SelfPlay(B, None, P, seeds=range(B), arena_words=1 << 18, plan=pv.native_plan(B))
+    sp.capture_graph()
+    for _ in range(5):
+        sp.step()
+    c = sp.engine.raise_on_error()
+    assert c["n_playout"] == 5 * B * P
+    # the canonical boards handed to the network are the flipped root boards of the reference
+    sp2 = SelfPlay(B, None, P, seeds=range(B), arena_words=1 << 18, plan=pv.plan())
+    for _ in range(5):
+        sp2.step()
+    # same seeds + (numerically close) network: the opening plies normally coincide; at least the engines agree on ply counts
+    assert (sp.engine.status()["ply"] == sp2.engine.status()["ply"]).all()
