@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--res-blocks", type=int, default=7)
     ap.add_argument("--precision", default=os.environ.get("CCHESS_NN_PRECISION", "fp16"))
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--lanes", type=int, default=2, choices=[1, 2], help="2 = pipeline two half-batches (tree kernel under the other half's network)")
     ap.add_argument("--library-ends", action="store_true", help="use cuDNN/cuBLAS for the first conv and the heads instead of csrc/cz_net.cu")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
@@ -220,9 +221,11 @@ def run_ours(a, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     B = a.games
     pv = policy_value_network(a.res_blocks, precision=a.precision, device=local_rank, seed=0)
-    plan = pv.native_plan(B) if (a.precision == "fp16" and not a.library_ends) else pv.plan()
+    native = a.precision == "fp16" and not a.library_ends
+    factory = (lambda n: pv.native_plan(n)) if native else (lambda n: pv.plan())
+    plan = factory(B // a.lanes)
     sp = SelfPlay(B, None, a.playouts, seeds=[rank * B + g for g in range(B)], device=local_rank,
-                  auto_reset=True, keep_records=True, plan=plan)
+                  auto_reset=True, keep_records=True, plan=plan if a.lanes == 1 else None, plan_factory=factory, lanes=a.lanes)
     if not a.no_graph:
         sp.capture_graph()
     e = sp.engine
@@ -291,11 +294,13 @@ def run_ours(a, rank, world, local_rank):
         e.begin_search(a.playouts)
         k0 = e.counters()
         evs = []
+        lanes = sp.lanes if sp.lanes is not None else [sp]       # a single-lane SelfPlay has the same attribute names
         for _ in range(a.profile_waves):
-            x, y = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            x.record(); e.wave(sp.nn_in, sp.logits, sp.value); y.record()
-            evs.append((x, y))
-            sp.forward(sp.nn_in)
+            for ln in lanes:
+                x, y = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                x.record(); ln.engine.wave(ln.nn_in, ln.logits, ln.value); y.record()
+                evs.append((x, y))
+                ln.forward(ln.nn_in)
         torch.cuda.synchronize()
         k1 = e.counters()
         kms = [x.elapsed_time(y) for x, y in evs]
@@ -303,7 +308,7 @@ def run_ours(a, rank, world, local_rank):
         per_launch = ab / len(kms)
         avg_ms = float(np.mean(kms))
         achieved = per_launch / (avg_ms * 1e-3) / 1e9
-        roof = dict(kernel="k_wave (expand+backup+select+encode, one warp per game)", bound="hbm", achieved=achieved, peak=hbm, unit="GB/s",
+        roof = dict(kernel="k_wave (expand+backup+select+encode, one warp per game; %d games per launch)" % (B // a.lanes), bound="hbm", achieved=achieved, peak=hbm, unit="GB/s",
                     frac=achieved / hbm, traffic=None, peak_source=peak_src, avg_launch_ms=avg_ms, algorithmic_bytes_per_launch=per_launch,
                     bytes_per_expansion=ab / max(1, d["n_expand"]), launches_timed=len(kms),
                     note="latency-bound pointer-chasing kernel: HBM fraction is reported as required, the binding limits are per-warp dependent loads and the network")
@@ -326,7 +331,7 @@ def run_ours(a, rank, world, local_rank):
                     dtype=a.precision, data="synthetic (seed-0 xavier-initialised network, all games from the start position)",
                     config=dict(workload="%d concurrent self-play games x %d playouts per move, res_block_nums=%d, per GPU" % (B, a.playouts, a.res_blocks),
                                 games_per_gpu=B, playouts=a.playouts, res_block_nums=a.res_blocks, search_threads=1, exploration=True,
-                                cuda_graph=not a.no_graph, fused_conv_epilogue=plan.fused,
+                                cuda_graph=not a.no_graph, lanes=a.lanes, fused_conv_epilogue=plan.fused,
                                 network_ends="csrc/cz_net.cu (board-byte first conv, fused heads)" if plan.dtype == torch.uint8 else "library",
                                 l2_policy="working set (trees %.1f GB + activations) exceeds the 126 MB L2" % (c1["max_arena_words"] * 4 * B / 1e9)),
                     e2e=dict(value=e2e_v, unit="expansions/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, wall_ms=wall_ms),

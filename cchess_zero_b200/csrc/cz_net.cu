@@ -19,87 +19,77 @@
 namespace {
 
 // ------------------------------------------------------------------------------------------
-// first convolution from board bytes
+// first convolution from board bytes: one CTA per position, one warp per output cell (128 channels, 4 per lane)
 // ------------------------------------------------------------------------------------------
-constexpr int FC_POS = 4;        // positions per CTA
-constexpr int FC_THREADS = 256;  // 64 channel-pair lanes x 4 cell groups
-
-__global__ void __launch_bounds__(FC_THREADS) k_first_conv(const uint8_t *__restrict__ boards, int B, const __half2 *__restrict__ w /* [9][14][64] pairs */,
-                                                            const float2 *__restrict__ bias /* [64] */, __half2 *__restrict__ out /* [B][90][64] */) {
-    __shared__ __half2 sw[9 * 14 * 64];   // 31.5 KB: fp16 weights (the tensor-core path rounds them the same way), fp32 accumulation
-    __shared__ uint8_t sb[FC_POS][96];
-    for (int i = threadIdx.x; i < 9 * 14 * 64; i += FC_THREADS) sw[i] = w[i];
-    const int p0 = blockIdx.x * FC_POS;
-    for (int i = threadIdx.x; i < FC_POS * 24; i += FC_THREADS) {
-        const int p = i / 24, wd = i - p * 24;
-        reinterpret_cast<uint32_t *>(sb[p])[wd] = p0 + p < B ? reinterpret_cast<const uint32_t *>(boards + (size_t)(p0 + p) * 96)[wd] : 0u;
+__global__ void __launch_bounds__(256) k_first_conv(const uint8_t *__restrict__ boards, int B, const __half *__restrict__ w /* [9][14][128] */,
+                                                     const float4 *__restrict__ bias /* [32] */, __half *__restrict__ out /* [B][90][128] */) {
+    __shared__ uint8_t pb[11 * 12 + 12];   // zero-bordered image: pb[(r+1)*12 + f+1] = canonical board byte r*9+f (r < 9, f < 10)
+    const int pos = blockIdx.x;
+    const uint8_t *bd = boards + (size_t)pos * 96;
+    if (threadIdx.x < 132) {
+        const int r = threadIdx.x / 12 - 1, f = threadIdx.x % 12 - 1;
+        pb[threadIdx.x] = (r >= 0 && r < 9 && f >= 0 && f < 10) ? bd[r * 9 + f] : (uint8_t)0;   // the reference's cell <- s[rank*9+file]
     }
     __syncthreads();
-    const int cp = threadIdx.x & 63, grp = threadIdx.x >> 6;   // channel pair, cell group
-    const float2 bv = bias[cp];
-    for (int idx = grp; idx < FC_POS * 90; idx += 4) {
-        const int p = idx / 90, cell = idx - p * 90;
-        if (p0 + p >= B) break;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float4 bv = bias[lane];
+    for (int cell = warp; cell < 90; cell += 8) {
         const int r = cell / 10, f = cell - r * 10;
-        float2 acc = bv;
+        const uint8_t *c0 = pb + r * 12 + f;          // top-left of the 3x3 window
+        int pc[9];
 #pragma unroll
-        for (int dr = -1; dr <= 1; dr++) {
-            const int rr = r + dr;
-            if (rr < 0 || rr > 8) continue;
+        for (int t = 0; t < 9; t++) pc[t] = c0[(t / 3) * 12 + (t % 3)];
+        float4 acc = bv;
 #pragma unroll
-            for (int df = -1; df <= 1; df++) {
-                const int ff = f + df;
-                if (ff < 0 || ff > 9) continue;
-                const int pc = sb[p][rr * 9 + ff];            // the reference's indexing: cell (rank, file) <- s[rank*9+file]
-                if (pc) {
-                    const float2 wv = __half22float2(sw[(((dr + 1) * 3 + (df + 1)) * 14 + (pc - 1)) * 64 + cp]);
-                    acc.x += wv.x;
-                    acc.y += wv.y;
-                }
+        for (int t = 0; t < 9; t++) {
+            if (pc[t]) {
+                const uint2 raw = __ldg(reinterpret_cast<const uint2 *>(w + ((size_t)(t * 14 + pc[t] - 1) * 128 + lane * 4)));
+                const float2 lo = __half22float2(*reinterpret_cast<const __half2 *>(&raw.x));
+                const float2 hi = __half22float2(*reinterpret_cast<const __half2 *>(&raw.y));
+                acc.x += lo.x; acc.y += lo.y; acc.z += hi.x; acc.w += hi.y;
             }
         }
-        out[((size_t)(p0 + p) * 90 + cell) * 64 + cp] = __floats2half2_rn(fmaxf(acc.x, 0.f), fmaxf(acc.y, 0.f));
+        const __half2 o0 = __floats2half2_rn(fmaxf(acc.x, 0.f), fmaxf(acc.y, 0.f));
+        const __half2 o1 = __floats2half2_rn(fmaxf(acc.z, 0.f), fmaxf(acc.w, 0.f));
+        uint2 o;
+        o.x = *reinterpret_cast<const uint32_t *>(&o0);
+        o.y = *reinterpret_cast<const uint32_t *>(&o1);
+        *reinterpret_cast<uint2 *>(out + ((size_t)pos * 90 + cell) * 128 + lane * 4) = o;
     }
 }
 
 // ------------------------------------------------------------------------------------------
-// heads: 1x1 conv (3 outputs) + value MLP
+// heads, stage 1: conv1x1 (128 -> 3) + bias + ReLU.  One CTA per position; all loads of a warp are issued first.
 // ------------------------------------------------------------------------------------------
-constexpr int HC_POS = 4;
-constexpr int HC_THREADS = 256;
-
-__global__ void __launch_bounds__(HC_THREADS) k_head_conv(const __half *__restrict__ x /* [B][90][128] */, int B, const float *__restrict__ wh /* [3][128] */,
-                                                           const float *__restrict__ bh /* [3] */, const float *__restrict__ w1t /* [90][256] */,
-                                                           const float *__restrict__ b1 /* [256] */, const float *__restrict__ w2 /* [256] */, float b2,
-                                                           __half *__restrict__ hp /* [B][192] */, float *__restrict__ value /* [B] */) {
-    __shared__ float swh[3][128];
-    __shared__ float hv[HC_POS][96];
-    __shared__ float red[HC_POS][8];
-    for (int i = threadIdx.x; i < 3 * 128; i += HC_THREADS) swh[i / 128][i % 128] = wh[i];
-    __syncthreads();
-    const int p0 = blockIdx.x * HC_POS;
+__global__ void __launch_bounds__(256) k_head_conv(const __half *__restrict__ x /* [B][90][128] */, int B, const float *__restrict__ wh /* [3][128] */,
+                                                    const float *__restrict__ bh /* [3] */, __half *__restrict__ hp /* [B][192] */,
+                                                    float *__restrict__ hv /* [B][96] */) {
+    const int pos = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int half_id = lane >> 4, l16 = lane & 15;   // two cells per warp iteration, 16 lanes x 8 channels each
     float wreg[3][8];
 #pragma unroll
     for (int o = 0; o < 3; o++)
 #pragma unroll
-        for (int k = 0; k < 8; k++) wreg[o][k] = swh[o][l16 * 8 + k];
+        for (int k = 0; k < 8; k++) wreg[o][k] = __ldg(wh + o * 128 + l16 * 8 + k);
     const float bh0 = bh[0], bh1 = bh[1], bh2 = bh[2];
-    for (int it = warp; it < HC_POS * 45; it += 8) {
-        const int cidx = it * 2 + half_id;           // 0 .. HC_POS*90-1
-        const int p = cidx / 90, cell = cidx - p * 90;
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-        if (p0 + p < B) {
-            const uint4 raw = *reinterpret_cast<const uint4 *>(x + ((size_t)(p0 + p) * 90 + cell) * 128 + l16 * 8);
-            const __half2 *h2 = reinterpret_cast<const __half2 *>(&raw);
+    uint4 raw[6];
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const float2 v = __half22float2(h2[k]);
-                s0 += v.x * wreg[0][2 * k] + v.y * wreg[0][2 * k + 1];
-                s1 += v.x * wreg[1][2 * k] + v.y * wreg[1][2 * k + 1];
-                s2 += v.x * wreg[2][2 * k] + v.y * wreg[2][2 * k + 1];
-            }
+    for (int j = 0; j < 6; j++) {                     // cells: (warp + 8j)*2 + half_id, 45 pairs over 8 warps
+        const int cell = (warp + 8 * j) * 2 + half_id;
+        raw[j] = cell < 90 ? __ldg(reinterpret_cast<const uint4 *>(x + ((size_t)pos * 90 + cell) * 128 + l16 * 8)) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int j = 0; j < 6; j++) {
+        const int cell = (warp + 8 * j) * 2 + half_id;
+        const __half2 *h2 = reinterpret_cast<const __half2 *>(&raw[j]);
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const float2 v = __half22float2(h2[k]);
+            s0 += v.x * wreg[0][2 * k] + v.y * wreg[0][2 * k + 1];
+            s1 += v.x * wreg[1][2 * k] + v.y * wreg[1][2 * k + 1];
+            s2 += v.x * wreg[2][2 * k] + v.y * wreg[2][2 * k + 1];
         }
 #pragma unroll
         for (int o = 8; o >= 1; o >>= 1) {
@@ -107,39 +97,46 @@ __global__ void __launch_bounds__(HC_THREADS) k_head_conv(const __half *__restri
             s1 += __shfl_xor_sync(0xffffffffu, s1, o);
             s2 += __shfl_xor_sync(0xffffffffu, s2, o);
         }
-        if (l16 == 0 && p0 + p < B) {
+        if (l16 == 0 && cell < 90) {
             // flatten order of tf.reshape on NHWC (policy_value_network.py:62, 72): index = cell*2 + c
-            const __half2 pv = __floats2half2_rn(fmaxf(s0 + bh0, 0.f), fmaxf(s1 + bh1, 0.f));
-            *reinterpret_cast<__half2 *>(hp + (size_t)(p0 + p) * 192 + cell * 2) = pv;
-            hv[p][cell] = fmaxf(s2 + bh2, 0.f);
+            *reinterpret_cast<__half2 *>(hp + (size_t)pos * 192 + cell * 2) = __floats2half2_rn(fmaxf(s0 + bh0, 0.f), fmaxf(s1 + bh1, 0.f));
+            hv[(size_t)pos * 96 + cell] = fmaxf(s2 + bh2, 0.f);
         }
     }
-    // zero padding of hp columns 180..191
-    if (threadIdx.x < HC_POS * 12) {
-        const int p = threadIdx.x / 12, c = threadIdx.x % 12;
-        if (p0 + p < B) hp[(size_t)(p0 + p) * 192 + 180 + c] = __float2half(0.f);
+    if (threadIdx.x < 12) hp[(size_t)pos * 192 + 180 + threadIdx.x] = __float2half(0.f);   // K padding of the policy GEMM
+}
+
+// heads, stage 2a: value MLP 90 -> 256 ReLU -> 1 tanh (policy_value_network.py:73-74), 16 positions per CTA
+constexpr int VM_POS = 16;
+__global__ void __launch_bounds__(256) k_value_mlp(const float *__restrict__ hv /* [B][96] */, int B, const float *__restrict__ w1t /* [90][256] */,
+                                                    const float *__restrict__ b1, const float *__restrict__ w2, float b2, float *__restrict__ value) {
+    __shared__ float sh[VM_POS][96];
+    __shared__ float red[VM_POS][8];
+    const int p0 = blockIdx.x * VM_POS, t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    for (int i = t; i < VM_POS * 96; i += 256) {
+        const int p = i / 96;
+        sh[p][i - p * 96] = p0 + p < B ? hv[(size_t)(p0 + p) * 96 + (i - p * 96)] : 0.f;
     }
     __syncthreads();
-    // value head: fc1 (90 -> 256) + ReLU, fc2 (256 -> 1), tanh   (policy_value_network.py:73-74)
-    const int t = threadIdx.x;
-    float a[HC_POS];
+    float a[VM_POS];
+    const float bb = b1[t];
 #pragma unroll
-    for (int p = 0; p < HC_POS; p++) a[p] = b1[t];
+    for (int p = 0; p < VM_POS; p++) a[p] = bb;
     for (int k = 0; k < 90; k++) {
-        const float wv = w1t[k * 256 + t];
+        const float wv = __ldg(w1t + k * 256 + t);
 #pragma unroll
-        for (int p = 0; p < HC_POS; p++) a[p] += wv * hv[p][k];
+        for (int p = 0; p < VM_POS; p++) a[p] += wv * sh[p][k];
     }
     const float w2v = w2[t];
 #pragma unroll
-    for (int p = 0; p < HC_POS; p++) {
+    for (int p = 0; p < VM_POS; p++) {
         float s = fmaxf(a[p], 0.f) * w2v;
 #pragma unroll
         for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         if (lane == 0) red[p][warp] = s;
     }
     __syncthreads();
-    if (t < HC_POS && p0 + t < B) {
+    if (t < VM_POS && p0 + t < B) {
         float s = b2;
 #pragma unroll
         for (int wq = 0; wq < 8; wq++) s += red[t][wq];
@@ -148,7 +145,7 @@ __global__ void __launch_bounds__(HC_THREADS) k_head_conv(const __half *__restri
 }
 
 // ------------------------------------------------------------------------------------------
-// policy FC on tensor cores (legacy mma.sync path: the GEMM is 0.77 GFLOP and bound by its 8.5 MB output)
+// heads, stage 2b: policy FC on tensor cores (legacy mma.sync path: 0.77 GFLOP, bound by its 8.5 MB f32 output)
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
@@ -156,22 +153,32 @@ __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], 
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
-constexpr int NPAD = 2112;  // 33 * 64 >= 2086
+constexpr int NPAD = 2112;   // 33 * 64 >= 2086
+constexpr int LDS_ROW = 200; // halves per staged row (192 + 8 pad): fragment loads hit 32 distinct banks
 
-// grid (ceil(B/64), 33), 128 threads: warp w -> rows [64*bx + 16w, +16), cols [64*by, +64)
-__global__ void __launch_bounds__(128) k_policy_fc(const __half *__restrict__ hp /* [Bpad][192] */, int B, const __half *__restrict__ wp /* [NPAD][192] */,
+// grid (ceil(B/64), 33), 128 threads.  A tile (64 positions x 192) and B tile (64 labels x 192) are staged through shared
+// memory with 16-byte coalesced loads, all in flight at once; warp w owns rows [16w, 16w+16) x 64 columns.
+__global__ void __launch_bounds__(128) k_policy_fc(const __half *__restrict__ hp /* [B][192] */, int B, const __half *__restrict__ wp /* [NPAD][192] */,
                                                     const float *__restrict__ bp /* [NPAD] */, float *__restrict__ logits /* [B][2086] */) {
+    extern __shared__ __align__(16) __half smem_fc[];
+    __half *sA = smem_fc, *sB = smem_fc + 64 * LDS_ROW;
+    const int row0 = blockIdx.x * 64, col0 = blockIdx.y * 64;
+    for (int i = threadIdx.x; i < 64 * 24; i += 128) {          // 24 x 16-byte chunks per 192-half row
+        const int r = i / 24, c = i - r * 24;
+        const int ra = min(row0 + r, B - 1);                     // clamp: rows >= B are computed but never stored
+        *reinterpret_cast<uint4 *>(sA + r * LDS_ROW + c * 8) = __ldg(reinterpret_cast<const uint4 *>(hp + (size_t)ra * 192 + c * 8));
+        *reinterpret_cast<uint4 *>(sB + r * LDS_ROW + c * 8) = __ldg(reinterpret_cast<const uint4 *>(wp + (size_t)(col0 + r) * 192 + c * 8));
+    }
+    __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-    const int row0 = blockIdx.x * 64 + warp * 16, col0 = blockIdx.y * 64;
     float acc[8][4];
 #pragma unroll
     for (int n = 0; n < 8; n++)
 #pragma unroll
         for (int k = 0; k < 4; k++) acc[n][k] = 0.f;
-    const int ra = min(row0 + g, B - 1), rb = min(row0 + g + 8, B - 1);   // clamp: rows >= B are computed but never stored
-    const uint32_t *A0 = reinterpret_cast<const uint32_t *>(hp + (size_t)ra * 192);
-    const uint32_t *A1 = reinterpret_cast<const uint32_t *>(hp + (size_t)rb * 192);
-#pragma unroll 4
+    const uint32_t *A0 = reinterpret_cast<const uint32_t *>(sA + (warp * 16 + g) * LDS_ROW);
+    const uint32_t *A1 = reinterpret_cast<const uint32_t *>(sA + (warp * 16 + g + 8) * LDS_ROW);
+#pragma unroll
     for (int ks = 0; ks < 12; ks++) {
         uint32_t a[4];
         a[0] = A0[ks * 8 + t];
@@ -180,20 +187,21 @@ __global__ void __launch_bounds__(128) k_policy_fc(const __half *__restrict__ hp
         a[3] = A1[ks * 8 + 4 + t];
 #pragma unroll
         for (int n = 0; n < 8; n++) {
-            const uint32_t *Bp = reinterpret_cast<const uint32_t *>(wp + (size_t)(col0 + n * 8 + g) * 192);
+            const uint32_t *Bp = reinterpret_cast<const uint32_t *>(sB + (n * 8 + g) * LDS_ROW);
             uint32_t b[2];
             b[0] = Bp[ks * 8 + t];
             b[1] = Bp[ks * 8 + 4 + t];
             mma16816(acc[n], a, b);
         }
     }
+    const int r0 = row0 + warp * 16 + g;
 #pragma unroll
     for (int n = 0; n < 8; n++) {
         const int col = col0 + n * 8 + t * 2;
         if (col >= CZ_NLABEL) continue;
         const float b0 = bp[col], b1 = bp[col + 1];
-        if (row0 + g < B) *reinterpret_cast<float2 *>(logits + (size_t)(row0 + g) * CZ_NLABEL + col) = make_float2(acc[n][0] + b0, acc[n][1] + b1);
-        if (row0 + g + 8 < B) *reinterpret_cast<float2 *>(logits + (size_t)(row0 + g + 8) * CZ_NLABEL + col) = make_float2(acc[n][2] + b0, acc[n][3] + b1);
+        if (r0 < B) *reinterpret_cast<float2 *>(logits + (size_t)r0 * CZ_NLABEL + col) = make_float2(acc[n][0] + b0, acc[n][1] + b1);
+        if (r0 + 8 < B) *reinterpret_cast<float2 *>(logits + (size_t)(r0 + 8) * CZ_NLABEL + col) = make_float2(acc[n][2] + b0, acc[n][3] + b1);
     }
 }
 
@@ -203,19 +211,27 @@ extern "C" {
 
 int cz_net_first_conv(const uint8_t *canon_boards, int B, const void *w1, const float *b1, void *out, void *stream) {
     if (!canon_boards || !w1 || !b1 || !out || B <= 0) return CZ_EINVAL;
-    k_first_conv<<<(B + FC_POS - 1) / FC_POS, FC_THREADS, 0, (cudaStream_t)stream>>>(canon_boards, B, reinterpret_cast<const __half2 *>(w1),
-                                                                                      reinterpret_cast<const float2 *>(b1), reinterpret_cast<__half2 *>(out));
+    k_first_conv<<<B, 256, 0, (cudaStream_t)stream>>>(canon_boards, B, reinterpret_cast<const __half *>(w1), reinterpret_cast<const float4 *>(b1),
+                                                      reinterpret_cast<__half *>(out));
     return cudaGetLastError() == cudaSuccess ? CZ_OK : CZ_ECUDA;
 }
 
 int cz_net_heads(const void *x, int B, const float *wh, const float *bh, const float *w1t, const float *b1, const float *w2, float b2,
-                 const void *wp, const float *bp, void *hp_scratch, float *logits, float *value, void *stream) {
-    if (!x || !wh || !bh || !w1t || !b1 || !w2 || !wp || !bp || !hp_scratch || !logits || !value || B <= 0) return CZ_EINVAL;
+                 const void *wp, const float *bp, void *hp_scratch, float *hv_scratch, float *logits, float *value, void *stream) {
+    if (!x || !wh || !bh || !w1t || !b1 || !w2 || !wp || !bp || !hp_scratch || !hv_scratch || !logits || !value || B <= 0) return CZ_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
-    k_head_conv<<<(B + HC_POS - 1) / HC_POS, HC_THREADS, 0, st>>>((const __half *)x, B, wh, bh, w1t, b1, w2, b2, (__half *)hp_scratch, value);
+    static bool attr = false;
+    const int smem = 2 * 64 * LDS_ROW * (int)sizeof(__half);   // 51200 B
+    if (!attr) {
+        if (cudaFuncSetAttribute(k_policy_fc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return CZ_ECUDA;
+        attr = true;
+    }
+    k_head_conv<<<B, 256, 0, st>>>((const __half *)x, B, wh, bh, (__half *)hp_scratch, hv_scratch);
+    if (cudaGetLastError() != cudaSuccess) return CZ_ECUDA;
+    k_value_mlp<<<(B + VM_POS - 1) / VM_POS, 256, 0, st>>>(hv_scratch, B, w1t, b1, w2, b2, value);
     if (cudaGetLastError() != cudaSuccess) return CZ_ECUDA;
     dim3 grid((B + 63) / 64, NPAD / 64);
-    k_policy_fc<<<grid, 128, 0, st>>>((const __half *)hp_scratch, B, (const __half *)wp, bp, logits);
+    k_policy_fc<<<grid, 128, smem, st>>>((const __half *)hp_scratch, B, (const __half *)wp, bp, logits);
     return cudaGetLastError() == cudaSuccess ? CZ_OK : CZ_ECUDA;
 }
 

@@ -214,6 +214,7 @@ class NativePlan:
         self.max_batch = max_batch
         self.x1 = torch.empty((max_batch, 9, 10, 128), dtype=torch.float16, device=dev)
         self.hp = torch.zeros((max_batch, 192), dtype=torch.float16, device=dev)
+        self.hv = torch.zeros((max_batch, 96), dtype=torch.float32, device=dev)
 
     def make_input(self, B):
         return torch.zeros((B, 96), dtype=torch.uint8, device=self.x1.device)
@@ -233,7 +234,7 @@ class NativePlan:
         if not x.is_contiguous(memory_format=torch.channels_last):
             x = x.contiguous(memory_format=torch.channels_last)
         rc = self._lib.cz_net_heads(x.data_ptr(), B, self.wh.data_ptr(), self.bh.data_ptr(), self.w1t.data_ptr(), self.bv1.data_ptr(),
-                                    self.w2.data_ptr(), self.b2, self.wp.data_ptr(), self.bp.data_ptr(), self.hp.data_ptr(),
+                                    self.w2.data_ptr(), self.b2, self.wp.data_ptr(), self.bp.data_ptr(), self.hp.data_ptr(), self.hv.data_ptr(),
                                     logits_out.data_ptr(), value_out.data_ptr(), st)
         if rc:
             raise RuntimeError("cz_net_heads failed (%d)" % rc)

@@ -53,6 +53,77 @@ class GameRecord:
         return zip(self.states, self.dense_pi(), self.z)
 
 
+class _Lane:
+    """One half-batch of a pipelined SelfPlay: its own engine, I/O buffers and evaluator scratch."""
+
+    def __init__(self, engine, lo, hi, nn_in, logits, value, forward):
+        self.engine, self.lo, self.hi = engine, lo, hi
+        self.nn_in, self.logits, self.value, self.forward = nn_in, logits, value, forward
+
+
+class _MultiEngine:
+    """Engine-shaped facade over the lanes' engines (games [lo, hi) of lane k live in engine k)."""
+
+    def __init__(self, lanes, B):
+        self.lanes, self.B = lanes, B
+        self.device = lanes[0].engine.device
+
+    @property
+    def launches(self):
+        return sum(l.engine.launches for l in self.lanes)
+
+    def _m(self, mask, l):
+        return None if mask is None else np.ascontiguousarray(mask[l.lo:l.hi], dtype=np.uint8)
+
+    def reset(self, mask=None, boards=None, sides=None, rr=None):
+        for l in self.lanes:
+            if mask is not None and not np.any(mask[l.lo:l.hi]):
+                continue
+            l.engine.reset(self._m(mask, l), None if boards is None else boards[l.lo:l.hi],
+                           None if sides is None else sides[l.lo:l.hi], None if rr is None else rr[l.lo:l.hi])
+
+    def begin_search(self, playouts, mask=None):
+        for l in self.lanes:
+            l.engine.begin_search(playouts, self._m(mask, l))
+
+    def unfinished(self):
+        return sum(l.engine.unfinished() for l in self.lanes)
+
+    def root_children(self, want_wpq=True):
+        parts = [l.engine.root_children(want_wpq) for l in self.lanes]
+        return {k: (np.concatenate([p[k] for p in parts]) if parts[0][k] is not None else None) for k in parts[0]}
+
+    def play(self, child_index):
+        for l in self.lanes:
+            l.engine.play(child_index[l.lo:l.hi])
+
+    def status(self, boards=True):
+        parts = [l.engine.status(boards) for l in self.lanes]
+        return {k: (np.concatenate([p[k] for p in parts]) if parts[0][k] is not None else None) for k in parts[0]}
+
+    def counters(self):
+        cs = [l.engine.counters() for l in self.lanes]
+        out = {k: sum(c[k] for c in cs) for k in ("n_expand", "n_playout", "sum_L", "sum_c", "sum_C")}
+        out["error"] = 0
+        for c in cs:
+            out["error"] |= c["error"]
+        out["max_arena_words"] = max(c["max_arena_words"] for c in cs)
+        out["max_depth"] = max(c["max_depth"] for c in cs)
+        out["first_error_game"] = next((l.lo + c["first_error_game"] for l, c in zip(self.lanes, cs) if c["first_error_game"] >= 0), -1)
+        return out
+
+    def raise_on_error(self):
+        for l in self.lanes:
+            l.engine.raise_on_error()
+        return self.counters()
+
+    def tree_signature(self, game):
+        for l in self.lanes:
+            if l.lo <= game < l.hi:
+                return l.engine.tree_signature(game - l.lo)
+        raise IndexError(game)
+
+
 class SelfPlay:
     """n_games concurrent self-play games on one engine.
 
@@ -61,17 +132,39 @@ class SelfPlay:
     device tensors (they are copied into the static buffers)."""
 
     def __init__(self, n_games, forward, playouts, seeds=None, exploration=True, temperature=1,
-                 nn_dtype=torch.float32, arena_words=0, auto_reset=True, device=None, keep_records=True, plan=None):
-        self.engine = Engine(n_games, arena_words, device)
+                 nn_dtype=torch.float32, arena_words=0, auto_reset=True, device=None, keep_records=True, plan=None,
+                 plan_factory=None, lanes=1):
+        """plan: an InferencePlan / NativePlan (defines the input buffer, writes logits/value in place).
+        plan_factory(n) + lanes=2: two half-batches, each with its own engine and plan; the search pipelines them so
+        that one half's tree kernel runs under the other half's network (see capture_graph)."""
         self.B = n_games
-        dev = torch.device("cuda", self.engine.device)
-        if plan is not None:     # an InferencePlan / NativePlan: it defines the input buffer and writes logits/value in place
-            self.nn_in = plan.make_input(n_games)
-            forward = lambda x: plan(x, self.logits, self.value)  # noqa: E731
+        if lanes > 1:
+            assert plan_factory is not None and n_games % lanes == 0
+            per = n_games // lanes
+            self.lanes = []
+            for k in range(lanes):
+                eng = Engine(per, arena_words, device)
+                dev = torch.device("cuda", eng.device)
+                pl = plan_factory(per)
+                lg = torch.zeros((per, NLABEL), dtype=torch.float32, device=dev)
+                vl = torch.zeros((per,), dtype=torch.float32, device=dev)
+                ni = pl.make_input(per)
+                self.lanes.append(_Lane(eng, k * per, (k + 1) * per, ni, lg, vl, (lambda x, pl=pl, lg=lg, vl=vl: pl(x, lg, vl))))
+            self.engine = _MultiEngine(self.lanes, n_games)
+            self.nn_in, self.logits, self.value, forward = None, None, None, None
         else:
-            self.nn_in = torch.zeros((n_games, 9, 10, 14), dtype=nn_dtype, device=dev)
-        self.logits = torch.zeros((n_games, NLABEL), dtype=torch.float32, device=dev)
-        self.value = torch.zeros((n_games,), dtype=torch.float32, device=dev)
+            self.engine = Engine(n_games, arena_words, device)
+            dev = torch.device("cuda", self.engine.device)
+            if plan is None and plan_factory is not None:
+                plan = plan_factory(n_games)
+            self.logits = torch.zeros((n_games, NLABEL), dtype=torch.float32, device=dev)
+            self.value = torch.zeros((n_games,), dtype=torch.float32, device=dev)
+            if plan is not None:
+                self.nn_in = plan.make_input(n_games)
+                forward = lambda x: plan(x, self.logits, self.value)  # noqa: E731
+            else:
+                self.nn_in = torch.zeros((n_games, 9, 10, 14), dtype=nn_dtype, device=dev)
+            self.lanes = None
         self.forward = forward
         self.playouts = np.broadcast_to(np.asarray(playouts, dtype=np.int64), (n_games,)).copy()
         seeds = range(n_games) if seeds is None else seeds
@@ -98,8 +191,67 @@ class SelfPlay:
             self.logits.copy_(lo.reshape(self.B, NLABEL))
             self.value.copy_(v.reshape(self.B))
 
+    def _capture_pipeline(self, warmup=3):
+        """Two-lane software pipeline in ONE CUDA graph:
+              stage 1:  network(A)  ||  k_wave(B)        stage 2:  network(B)  ||  k_wave(A)
+        k_wave is a latency-bound kernel (one warp per game, ~17 % issue utilisation), so it runs on a side stream
+        underneath the other half-batch's convolutions.  Data flow per replay: network(A) consumes the leaves lane A
+        selected in the previous replay (or in the prologue wave), k_wave(B) consumes network(B)'s previous output."""
+        A, Bn = self.lanes
+        side = torch.cuda.Stream()
+        cs = torch.cuda.Stream()
+        cs.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(cs):
+            for _ in range(warmup):
+                A.forward(A.nn_in)
+                Bn.forward(Bn.nn_in)
+        torch.cuda.current_stream().wait_stream(cs)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=cs):
+            side.wait_stream(cs)
+            with torch.cuda.stream(side):
+                Bn.engine.wave(Bn.nn_in, Bn.logits, Bn.value)
+            A.forward(A.nn_in)
+            cs.wait_stream(side)
+            side.wait_stream(cs)
+            with torch.cuda.stream(side):
+                A.engine.wave(A.nn_in, A.logits, A.value)
+            Bn.forward(Bn.nn_in)
+            cs.wait_stream(side)
+        self.graph = g
+
+    def _search_pipeline(self):
+        e = self.engine
+        A, Bn = self.lanes
+        for p in np.unique(self.playouts[self.live]):
+            e.begin_search(int(p), (self.live & (self.playouts == p)).astype(np.uint8))
+        pmax = int(self.playouts[self.live].max()) if self.live.any() else 0
+        A.engine.wave(A.nn_in, A.logits, A.value)      # prologue: lane A's first leaves
+        waves = 1
+        while True:
+            if self.graph is not None:
+                self.graph.replay()
+                A.engine.launches += 1
+                Bn.engine.launches += 1
+            else:
+                Bn.engine.wave(Bn.nn_in, Bn.logits, Bn.value)
+                A.forward(A.nn_in)
+                A.engine.wave(A.nn_in, A.logits, A.value)
+                Bn.forward(Bn.nn_in)
+            waves += 1
+            if waves > pmax and e.unfinished() == 0:
+                break
+            if waves > 4 * pmax + 64:
+                e.raise_on_error()
+                raise EngineError("search did not converge")
+        self.waves += waves
+        return waves
+
     def capture_graph(self, warmup=3):
         """Capture (wave kernel -> network) into one CUDA graph; the search loop then replays it."""
+        if self.lanes is not None:
+            return self._capture_pipeline(warmup)
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
@@ -115,6 +267,8 @@ class SelfPlay:
 
     def search(self):
         """MCTS_tree.main for every live game: `playouts[g]` playouts each."""
+        if self.lanes is not None:
+            return self._search_pipeline()
         e = self.engine
         for p in np.unique(self.playouts[self.live]):
             e.begin_search(int(p), (self.live & (self.playouts == p)).astype(np.uint8))

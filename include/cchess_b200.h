@@ -154,10 +154,11 @@ int cz_engine_tree_signature(cz_engine *e, void *stream, int game, int64_t *out,
  *     (batch norm already folded in).  The one-hot [9][10][14] tensor of main.py:547-557 is never materialised.
  * cz_net_heads: x fp16 [B][90][128] -> logits f32 [B][2086] (raw, no softmax) and value f32 [B] (tanh).
  *     wh f32 [3][128] / bh [3]: 1x1 convs of the policy (2) and value (1) heads with BN folded; w1t f32 [90][256], b1 [256],
- *     w2 [256], b2: value MLP; wp fp16 [2112][192] / bp f32 [2112]: policy FC zero-padded; hp_scratch fp16 [B][192]. */
+ *     w2 [256], b2: value MLP; wp fp16 [2112][192] / bp f32 [2112]: policy FC zero-padded; hp_scratch fp16 [B][192],
+ *     hv_scratch f32 [B][96]. */
 int cz_net_first_conv(const uint8_t *canon_boards, int B, const void *w1, const float *b1, void *out, void *stream);
 int cz_net_heads(const void *x, int B, const float *wh, const float *bh, const float *w1t, const float *b1, const float *w2, float b2,
-                 const void *wp, const float *bp, void *hp_scratch, float *logits, float *value, void *stream);
+                 const void *wp, const float *bp, void *hp_scratch, float *hv_scratch, float *logits, float *value, void *stream);
 
 #ifdef __cplusplus
 }

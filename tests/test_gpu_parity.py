@@ -235,3 +235,32 @@ def test_selfplay_many_games_vs_oracle(graph, O, R):
         assert np.array_equal(rec.z, r["z"])
         assert np.array_equal(rec.dense_pi(), r["pis"])
         assert rec.actions == r["actions"]
+
+
+def test_two_lane_pipeline_is_bit_exact_vs_oracle(O, R):
+    """The pipelined two-lane schedule (tree kernel of one half under the network of the other) must not change results."""
+    from cchess_zero_b200.fakenet import FakeNet
+    from cchess_zero_b200.selfplay import SelfPlay
+    B, playouts, net = 32, 30, "hash_signed"
+
+    class Plan:
+        def __init__(self, n):
+            self.fn = FakeNet(net)
+        def make_input(self, n):
+            return torch.zeros((n, 9, 10, 14), device="cuda")
+        def __call__(self, x, lo, v):
+            l, val = self.fn(x)
+            lo.copy_(l); v.copy_(val)
+
+    for graph in (False, True):
+        sp = SelfPlay(B, None, playouts, seeds=[500 + i for i in range(B)], arena_words=1 << 20, auto_reset=False,
+                      plan_factory=lambda n: Plan(n), lanes=2)
+        if graph:
+            sp.capture_graph()
+        out = sp.play_games()
+        assert len(out) == B
+        for slot, rec in out:
+            with np.errstate(all="ignore"):
+                r = O.selfplay_game(net, playouts, np.random.RandomState(500 + slot))
+            assert rec.states == r["states"], (graph, slot)
+            assert np.array_equal(rec.dense_pi(), r["pis"]) and np.array_equal(rec.z, r["z"])
