@@ -43,7 +43,7 @@ def parse():
     ap.add_argument("--res-blocks", type=int, default=7)
     ap.add_argument("--precision", default=os.environ.get("CCHESS_NN_PRECISION", "fp16"))
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--lanes", type=int, default=2, choices=[1, 2], help="2 = pipeline two half-batches (tree kernel under the other half's network)")
+    ap.add_argument("--lanes", type=int, default=1, choices=[1, 2], help="2 = pipeline two half-batches (tree kernel under the other half's network)")
     ap.add_argument("--library-ends", action="store_true", help="use cuDNN/cuBLAS for the first conv and the heads instead of csrc/cz_net.cu")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
@@ -112,101 +112,97 @@ def algorithmic_bytes(c0, c1, enc_bytes):
 
 
 # ---------------------------------------------------------------------------------------------
-def cpu_reference(n_games, playouts, res_blocks, seconds, threads, warm_waves=1, fixed_waves=None):
-    """The reference's path on the host cores: the C oracle port (oracle/cchess_oracle.c) drives
-    n_games trees in lock-step (one leaf per game per wave, search_threads=1 semantics) and the same
-    network (same seed-0 weights) is evaluated by PyTorch on the CPU with all host threads."""
-    import ctypes as C
-    from cchess_zero_b200.net import PolicyValueNet
-    from oracle import oracle as O
-    torch.set_num_threads(threads)
-    torch.manual_seed(0)
-    net = PolicyValueNet(res_blocks).eval().to(memory_format=torch.channels_last)
-    L = O.lib()
-    trees = [O.Tree() for _ in range(n_games)]
-    arr = (C.c_void_p * n_games)(*[t.h for t in trees])
-    side = np.zeros(n_games, dtype=np.int32)
-    rr = np.zeros(n_games, dtype=np.int32)
-    nn_in = np.zeros((n_games, 9, 10, 14), dtype=np.float32)
-    pending = np.zeros(n_games, dtype=np.uint8)
-    p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+def host_cores():
+    """Cores this process may really use: affinity mask, capped by the cgroup CPU quota when there is one."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q[0] != "max":
+            n = max(1, min(n, int(float(q[0]) / float(q[1]) + 0.5)))
+    except Exception:
+        pass
+    return n
 
-    def wave():
-        L.co_batch_select(arr, p(side), p(rr), n_games, playouts, p(nn_in), p(pending), threads)
+
+class CpuArm:
+    """The reference's path on the host cores: the C oracle port (oracle/cchess_oracle.c) drives n_games trees in
+    lock-step (one leaf per game per wave, search_threads=1 semantics) and the same seed-0 network is evaluated by
+    PyTorch on the CPU.  The thread count is calibrated (a few candidates, one wave each) and the best is kept."""
+
+    def __init__(self, n_games, playouts, res_blocks):
+        import ctypes as C
+        from cchess_zero_b200.net import PolicyValueNet
+        from oracle import oracle as O
+        self.C, self.O, self.L = C, O, O.lib()
+        torch.manual_seed(0)
+        self.net = PolicyValueNet(res_blocks).eval().to(memory_format=torch.channels_last)
+        self.B, self.playouts = n_games, playouts
+        self.trees = [O.Tree() for _ in range(n_games)]
+        self.arr = (C.c_void_p * n_games)(*[t.h for t in self.trees])
+        self.side = np.zeros(n_games, dtype=np.int32)
+        self.rr = np.zeros(n_games, dtype=np.int32)
+        self.nn_in = np.zeros((n_games, 9, 10, 14), dtype=np.float32)
+        self.pending = np.zeros(n_games, dtype=np.uint8)
+        self.cores = host_cores()
+        self.threads = self.cores
+        self.calibrate()
+
+    def _p(self, a):
+        return a.ctypes.data_as(self.C.c_void_p)
+
+    def wave(self):
+        L, p = self.L, self._p
+        L.co_batch_select(self.arr, p(self.side), p(self.rr), self.B, self.playouts, p(self.nn_in), p(self.pending), self.threads)
         with torch.no_grad():
-            lo, v = net(torch.from_numpy(nn_in))
+            lo, v = self.net(torch.from_numpy(self.nn_in))
         lo = np.ascontiguousarray(lo.numpy(), dtype=np.float32)
         v = np.ascontiguousarray(v.numpy().reshape(-1), dtype=np.float32)
-        L.co_batch_finish(arr, n_games, p(lo), p(v), p(pending), threads)
+        L.co_batch_finish(self.arr, self.B, p(lo), p(v), p(self.pending), self.threads)
 
-    def expansions():
-        return sum(t.stats()["n_expand"] for t in trees)
-
-    for _ in range(warm_waves):
-        wave()
-    e0, t0, n = expansions(), time.perf_counter(), 0
-    while True:
-        wave(); n += 1
-        if fixed_waves is not None:
-            if n >= fixed_waves:
+    def calibrate(self):
+        cands = sorted({c for c in (self.cores, self.cores // 2, 64, 32, 16, 8) if 1 <= c <= self.cores}, reverse=True)
+        best, best_t = cands[0], None
+        for c in cands:
+            self.threads = c
+            torch.set_num_threads(c)
+            t0 = time.perf_counter(); self.wave(); dt = time.perf_counter() - t0
+            if best_t is None or dt < best_t:
+                best, best_t = c, dt
+            if best_t is not None and dt > 3 * best_t:
                 break
-        elif time.perf_counter() - t0 >= seconds:
-            break
-    dt = time.perf_counter() - t0
-    ex = expansions() - e0
-    return dict(value=ex / dt, seconds=dt, waves=n, expansions=ex)
+        self.threads = best
+        torch.set_num_threads(best)
+
+    def expansions(self):
+        return sum(t.stats()["n_expand"] for t in self.trees)
+
+    def run(self, seconds=None, waves=None):
+        e0, t0, n = self.expansions(), time.perf_counter(), 0
+        while True:
+            self.wave(); n += 1
+            if (waves is not None and n >= waves) or (waves is None and time.perf_counter() - t0 >= seconds):
+                break
+        dt = time.perf_counter() - t0
+        return dict(value=(self.expansions() - e0) / dt, seconds=dt, waves=n)
 
 
 def run_reference(a, rank, world):
-    """--impl reference: rank 0 times the CPU arm, other ranks exit 0."""
+    """--impl reference: rank 0 times the CPU arm (oracle port; the Python reference cannot travel), other ranks exit 0."""
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
     waves_per_step = max(1, int(os.environ.get("CCHESS_REF_WAVES_PER_STEP", "4")))
-    r = None
-    t_steps = []
-    # one persistent set of trees: warm-up steps then timed steps, each step = waves_per_step waves
-    import ctypes as C
-    from cchess_zero_b200.net import PolicyValueNet
-    from oracle import oracle as O
-    torch.set_num_threads(threads)
-    torch.manual_seed(0)
-    net = PolicyValueNet(a.res_blocks).eval().to(memory_format=torch.channels_last)
-    L = O.lib()
-    B = a.games
-    trees = [O.Tree() for _ in range(B)]
-    arr = (C.c_void_p * B)(*[t.h for t in trees])
-    side = np.zeros(B, dtype=np.int32); rr = np.zeros(B, dtype=np.int32)
-    nn_in = np.zeros((B, 9, 10, 14), dtype=np.float32); pending = np.zeros(B, dtype=np.uint8)
-    p = lambda x: x.ctypes.data_as(C.c_void_p)  # noqa: E731
-
-    def wave():
-        L.co_batch_select(arr, p(side), p(rr), B, a.playouts, p(nn_in), p(pending), threads)
-        with torch.no_grad():
-            lo, v = net(torch.from_numpy(nn_in))
-        lo = np.ascontiguousarray(lo.numpy(), dtype=np.float32)
-        v = np.ascontiguousarray(v.numpy().reshape(-1), dtype=np.float32)
-        L.co_batch_finish(arr, B, p(lo), p(v), p(pending), threads)
-
-    def expansions():
-        return sum(t.stats()["n_expand"] for t in trees)
-
-    for _ in range(a.warmup * waves_per_step):
-        wave()
-    e0, t0 = expansions(), time.perf_counter()
-    for _ in range(a.steps * waves_per_step):
-        wave()
-    dt = time.perf_counter() - t0
-    ex = expansions() - e0
-    v = ex / dt
-    sample = "%d games x %d lock-step waves per step (first waves of the %d-playout search from the start position), oracle C port + torch CPU fp32 net" % (
-        B, waves_per_step, a.playouts)
+    arm = CpuArm(a.games, a.playouts, a.res_blocks)
+    arm.run(waves=max(1, a.warmup * waves_per_step))
+    r = arm.run(waves=a.steps * waves_per_step)
+    v = r["value"]
+    sample = "%d games x %d lock-step waves per step (first waves of the %d-playout search from the start position), oracle C port + torch CPU fp32 net, %d threads of %d usable cores" % (
+        a.games, waves_per_step, a.playouts, arm.threads, arm.cores)
     line = dict(metric=METRIC, value=v, unit="expansions/s", n_gpus=a.gpus, steps=a.steps, warmup=a.warmup,
-                ms_per_step=dt / a.steps * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                ms_per_step=r["seconds"] / a.steps * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
                 data="synthetic", impl="reference",
-                config=dict(workload="%d concurrent self-play games x %d playouts, res_block_nums=%d" % (B, a.playouts, a.res_blocks),
-                            games_per_gpu=B, playouts=a.playouts, res_block_nums=a.res_blocks),
-                cpu_baseline=dict(value=v, unit="expansions/s", cores=threads, kind="port", sample=sample),
+                config=dict(workload="%d concurrent self-play games x %d playouts, res_block_nums=%d" % (a.games, a.playouts, a.res_blocks),
+                            games_per_gpu=a.games, playouts=a.playouts, res_block_nums=a.res_blocks),
+                cpu_baseline=dict(value=v, unit="expansions/s", cores=arm.threads, kind="port", sample=sample),
                 e2e=dict(value=v, unit="expansions/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line), flush=True)
 
@@ -313,11 +309,11 @@ def run_ours(a, rank, world, local_rank):
                     bytes_per_expansion=ab / max(1, d["n_expand"]), launches_timed=len(kms),
                     note="latency-bound pointer-chasing kernel: HBM fraction is reported as required, the binding limits are per-warp dependent loads and the network")
         if not a.no_cpu_baseline:
-            threads = os.cpu_count() or 1
-            r = cpu_reference(min(B, 256), a.playouts, a.res_blocks, a.cpu_seconds, threads)
-            cpu = dict(value=r["value"], unit="expansions/s", cores=threads, kind="port",
-                       sample="%d games x %d lock-step waves (%.1f s) from the start position, oracle C port + torch CPU fp32 net, %d threads" % (
-                           min(B, 256), r["waves"], r["seconds"], threads))
+            arm = CpuArm(min(B, 256), a.playouts, a.res_blocks)
+            r = arm.run(seconds=a.cpu_seconds)
+            cpu = dict(value=r["value"], unit="expansions/s", cores=arm.threads, kind="port",
+                       sample="%d games x %d lock-step waves (%.1f s) from the start position, oracle C port + torch CPU fp32 net, %d threads (calibrated) of %d usable cores" % (
+                           min(B, 256), r["waves"], r["seconds"], arm.threads, arm.cores))
 
     if rank == 0:
         value = tot_exp / (dev_ms * 1e-3)
