@@ -19,7 +19,7 @@
 namespace {
 
 // ------------------------------------------------------------------------------------------
-// first convolution from board bytes: one CTA per position, one warp per output cell (128 channels, 4 per lane)
+// first convolution from board bytes: one CTA per position, a half-warp per output cell (128 channels, 8 per lane)
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_first_conv(const uint8_t *__restrict__ boards, int B, const __half *__restrict__ w /* [9][14][128] */,
                                                      const float4 *__restrict__ bias /* [32] */, __half *__restrict__ out /* [B][90][128] */) {
@@ -31,30 +31,33 @@ __global__ void __launch_bounds__(256) k_first_conv(const uint8_t *__restrict__ 
         pb[threadIdx.x] = (r >= 0 && r < 9 && f >= 0 && f < 10) ? bd[r * 9 + f] : (uint8_t)0;   // the reference's cell <- s[rank*9+file]
     }
     __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const float4 bv = bias[lane];
-    for (int cell = warp; cell < 90; cell += 8) {
+    const int hw = threadIdx.x >> 4, l16 = threadIdx.x & 15;   // 16 half-warps, lane owns channels 8*l16 .. 8*l16+7
+    const float4 b0 = bias[l16 * 2], b1 = bias[l16 * 2 + 1];
+    for (int cell = hw; cell < 90; cell += 16) {
         const int r = cell / 10, f = cell - r * 10;
         const uint8_t *c0 = pb + r * 12 + f;          // top-left of the 3x3 window
         int pc[9];
 #pragma unroll
         for (int t = 0; t < 9; t++) pc[t] = c0[(t / 3) * 12 + (t % 3)];
-        float4 acc = bv;
+        float acc[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
         for (int t = 0; t < 9; t++) {
             if (pc[t]) {
-                const uint2 raw = __ldg(reinterpret_cast<const uint2 *>(w + ((size_t)(t * 14 + pc[t] - 1) * 128 + lane * 4)));
-                const float2 lo = __half22float2(*reinterpret_cast<const __half2 *>(&raw.x));
-                const float2 hi = __half22float2(*reinterpret_cast<const __half2 *>(&raw.y));
-                acc.x += lo.x; acc.y += lo.y; acc.z += hi.x; acc.w += hi.y;
+                const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(w + ((size_t)(t * 14 + pc[t] - 1) * 128 + l16 * 8)));
+                const __half2 *h2 = reinterpret_cast<const __half2 *>(&raw);
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const float2 v = __half22float2(h2[k]);
+                    acc[2 * k] += v.x;
+                    acc[2 * k + 1] += v.y;
+                }
             }
         }
-        const __half2 o0 = __floats2half2_rn(fmaxf(acc.x, 0.f), fmaxf(acc.y, 0.f));
-        const __half2 o1 = __floats2half2_rn(fmaxf(acc.z, 0.f), fmaxf(acc.w, 0.f));
-        uint2 o;
-        o.x = *reinterpret_cast<const uint32_t *>(&o0);
-        o.y = *reinterpret_cast<const uint32_t *>(&o1);
-        *reinterpret_cast<uint2 *>(out + ((size_t)pos * 90 + cell) * 128 + lane * 4) = o;
+        uint4 o;
+        __half2 *oh = reinterpret_cast<__half2 *>(&o);
+#pragma unroll
+        for (int k = 0; k < 4; k++) oh[k] = __floats2half2_rn(fmaxf(acc[2 * k], 0.f), fmaxf(acc[2 * k + 1], 0.f));
+        *reinterpret_cast<uint4 *>(out + ((size_t)pos * 90 + cell) * 128 + l16 * 8) = o;
     }
 }
 
@@ -106,8 +109,8 @@ __global__ void __launch_bounds__(256) k_head_conv(const __half *__restrict__ x 
     if (threadIdx.x < 12) hp[(size_t)pos * 192 + 180 + threadIdx.x] = __float2half(0.f);   // K padding of the policy GEMM
 }
 
-// heads, stage 2a: value MLP 90 -> 256 ReLU -> 1 tanh (policy_value_network.py:73-74), 16 positions per CTA
-constexpr int VM_POS = 16;
+// heads, stage 2a: value MLP 90 -> 256 ReLU -> 1 tanh (policy_value_network.py:73-74), 4 positions per CTA
+constexpr int VM_POS = 4;
 __global__ void __launch_bounds__(256) k_value_mlp(const float *__restrict__ hv /* [B][96] */, int B, const float *__restrict__ w1t /* [90][256] */,
                                                     const float *__restrict__ b1, const float *__restrict__ w2, float b2, float *__restrict__ value) {
     __shared__ float sh[VM_POS][96];
@@ -122,10 +125,15 @@ __global__ void __launch_bounds__(256) k_value_mlp(const float *__restrict__ hv 
     const float bb = b1[t];
 #pragma unroll
     for (int p = 0; p < VM_POS; p++) a[p] = bb;
-    for (int k = 0; k < 90; k++) {
-        const float wv = __ldg(w1t + k * 256 + t);
+#pragma unroll 1
+    for (int k0 = 0; k0 < 90; k0 += 10) {
+        float wv[10];
 #pragma unroll
-        for (int p = 0; p < VM_POS; p++) a[p] += wv * sh[p][k];
+        for (int j = 0; j < 10; j++) wv[j] = __ldg(w1t + (k0 + j) * 256 + t);   // 10 independent coalesced loads in flight
+#pragma unroll
+        for (int j = 0; j < 10; j++)
+#pragma unroll
+            for (int p = 0; p < VM_POS; p++) a[p] += wv[j] * sh[p][k0 + j];
     }
     const float w2v = w2[t];
 #pragma unroll
