@@ -63,11 +63,20 @@ class MCTS_tree(object):
         self.search_threads = search_threads
         self.engine = Engine(1, arena_words)
         dev = torch.device("cuda", self.engine.device)
-        self._dev_forward = getattr(getattr(in_forward, "__self__", None), "forward_device", None)
-        dt = getattr(getattr(in_forward, "__self__", None), "nn_dtype", torch.float32) if self._dev_forward else torch.float32
-        self._nn_in = torch.zeros((1, 9, 10, 14), dtype=dt, device=dev)
+        owner = getattr(in_forward, "__self__", None)
         self._logits = torch.zeros((1, NLABEL), dtype=torch.float32, device=dev)
         self._value = torch.zeros((1,), dtype=torch.float32, device=dev)
+        self._plan = self._graph = None
+        if owner is not None and hasattr(owner, "native_plan") and getattr(owner, "precision", "") == "fp16":
+            # the evaluator is this package's network: stay on the device (board bytes -> cz_net kernels -> tower) and
+            # replay one CUDA graph per playout
+            self._plan = owner.native_plan(1)
+            self._nn_in = self._plan.make_input(1)
+            self._dev_forward = lambda x, lo, v: self._plan(x, lo, v)
+        else:
+            self._dev_forward = getattr(owner, "forward_device", None)
+            dt = getattr(owner, "nn_dtype", torch.float32) if self._dev_forward else torch.float32
+            self._nn_in = torch.zeros((1, 9, 10, 14), dtype=dt, device=dev)
         self._h_in = torch.zeros((1, 9, 10, 14), dtype=torch.float32).pin_memory()
         self._h_logits = torch.zeros((1, NLABEL), dtype=torch.float32).pin_memory()
         self._h_value = torch.zeros((1,), dtype=torch.float32).pin_memory()
@@ -132,9 +141,38 @@ class MCTS_tree(object):
         if side != self._side or restrict_round != self._rr:
             self.engine.set_root_meta([side], [restrict_round])
             self._side, self._rr = side, restrict_round
-        self.engine.search(self._eval, playouts, self._nn_in, self._logits, self._value)
+        if self._plan is not None:
+            self._search_graph(playouts)
+        else:
+            self.engine.search(self._eval, playouts, self._nn_in, self._logits, self._value)
         self.engine.raise_on_error()
         self._cache = None
+
+    def _search_graph(self, playouts):
+        if self._graph is None:
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                for _ in range(3):
+                    self._plan(self._nn_in, self._logits, self._value)
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.engine.wave(self._nn_in, self._logits, self._value)
+                self._plan(self._nn_in, self._logits, self._value)
+            self._graph = g
+        self.engine.begin_search(playouts)
+        waves = 0
+        while True:
+            self._graph.replay()
+            self.engine.launches += 1
+            waves += 1
+            if waves > playouts and self.engine.unfinished() == 0:
+                break
+            if waves > 4 * playouts + 64:
+                self.engine.raise_on_error()
+                raise RuntimeError("search did not converge")
 
     def generate_inputs(self, in_state, current_player):  # main.py:531-533
         return rules.encode_batch(rules.state_to_board(in_state)[None], [rules.side_of(current_player)])[0]

@@ -32,19 +32,78 @@ def _flip_move_label_index(mv):
     return rules.label2i[rules.move_to_label(s | (d << 7))]
 
 
+_LABEL_OF = None
+
+
+def _label_table():
+    """(src_sq, dst_sq) -> label index as a numpy table (cz_label_index); -1 where the pair is not a label."""
+    global _LABEL_OF
+    if _LABEL_OF is None:
+        from ._lib import lib
+        L = lib()
+        _LABEL_OF = np.array([[L.cz_label_index(s, d) for d in range(90)] for s in range(90)], dtype=np.int64)
+    return _LABEL_OF
+
+
 class GameRecord:
-    """(s, pi, z) tuples of one finished game in the reference's format (selfplay, main.py:1493-1554)."""
+    """(s, pi, z) tuples of one finished game in the reference's format (selfplay, main.py:1493-1554).
+
+    During play only raw per-ply data is appended (board bytes, side, moves, probs); the canonical state strings and
+    label indices are materialised on first access, vectorised per game."""
 
     def __init__(self):
-        self.states, self.pi_idx, self.pi_val, self.players, self.actions, self.visits = [], [], [], [], [], []
+        self._boards, self._moves, self.pi_val, self.players, self._chosen, self.visits = [], [], [], [], [], []
         self.z = None
         self.winner = None
+        self._states = self._pi_idx = self._actions = None
 
     def __len__(self):
-        return len(self.states)
+        return len(self.players)
+
+    def _materialise(self):
+        if self._states is not None and len(self._states) == len(self.players):
+            return
+        tab = _label_table()
+        st, ix = [], []
+        for b, side, mv in zip(self._boards, self.players, self._moves):
+            st.append(rules.board_to_state(_flip_board(b) if side == 1 else b))             # main.py:1504-1505
+            src, dst = (mv & 127).astype(np.int64), (mv >> 7).astype(np.int64)
+            if side == 1:   # flipped_uci_labels for black (main.py:1507-1512): rank y -> 9-y
+                src = (9 - src // 9) * 9 + src % 9
+                dst = (9 - dst // 9) * 9 + dst % 9
+            li = tab[src, dst]
+            if (li < 0).any():
+                raise KeyError("move outside the label table")                                # label2i[...] KeyError in the reference
+            ix.append(li)
+        self._states, self._pi_idx = st, ix
+        self._actions = [rules.move_to_label(mv[c]) for mv, c in zip(self._moves, self._chosen)]
+
+    @classmethod
+    def from_tuples(cls, states, pi_idx, pi_val, z):
+        """A record built from already materialised tuples (tests, gathered data)."""
+        r = cls()
+        r._states, r._pi_idx, r.pi_val, r.z = list(states), list(pi_idx), list(pi_val), z
+        r.players = [0] * len(r._states)
+        r._boards = [None] * len(r._states)
+        return r
+
+    @property
+    def states(self):
+        self._materialise()
+        return self._states
+
+    @property
+    def pi_idx(self):
+        self._materialise()
+        return self._pi_idx
+
+    @property
+    def actions(self):
+        self._materialise()
+        return self._actions
 
     def dense_pi(self):
-        out = np.zeros((len(self.states), NLABEL))
+        out = np.zeros((len(self), NLABEL))
         for i, (ix, v) in enumerate(zip(self.pi_idx, self.pi_val)):
             out[i, ix] = v
         return out
@@ -181,7 +240,14 @@ class SelfPlay:
         self.plies = 0
         self.waves = 0
         self.graph = None
+        self._alphas = {}
         rules._init_tables()
+
+    def _alpha(self, n):
+        a = self._alphas.get(n)
+        if a is None:
+            a = self._alphas[n] = 0.3 * np.ones(n)
+        return a
 
     # -- evaluation step ---------------------------------------------------------------------
     def _eval(self, nn_in):
@@ -298,39 +364,45 @@ class SelfPlay:
         rc = e.root_children(want_wpq=True)
         choice = np.full(self.B, -1, dtype=np.int32)
         win_rate = np.zeros(self.B, dtype=np.float32)
+        live = np.nonzero(self.live)[0]
+        if (rc["n"][live] <= 0).any():
+            e.raise_on_error()
+            raise EngineError("game %d has no root children" % int(live[np.argmax(rc["n"][live] <= 0)]))
         with np.errstate(divide="ignore", invalid="ignore"):
-            for g in np.nonzero(self.live)[0]:
+            # softmax(1/T * log(visits)) of main.py:1341, 1111-1116.  log / exp / max are element-wise or exact, so they are
+            # taken over the whole [B,128] batch at once (padding: visits 0 -> -inf -> exp 0); the order-sensitive row sum
+            # and the RNG draws stay per game, on slices of exactly n entries, as the reference computes them.
+            lv = (1.0 / self.temperature) * np.log(rc["visits"].astype(np.int64))
+            valid = np.arange(MAXCHILD)[None, :] < rc["n"][:, None]
+            lv[~valid] = -np.inf
+            ex = np.exp(lv - np.max(lv, axis=1, keepdims=True))
+            for g in live:
                 n = int(rc["n"][g])
-                if n <= 0:
-                    e.raise_on_error()
-                    raise EngineError("game %d has no root children" % g)
-                visits = rc["visits"][g, :n].astype(np.int64)
-                probs = rules.softmax(1.0 / self.temperature * np.log(visits))        # main.py:1341
+                probs = ex[g, :n].copy()
+                probs /= np.sum(probs)
                 rs = self.rs[g]
-                if self.exploration:                                                     # main.py:1345-1348
-                    p = 0.75 * probs + 0.25 * rs.dirichlet(0.3 * np.ones(len(probs)))
+                if self.exploration:                                                     # main.py:1345-1346
+                    p = 0.75 * probs + 0.25 * rs.dirichlet(self._alpha(n))
                 else:
                     p = probs
-                idx = int(rs.choice(n, p=p))
-                choice[g] = idx
-                win_rate[g] = rc["q"][g, idx]                                            # mcts.Q(act), main.py:1350
-                if self.keep_records:
-                    rec = self.records[g]
-                    mv = rc["moves"][g, :n]
-                    black = self.sides[g] == 1
-                    sb = _flip_board(self.boards[g]) if black else self.boards[g]
-                    rec.states.append(rules.board_to_state(sb))                           # main.py:1504-1505
-                    if black:
-                        ix = np.fromiter((_flip_move_label_index(m) for m in mv), dtype=np.int64, count=n)
-                    else:
-                        ix = np.fromiter((rules.label2i[rules.move_to_label(m)] for m in mv), dtype=np.int64, count=n)
-                    rec.pi_idx.append(ix)
-                    rec.pi_val.append(probs)
-                    rec.players.append(int(self.sides[g]))
-                    rec.actions.append(rules.move_to_label(mv[idx]))
-                    rec.visits.append(visits)
+                # np.random.choice(actions, p=p) (main.py:1346-1348): cdf = p.cumsum(); cdf /= cdf[-1];
+                # idx = cdf.searchsorted(random_sample(), side='right') -- numpy's legacy algorithm, same draws
+                cdf = np.cumsum(p)
+                if not (cdf[-1] == cdf[-1]) or abs(cdf[-1] - 1.0) > 1.5e-8 * max(1.0, n) or p.min() < 0:
+                    idx = int(rs.choice(n, p=p))          # let numpy raise exactly what the reference would raise
                 else:
-                    self.records[g].players.append(int(self.sides[g]))
+                    cdf /= cdf[-1]
+                    idx = int(cdf.searchsorted(rs.random_sample(), side="right"))
+                choice[g] = idx
+                rec = self.records[g]
+                rec.players.append(int(self.sides[g]))
+                if self.keep_records:
+                    rec._boards.append(self.boards[g].copy())
+                    rec._moves.append(rc["moves"][g, :n].copy())
+                    rec.pi_val.append(probs)
+                    rec._chosen.append(idx)
+                    rec.visits.append(rc["visits"][g, :n].copy())
+            win_rate[live] = rc["q"][live, choice[live]]                                # mcts.Q(act), main.py:1350
         e.play(choice)
         st = e.status(boards=True)
         self.boards, self.sides = st["boards"], st["side"]

@@ -202,3 +202,26 @@ def test_selfplay_native_plan_board_mode(tmp_path, monkeypatch):
         sp2.step()
     # same seeds + (numerically close) network: the opening plies normally coincide; at least the engines agree on ply counts
     assert (sp.engine.status()["ply"] == sp2.engine.status()["ply"]).all()
+
+
+def test_mcts_tree_with_package_network_and_move_latency(tmp_path, monkeypatch):
+    """BASELINE config 5 shape: one tree, the package's own network, select_move('mcts') for both sides."""
+    monkeypatch.chdir(tmp_path)
+    import contextlib, io, time
+    from cchess_zero_b200.net import policy_value_network
+    from cchess_zero_b200.selfplay import cchess_main
+    pv = policy_value_network(res_block_nums=7)
+    m = cchess_main(playout=200, in_search_threads=16, network=pv, exploration=False, log_file=False)
+    np.random.seed(0)
+    lat = []
+    with contextlib.redirect_stdout(io.StringIO()):
+        for _ in range(4):
+            t0 = time.perf_counter()
+            (sx, sy, dx, dy), win = m.select_move("mcts")
+            lat.append(time.perf_counter() - t0)
+            assert 0 <= sx < 9 and 0 <= sy < 10 and -1 <= float(win) <= 1
+    visits = [n.N for n in m.mcts.root.child.values()]
+    assert m.game_borad.round == 5 and m.game_borad.current_player == "w"
+    assert sum(visits) <= 200 + m.mcts.root.N
+    print("move latency (200 playouts, 7 blocks): %s" % ["%.3f" % x for x in lat])
+    assert min(lat) < 5.0

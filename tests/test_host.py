@@ -76,11 +76,8 @@ def test_flip_helpers_and_record_packing():
         assert _flip_move_label_index(mv) == rules.label2i[O.flip_label(m)]
     with np.errstate(all="ignore"):
         g = O.selfplay_game("hash_pos", 12, np.random.RandomState(4))
-    rec = GameRecord()
-    rec.states, rec.z = g["states"], g["z"]
-    for p in g["pis"]:
-        ix = np.nonzero(p)[0]
-        rec.pi_idx.append(ix); rec.pi_val.append(p[ix])
+    nz = [np.nonzero(p)[0] for p in g["pis"]]
+    rec = GameRecord.from_tuples(g["states"], nz, [p[ix] for p, ix in zip(g["pis"], nz)], g["z"])
     buf, k, left = pack_records([rec], 4096)
     assert k == len(g["states"]) and not left
     back = unpack_records(buf, k)
@@ -103,10 +100,8 @@ rank, world = dist.get_rank(), dist.get_world_size()
 def game(seed):
     with np.errstate(all="ignore"):
         g = O.selfplay_game("hash_pos", 10, np.random.RandomState(seed))
-    r = GameRecord(); r.states, r.z = g["states"], g["z"]
-    for p in g["pis"]:
-        ix = np.nonzero(p)[0]; r.pi_idx.append(ix); r.pi_val.append(p[ix])
-    return g, r
+    nz = [np.nonzero(p)[0] for p in g["pis"]]
+    return g, GameRecord.from_tuples(g["states"], nz, [p[ix] for p, ix in zip(g["pis"], nz)], g["z"])
 mine = [game(100 + rank * 2 + i) for i in range(2 if rank == 0 else 1)]     # ragged: rank 0 two games, rank 1 one
 out = all_gather_tuples([r for _, r in mine], torch.device("cpu"), cap=1024)
 exp = []
