@@ -305,7 +305,8 @@ def run_ours(a, rank, world, local_rank):
         avg_ms = float(np.mean(kms))
         achieved = per_launch / (avg_ms * 1e-3) / 1e9
         roof = dict(kernel="k_wave (expand+backup+select+encode, one warp per game; %d games per launch)" % (B // a.lanes), bound="hbm", achieved=achieved, peak=hbm, unit="GB/s",
-                    frac=achieved / hbm, traffic=None, peak_source=peak_src, avg_launch_ms=avg_ms, algorithmic_bytes_per_launch=per_launch,
+                    frac=achieved / hbm, traffic=None, peak_source=peak_src, avg_launch_ms=avg_ms, p50_launch_ms=float(np.median(kms)), max_launch_ms=float(np.max(kms)),
+                    algorithmic_bytes_per_launch=per_launch,
                     bytes_per_expansion=ab / max(1, d["n_expand"]), launches_timed=len(kms),
                     note="latency-bound pointer-chasing kernel: HBM fraction is reported as required, the binding limits are per-warp dependent loads and the network")
         if not a.no_cpu_baseline:

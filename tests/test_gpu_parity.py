@@ -264,3 +264,51 @@ def test_two_lane_pipeline_is_bit_exact_vs_oracle(O, R):
                 r = O.selfplay_game(net, playouts, np.random.RandomState(500 + slot))
             assert rec.states == r["states"], (graph, slot)
             assert np.array_equal(rec.dense_pi(), r["pis"]) and np.array_equal(rec.z, r["z"])
+
+
+def test_full_size_1024_games_1200_playouts_properties_and_samples(O, R):
+    """BASELINE configs[1] size (1024 games x 1200 playouts).  Size-independent properties on every game, bit-exact
+    comparison with the oracle on a sample of games, determinism (duplicate seeds -> identical trees)."""
+    from cchess_zero_b200.fakenet import FakeNet
+    from cchess_zero_b200.selfplay import SelfPlay
+    B, P, net = 1024, 1200, "hash_pos"
+    seeds = [9000 + (g % 512) for g in range(B)]          # game g and g+512 share a seed
+    sp = SelfPlay(B, FakeNet(net), P, seeds=seeds, auto_reset=False)
+    sp.capture_graph()
+    e = sp.engine
+    # ply 1
+    sp.search()
+    rc1 = e.root_children()
+    assert (rc1["n"] == 44).all()                                     # 44 pseudo-legal moves at the start position
+    assert (rc1["visits"].sum(axis=1) == P).all()                     # root.N is never incremented, every playout passes a child
+    sig0 = e.tree_signature(0)
+    for g in (1, 511, 512, 1023):
+        assert np.array_equal(e.tree_signature(g), sig0)              # same position, same net -> same tree, any slot
+    t = O.Tree()
+    assert t.search(0, 0, P, net) == 0
+    assert np.array_equal(t.signature(), sig0)                        # ... and it is the oracle's tree, bit for bit
+    out = sp.step.__func__  # noqa: F841  (documented: step() = search + move choice; we already searched, so choose by hand)
+    choice = np.array([int(np.random.RandomState(s).randint(44)) for s in seeds], dtype=np.int32)
+    N_chosen = rc1["visits"][np.arange(B), choice]
+    e.play(choice)
+    # ply 2 (tree re-use): children of the new root keep their statistics, then P more playouts are added
+    sp.boards, sp.sides = e.status()["boards"], e.status()["side"]
+    sp.search()
+    rc2 = e.root_children()
+    tot = rc2["visits"][np.arange(128)[None, :] < rc2["n"][:, None]].reshape(-1) if False else np.array(
+        [rc2["visits"][g, : rc2["n"][g]].sum() for g in range(B)])
+    expect = np.where(N_chosen > 0, N_chosen - 1 + P, P)              # first visit of a node expands it, the rest descend
+    assert np.array_equal(tot, expect)
+    for g in range(0, 512, 37):
+        assert choice[g] == choice[g + 512]
+        assert np.array_equal(e.tree_signature(g), e.tree_signature(g + 512))
+    for g in (3, 77, 300):                                            # oracle replay of the same two plies
+        t = O.Tree()
+        t.search(0, 0, P, net)
+        t.update(int(choice[g]))
+        b, cap = O.apply_move(O.from_state(O.START), int(rc1["moves"][g, choice[g]]))
+        assert np.array_equal(t.root_board(), b)
+        t.search(1, 1 if cap == 0 else 0, P, net)
+        assert np.array_equal(t.signature(), e.tree_signature(g)), g
+    c = e.raise_on_error()
+    assert c["n_playout"] == 2 * B * P
