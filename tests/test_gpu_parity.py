@@ -287,7 +287,7 @@ def test_full_size_1024_games_1200_playouts_properties_and_samples(O, R):
     t = O.Tree()
     assert t.search(0, 0, P, net) == 0
     assert np.array_equal(t.signature(), sig0)                        # ... and it is the oracle's tree, bit for bit
-    out = sp.step.__func__  # noqa: F841  (documented: step() = search + move choice; we already searched, so choose by hand)
+    # step() = search + host move choice; the search is done, choose the moves by hand (any legal child will do)
     choice = np.array([int(np.random.RandomState(s).randint(44)) for s in seeds], dtype=np.int32)
     N_chosen = rc1["visits"][np.arange(B), choice]
     e.play(choice)
@@ -295,8 +295,7 @@ def test_full_size_1024_games_1200_playouts_properties_and_samples(O, R):
     sp.boards, sp.sides = e.status()["boards"], e.status()["side"]
     sp.search()
     rc2 = e.root_children()
-    tot = rc2["visits"][np.arange(128)[None, :] < rc2["n"][:, None]].reshape(-1) if False else np.array(
-        [rc2["visits"][g, : rc2["n"][g]].sum() for g in range(B)])
+    tot = np.array([rc2["visits"][g, : rc2["n"][g]].sum() for g in range(B)])
     expect = np.where(N_chosen > 0, N_chosen - 1 + P, P)              # first visit of a node expands it, the rest descend
     assert np.array_equal(tot, expect)
     for g in range(0, 512, 37):
