@@ -129,7 +129,7 @@ class CpuArm:
     lock-step (one leaf per game per wave, search_threads=1 semantics) and the same seed-0 network is evaluated by
     PyTorch on the CPU.  The thread count is calibrated (a few candidates, one wave each) and the best is kept."""
 
-    def __init__(self, n_games, playouts, res_blocks):
+    def __init__(self, n_games, playouts, res_blocks, threads=None):
         import ctypes as C
         from cchess_zero_b200.net import PolicyValueNet
         from oracle import oracle as O
@@ -144,8 +144,12 @@ class CpuArm:
         self.nn_in = np.zeros((n_games, 9, 10, 14), dtype=np.float32)
         self.pending = np.zeros(n_games, dtype=np.uint8)
         self.cores = host_cores()
-        self.threads = self.cores
-        self.calibrate()
+        self.wave_s = None
+        if threads is None:
+            self.calibrate()
+        else:
+            self.threads = threads
+            torch.set_num_threads(threads)
 
     def _p(self, a):
         return a.ctypes.data_as(self.C.c_void_p)
@@ -168,9 +172,7 @@ class CpuArm:
             t0 = time.perf_counter(); self.wave(); dt = time.perf_counter() - t0
             if best_t is None or dt < best_t:
                 best, best_t = c, dt
-            if best_t is not None and dt > 3 * best_t:
-                break
-        self.threads = best
+        self.threads, self.wave_s = best, best_t
         torch.set_num_threads(best)
 
     def expansions(self):
@@ -186,17 +188,34 @@ class CpuArm:
         return dict(value=(self.expansions() - e0) / dt, seconds=dt, waves=n)
 
 
+def sized_cpu_arm(max_games, playouts, res_blocks, wave_budget_s):
+    """Probe with 64 games (also calibrates the thread count), then size the sample so that one lock-step wave of the
+    sample costs about wave_budget_s on this host.  Keeps every CPU leg bounded whatever the box's core count is."""
+    probe = CpuArm(min(64, max_games), playouts, res_blocks)
+    per_game = max(probe.wave_s, 1e-4) / probe.B
+    n = int(min(max_games, max(32, wave_budget_s / per_game)))
+    n = 1 << (n.bit_length() - 1)                                   # power of two <= n
+    if n <= probe.B:
+        return probe
+    return CpuArm(min(n, max_games), playouts, res_blocks, threads=probe.threads)
+
+
 def run_reference(a, rank, world):
-    """--impl reference: rank 0 times the CPU arm (oracle port; the Python reference cannot travel), other ranks exit 0."""
+    """--impl reference: rank 0 times the CPU arm (oracle port; the Python reference cannot travel), other ranks exit 0.
+    Each step is a bounded sample of the workload: `waves_per_step` lock-step waves of a sample of the games, the sample
+    sized so that the whole --steps/--warmup run takes about two minutes."""
     if rank != 0:
         return
-    waves_per_step = max(1, int(os.environ.get("CCHESS_REF_WAVES_PER_STEP", "4")))
-    arm = CpuArm(a.games, a.playouts, a.res_blocks)
-    arm.run(waves=max(1, a.warmup * waves_per_step))
+    waves_per_step = max(1, int(os.environ.get("CCHESS_REF_WAVES_PER_STEP", "2")))
+    total_budget = float(os.environ.get("CCHESS_REF_SECONDS", "120"))
+    wave_budget = total_budget / max(1, (a.steps + a.warmup) * waves_per_step)
+    arm = sized_cpu_arm(a.games, a.playouts, a.res_blocks, wave_budget)
+    if a.warmup:
+        arm.run(waves=a.warmup * waves_per_step)
     r = arm.run(waves=a.steps * waves_per_step)
     v = r["value"]
-    sample = "%d games x %d lock-step waves per step (first waves of the %d-playout search from the start position), oracle C port + torch CPU fp32 net, %d threads of %d usable cores" % (
-        a.games, waves_per_step, a.playouts, arm.threads, arm.cores)
+    sample = "%d of the %d games x %d lock-step waves per step (first waves of the %d-playout search from the start position), oracle C port + torch CPU fp32 net, %d threads (calibrated) of %d usable cores" % (
+        arm.B, a.games, waves_per_step, a.playouts, arm.threads, arm.cores)
     line = dict(metric=METRIC, value=v, unit="expansions/s", n_gpus=a.gpus, steps=a.steps, warmup=a.warmup,
                 ms_per_step=r["seconds"] / a.steps * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
                 data="synthetic", impl="reference",
@@ -310,11 +329,11 @@ def run_ours(a, rank, world, local_rank):
                     bytes_per_expansion=ab / max(1, d["n_expand"]), launches_timed=len(kms),
                     note="latency-bound pointer-chasing kernel: HBM fraction is reported as required, the binding limits are per-warp dependent loads and the network")
         if not a.no_cpu_baseline:
-            arm = CpuArm(min(B, 256), a.playouts, a.res_blocks)
+            arm = sized_cpu_arm(B, a.playouts, a.res_blocks, wave_budget_s=a.cpu_seconds / 5.0)
             r = arm.run(seconds=a.cpu_seconds)
             cpu = dict(value=r["value"], unit="expansions/s", cores=arm.threads, kind="port",
-                       sample="%d games x %d lock-step waves (%.1f s) from the start position, oracle C port + torch CPU fp32 net, %d threads (calibrated) of %d usable cores" % (
-                           min(B, 256), r["waves"], r["seconds"], arm.threads, arm.cores))
+                       sample="%d of the %d games x %d lock-step waves (%.1f s) from the start position, oracle C port + torch CPU fp32 net, %d threads (calibrated) of %d usable cores" % (
+                           arm.B, B, r["waves"], r["seconds"], arm.threads, arm.cores))
 
     if rank == 0:
         value = tot_exp / (dev_ms * 1e-3)

@@ -184,7 +184,8 @@ __device__ bool warp_expand(const Dev &E, int g, uint32_t *ar, WarpSmem &S, cons
         if (errf & (CZ_ERR_ARENA | CZ_ERR_NOMOVES)) return false;
     }
     float tot = 1e-8f;  // tot_p = 1e-8 accumulated in float32, in move order (main.py:176, 184)
-    for (int i = 0; i < n; i++) tot = __fadd_rn(tot, S.ps[i]);
+#pragma unroll 8
+    for (int i = 0; i < n; i++) tot = __fadd_rn(tot, S.ps[i]);   // strictly serial adds; unrolled so the LDS latency overlaps
     uint32_t *blk = ar + base;
     if (lane < HDR) blk[lane] = lane == 0 ? (uint32_t)n : 0u;
     for (int i = lane; i < (int)cs; i += 32) {

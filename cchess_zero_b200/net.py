@@ -120,6 +120,8 @@ class InferencePlan:
             self.v_fc1 = (net.v_fc1.weight.detach().float().contiguous(), net.v_fc1.bias.detach().float().contiguous())
             self.v_fc2 = (net.v_fc2.weight.detach().float().contiguous(), net.v_fc2.bias.detach().float().contiguous())
         self.fused = bool(fused) and self._probe_fused()
+        if os.environ.get("CCHESS_CUDNN_BENCHMARK", "0") == "1":
+            torch.backends.cudnn.benchmark = True     # let cuDNN time its engines for the (fixed) tower shapes
 
     def _probe_fused(self):
         try:
