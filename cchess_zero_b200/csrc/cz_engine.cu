@@ -32,6 +32,7 @@
 #define NONE 0xFFFFFFFFu
 #define HDR 8
 #define WARPS_PER_BLOCK 4
+#define MAX_INKERNEL_PLAYOUTS 16
 
 namespace {
 
@@ -281,7 +282,11 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_wave(Dev E, T *nn_in, 
     }
     unsigned long long accL = 0, accC = 0;
     int maxdep = 0;
-    while (done < target) {
+    // Terminal playouts are resolved here without the network.  A position with a king capture at the root sends
+    // nearly all of its playouts down that edge; bounding the number resolved per launch keeps one such game from
+    // stretching the wave for the other games (it simply continues in the next wave; per-game order is unchanged).
+    int budget = MAX_INKERNEL_PLAYOUTS;
+    while (done < target && budget-- > 0) {
         // ---- one playout of start_tree_search (main.py:350-440) ----
         if (lane < 24) reinterpret_cast<uint32_t *>(S.board)[lane] = rb[lane];
         __syncwarp();
