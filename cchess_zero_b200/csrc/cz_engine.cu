@@ -678,12 +678,26 @@ int cz_encode_dev(const uint8_t *boards, const uint8_t *sides, int n, void *out,
     return CZ_OK;
 }
 
-static int batch_io(int device, const uint8_t *boards, const uint8_t *sides, int n, uint8_t **db, uint8_t **ds) {
+extern "C++" {
+// frees the scratch device buffers of the stateless batch entry points on every exit path
+struct DevBufs {
+    std::vector<void *> p;
+    ~DevBufs() { for (void *q : p) cudaFree(q); }
+    template <typename T> cudaError_t alloc(T **out, size_t bytes) {
+        void *q = nullptr;
+        cudaError_t e = cudaMalloc(&q, bytes);
+        if (e == cudaSuccess) { p.push_back(q); *out = (T *)q; }
+        return e;
+    }
+};
+}  // extern "C++"
+
+static int batch_io(DevBufs &bufs, int device, const uint8_t *boards, const uint8_t *sides, int n, uint8_t **db, uint8_t **ds) {
     CUDA_TRY(cudaSetDevice(device));
-    CUDA_TRY(cudaMalloc(db, (size_t)n * 90));
+    CUDA_TRY(bufs.alloc(db, (size_t)n * 90));
     CUDA_TRY(cudaMemcpy(*db, boards, (size_t)n * 90, cudaMemcpyHostToDevice));
     if (sides) {
-        CUDA_TRY(cudaMalloc(ds, (size_t)n));
+        CUDA_TRY(bufs.alloc(ds, (size_t)n));
         CUDA_TRY(cudaMemcpy(*ds, sides, (size_t)n, cudaMemcpyHostToDevice));
     }
     return CZ_OK;
@@ -692,51 +706,51 @@ static int batch_io(int device, const uint8_t *boards, const uint8_t *sides, int
 int cz_legal_moves_batch(int device, const uint8_t *boards, const uint8_t *sides, int n, uint16_t *moves, int32_t *counts) {
     if (n < 0 || (n && (!boards || !sides || !moves || !counts))) return fail(CZ_EINVAL, "cz_legal_moves_batch: null");
     if (n == 0) return CZ_OK;
+    DevBufs bufs;
     uint8_t *db = nullptr, *ds = nullptr;
     uint16_t *dm = nullptr;
     int32_t *dc = nullptr;
-    int rc = batch_io(device, boards, sides, n, &db, &ds);
+    int rc = batch_io(bufs, device, boards, sides, n, &db, &ds);
     if (rc) return rc;
-    CUDA_TRY(cudaMalloc(&dm, (size_t)n * CZ_MAXCHILD * 2));
-    CUDA_TRY(cudaMalloc(&dc, (size_t)n * 4));
+    CUDA_TRY(bufs.alloc(&dm, (size_t)n * CZ_MAXCHILD * 2));
+    CUDA_TRY(bufs.alloc(&dc, (size_t)n * 4));
     rc = cz_legal_moves_dev(db, ds, n, dm, dc, nullptr);
     if (rc) return rc;
     CUDA_TRY(cudaMemcpy(moves, dm, (size_t)n * CZ_MAXCHILD * 2, cudaMemcpyDeviceToHost));
     CUDA_TRY(cudaMemcpy(counts, dc, (size_t)n * 4, cudaMemcpyDeviceToHost));
-    cudaFree(db); cudaFree(ds); cudaFree(dm); cudaFree(dc);
     return CZ_OK;
 }
 
 int cz_apply_moves_batch(int device, uint8_t *boards, const uint16_t *moves, int n, uint8_t *captured) {
     if (n < 0 || (n && (!boards || !moves || !captured))) return fail(CZ_EINVAL, "cz_apply_moves_batch: null");
     if (n == 0) return CZ_OK;
+    DevBufs bufs;
     uint8_t *db = nullptr, *ds = nullptr, *dcap = nullptr;
     uint16_t *dm = nullptr;
-    int rc = batch_io(device, boards, nullptr, n, &db, &ds);
+    int rc = batch_io(bufs, device, boards, nullptr, n, &db, &ds);
     if (rc) return rc;
-    CUDA_TRY(cudaMalloc(&dm, (size_t)n * 2));
-    CUDA_TRY(cudaMalloc(&dcap, (size_t)n));
+    CUDA_TRY(bufs.alloc(&dm, (size_t)n * 2));
+    CUDA_TRY(bufs.alloc(&dcap, (size_t)n));
     CUDA_TRY(cudaMemcpy(dm, moves, (size_t)n * 2, cudaMemcpyHostToDevice));
     k_apply<<<nblk(n, 128), 128>>>(db, dm, n, dcap);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpy(boards, db, (size_t)n * 90, cudaMemcpyDeviceToHost));
     CUDA_TRY(cudaMemcpy(captured, dcap, (size_t)n, cudaMemcpyDeviceToHost));
-    cudaFree(db); cudaFree(dm); cudaFree(dcap);
     return CZ_OK;
 }
 
 int cz_encode_batch(int device, const uint8_t *boards, const uint8_t *sides, int n, float *out) {
     if (n < 0 || (n && (!boards || !sides || !out))) return fail(CZ_EINVAL, "cz_encode_batch: null");
     if (n == 0) return CZ_OK;
+    DevBufs bufs;
     uint8_t *db = nullptr, *ds = nullptr;
     float *dout = nullptr;
-    int rc = batch_io(device, boards, sides, n, &db, &ds);
+    int rc = batch_io(bufs, device, boards, sides, n, &db, &ds);
     if (rc) return rc;
-    CUDA_TRY(cudaMalloc(&dout, (size_t)n * CZ_ENC_LEN * 4));
+    CUDA_TRY(bufs.alloc(&dout, (size_t)n * CZ_ENC_LEN * 4));
     rc = cz_encode_dev(db, ds, n, dout, CZ_F32, nullptr);
     if (rc) return rc;
     CUDA_TRY(cudaMemcpy(out, dout, (size_t)n * CZ_ENC_LEN * 4, cudaMemcpyDeviceToHost));
-    cudaFree(db); cudaFree(ds); cudaFree(dout);
     return CZ_OK;
 }
 

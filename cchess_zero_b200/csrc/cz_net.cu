@@ -228,12 +228,8 @@ int cz_net_heads(const void *x, int B, const float *wh, const float *bh, const f
                  const void *wp, const float *bp, void *hp_scratch, float *hv_scratch, float *logits, float *value, void *stream) {
     if (!x || !wh || !bh || !w1t || !b1 || !w2 || !wp || !bp || !hp_scratch || !hv_scratch || !logits || !value || B <= 0) return CZ_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
-    static bool attr = false;
-    const int smem = 2 * 64 * LDS_ROW * (int)sizeof(__half);   // 51200 B
-    if (!attr) {
-        if (cudaFuncSetAttribute(k_policy_fc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return CZ_ECUDA;
-        attr = true;
-    }
+    const int smem = 2 * 64 * LDS_ROW * (int)sizeof(__half);   // 51200 B > the 48 KB default: opt in (per device, so every call)
+    if (cudaFuncSetAttribute(k_policy_fc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return CZ_ECUDA;
     k_head_conv<<<B, 256, 0, st>>>((const __half *)x, B, wh, bh, (__half *)hp_scratch, hv_scratch);
     if (cudaGetLastError() != cudaSuccess) return CZ_ECUDA;
     k_value_mlp<<<(B + VM_POS - 1) / VM_POS, 256, 0, st>>>(hv_scratch, B, w1t, b1, w2, b2, value);

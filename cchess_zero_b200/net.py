@@ -257,6 +257,42 @@ class _Tf32:
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = self.prev
 
 
+def train_step_module(net, opt, x, pi, z, learning_rate, c_l2=1e-4, global_norm=100, group=None):
+    """One optimiser step with the reference's loss and update rule (policy_value_network.py:76-126):
+    softmax cross-entropy(pi, logits) + MSE(z, value) + 1e-4 * sum(w^2)/2 over ALL trainables, Nesterov momentum,
+    clip_by_global_norm(100), NaN check.  When torch.distributed is initialised with more than one rank the
+    gradients are averaged with one all_reduce per step before clipping -- the data-parallel replacement of
+    policy_value_network_gpus.average_gradients (policy_value_network_gpus.py:216-250): each rank's mini-batch is
+    one 'tower', batch-norm statistics stay per tower exactly as in the reference's tower_loss."""
+    import torch.distributed as dist
+    net.train()
+    for gp in opt.param_groups:
+        gp["lr"] = float(learning_rate)
+    logits, value = net(x)
+    policy_loss = (-(pi * F.log_softmax(logits, dim=1)).sum(dim=1)).mean()
+    value_loss = F.mse_loss(value, z)
+    l2 = sum((p * p).sum() for p in net.parameters()) * (0.5 * c_l2)
+    loss = value_loss + policy_loss + l2
+    opt.zero_grad(set_to_none=True)
+    loss.backward()
+    params = [p for p in net.parameters() if p.grad is not None]
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        flat = torch.cat([p.grad.reshape(-1) for p in params])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        flat /= dist.get_world_size(group)
+        o = 0
+        for p in params:
+            k = p.grad.numel()
+            p.grad.copy_(flat[o:o + k].view_as(p.grad))
+            o += k
+    torch.nn.utils.clip_grad_norm_(params, global_norm)
+    if not all(torch.isfinite(p.grad).all() for p in params):
+        raise FloatingPointError("NaN Found!")   # tf.check_numerics, policy_value_network.py:122
+    opt.step()
+    accuracy = (logits.argmax(1) == pi.argmax(1)).float().mean().item()
+    return accuracy, loss.item()
+
+
 class policy_value_network(object):
     """Drop-in for the reference class of the same name (policy_value_network.py:8-214):
     forward(positions) -> (logits np [B,2086] f32, value np [B,1] f32); train_step; save; restore."""
@@ -311,26 +347,12 @@ class policy_value_network(object):
     # -- training (policy_value_network.py:76-126, 186-199) ---------------------------------------
     def train_step(self, positions, probs, winners, learning_rate):
         self._plan = None
-        self.net.train()
         x = torch.as_tensor(np.asarray(positions, dtype=np.float32)).reshape(-1, 9, 10, 14).to(self.device)
         pi = torch.as_tensor(np.asarray(probs, dtype=np.float32)).to(self.device)
         z = torch.as_tensor(np.asarray(winners, dtype=np.float32)).reshape(-1, 1).to(self.device)
-        for gp in self.opt.param_groups:
-            gp["lr"] = float(learning_rate)
-        logits, value = self.net(x)
-        policy_loss = (-(pi * F.log_softmax(logits, dim=1)).sum(dim=1)).mean()
-        value_loss = F.mse_loss(value, z)
-        l2 = sum((p * p).sum() for p in self.net.parameters()) * (0.5 * self.c_l2)
-        loss = value_loss + policy_loss + l2
-        self.opt.zero_grad(set_to_none=True)
-        loss.backward()
-        torch.nn.utils.clip_grad_norm_(self.net.parameters(), self.global_norm)
-        if not all(torch.isfinite(p.grad).all() for p in self.net.parameters()):
-            raise FloatingPointError("NaN Found!")   # tf.check_numerics, policy_value_network.py:122
-        self.opt.step()
+        accuracy, loss = train_step_module(self.net, self.opt, x, pi, z, learning_rate, self.c_l2, self.global_norm)
         self.global_step += 1
-        accuracy = (logits.argmax(1) == pi.argmax(1)).float().mean().item()
-        return accuracy, loss.item(), self.global_step
+        return accuracy, loss, self.global_step
 
     # -- checkpoints (policy_value_network.py:164-184) -------------------------------------------
     def save(self, in_global_step):

@@ -134,3 +134,39 @@ def test_bench_reference_arm_prints_contract_line():
     line = json.loads(r.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["metric"] == "mcts_node_expansions_per_sec" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+_DP = r'''
+import sys
+sys.path.insert(0, %r)
+import torch, torch.distributed as dist
+from cchess_zero_b200.net import PolicyValueNet, train_step_module
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+torch.manual_seed(0)
+net = PolicyValueNet(1)                               # same initial weights on every rank
+opt = torch.optim.SGD(net.parameters(), lr=1e-2, momentum=0.9, nesterov=True)
+g = torch.Generator().manual_seed(100 + rank)         # a different mini-batch ("tower") per rank
+x = (torch.rand(6, 9, 10, 14, generator=g) < 0.03).float()
+pi = torch.softmax(torch.randn(6, 2086, generator=g), 1)
+z = torch.sign(torch.randn(6, 1, generator=g))
+before = torch.cat([p.detach().reshape(-1) for p in net.parameters()]).clone()
+for _ in range(3):
+    acc, loss = train_step_module(net, opt, x, pi, z, 1e-2)
+after = torch.cat([p.detach().reshape(-1) for p in net.parameters()])
+allp = [torch.empty_like(after) for _ in range(world)]
+dist.all_gather(allp, after)
+assert torch.isfinite(after).all() and not torch.equal(before, after)
+assert all(torch.equal(allp[0], q) for q in allp), "replicas diverged"
+if rank == 0: print("DP_OK", float(loss))
+dist.destroy_process_group()
+'''
+
+
+def test_data_parallel_train_step_keeps_replicas_in_sync_gloo(tmp_path):
+    script = tmp_path / "dp.py"
+    script.write_text(_DP % ROOT)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29533", str(script)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "DP_OK" in r.stdout
