@@ -225,3 +225,21 @@ def test_mcts_tree_with_package_network_and_move_latency(tmp_path, monkeypatch):
     assert sum(visits) <= 200 + m.mcts.root.N
     print("move latency (200 playouts, 7 blocks): %s" % ["%.3f" % x for x in lat])
     assert min(lat) < 5.0
+
+
+def test_headless_play_mode_ai_vs_ai(tmp_path, monkeypatch):
+    """--mode play --ai_count 2 of the reference (ChessGame.game_mode_2) without tkinter."""
+    monkeypatch.chdir(tmp_path)
+    import contextlib, io
+    from cchess_zero_b200.net import policy_value_network
+    from cchess_zero_b200.play import ChessGame
+    np.random.seed(3)
+    with contextlib.redirect_stdout(io.StringIO()):
+        g = ChessGame(2, "mcts", 64, network=policy_value_network(res_block_nums=2))
+        who = g.start(max_moves=12)
+    assert who in ("", "w", "b", "t")
+    assert g.cchess_engine.game_borad.round >= 2 and len(g.move_times) >= 1
+    with contextlib.redirect_stdout(io.StringIO()):
+        g2 = ChessGame(2, "net", 64, network=g.cchess_engine.policy_value_netowrk)
+        g2.start(max_moves=4)
+    assert g2.cchess_engine.game_borad.round == 5

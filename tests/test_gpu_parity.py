@@ -311,3 +311,46 @@ def test_full_size_1024_games_1200_playouts_properties_and_samples(O, R):
         assert np.array_equal(t.signature(), e.tree_signature(g)), g
     c = e.raise_on_error()
     assert c["n_playout"] == 2 * B * P
+
+
+def test_edge_cases_empty_batches_bad_arguments_and_loud_failures(R):
+    import ctypes as C
+    from cchess_zero_b200._lib import EngineError, lib
+    from cchess_zero_b200.engine import Engine
+    from cchess_zero_b200.fakenet import FakeNet
+    L = lib()
+    # empty batches are fine
+    mv, cnt = R.legal_moves_batch(np.zeros((0, 90), np.uint8), np.zeros(0, np.uint8))
+    assert mv.shape == (0, 128) and cnt.shape == (0,)
+    assert R.encode_batch(np.zeros((0, 90), np.uint8), np.zeros(0, np.uint8)).shape == (0, 9, 10, 14)
+    # bad arguments return error codes with a message, never crash
+    assert L.cz_legal_moves_batch(0, None, None, 3, None, None) < 0 and b"null" in L.cz_last_error()
+    assert L.cz_label_index(-1, 200) == -1
+    with pytest.raises(EngineError):
+        R.state_to_board("9/9")
+    h = C.c_void_p()
+    assert L.cz_engine_create(0, 0, 0, C.byref(h)) < 0
+    assert L.cz_engine_create(4, 100, 0, C.byref(h)) < 0            # arena too small to be meaningful
+    # an empty board (no kings, no pieces): zero moves -> the engine flags it instead of hanging (reference: ValueError)
+    e = Engine(2, arena_words=1 << 16)
+    boards = np.zeros((2, 90), np.uint8)
+    boards[1] = R.state_to_board(R.START_STATE)
+    e.reset(None, boards, [0, 0], [0, 0])
+    fn = FakeNet("hash_pos")
+    nn_in = torch.zeros((2, 9, 10, 14), device="cuda"); lo = torch.zeros((2, 2086), device="cuda"); v = torch.zeros(2, device="cuda")
+
+    def fwd(x):
+        l, val = fn(x); lo.copy_(l); v.copy_(val)
+    e.search(fwd, 20, nn_in, lo, v)
+    with pytest.raises(EngineError, match="NOMOVES"):
+        e.raise_on_error()
+    assert e.counters()["first_error_game"] == 0
+    # arena exhaustion is reported loudly, not silently truncated
+    e2 = Engine(1, arena_words=4096)
+    nn1 = torch.zeros((1, 9, 10, 14), device="cuda"); lo1 = torch.zeros((1, 2086), device="cuda"); v1 = torch.zeros(1, device="cuda")
+
+    def fwd1(x):
+        l, val = fn(x); lo1.copy_(l); v1.copy_(val)
+    e2.search(fwd1, 400, nn1, lo1, v1)
+    with pytest.raises(EngineError, match="ARENA"):
+        e2.raise_on_error()
