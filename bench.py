@@ -328,7 +328,7 @@ def run_ours(a, rank, world, local_rank):
                     algorithmic_bytes_per_launch=per_launch,
                     bytes_per_expansion=ab / max(1, d["n_expand"]), launches_timed=len(kms),
                     note="latency-bound pointer-chasing kernel: HBM fraction is reported as required, the binding limits are per-warp dependent loads and the network")
-        if not a.no_cpu_baseline:
+        if not a.no_cpu_baseline and world == 1:      # reported baseline: rank 0, N=1 only
             arm = sized_cpu_arm(B, a.playouts, a.res_blocks, wave_budget_s=a.cpu_seconds / 5.0)
             r = arm.run(seconds=a.cpu_seconds)
             cpu = dict(value=r["value"], unit="expansions/s", cores=arm.threads, kind="port",
