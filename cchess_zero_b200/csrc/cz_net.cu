@@ -232,11 +232,27 @@ int cz_net_heads(const void *x, int B, const float *wh, const float *bh, const f
     if (cudaFuncSetAttribute(k_policy_fc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return CZ_ECUDA;
     k_head_conv<<<B, 256, 0, st>>>((const __half *)x, B, wh, bh, (__half *)hp_scratch, hv_scratch);
     if (cudaGetLastError() != cudaSuccess) return CZ_ECUDA;
-    k_value_mlp<<<(B + VM_POS - 1) / VM_POS, 256, 0, st>>>(hv_scratch, B, w1t, b1, w2, b2, value);
+    // The value MLP and the policy FC are independent: fork the value MLP onto a side stream (event fork/join, which
+    // CUDA-graph capture records as two parallel branches) so that the two small kernels overlap.
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return CZ_ECUDA;
+    static cudaStream_t side[64] = {nullptr};
+    static cudaEvent_t ev_fork[64] = {nullptr}, ev_join[64] = {nullptr};
+    if (!side[dev]) {   // created on the first (eager, warm-up) call, never during capture
+        if (cudaStreamCreateWithFlags(&side[dev], cudaStreamNonBlocking) != cudaSuccess) return CZ_ECUDA;
+        if (cudaEventCreateWithFlags(&ev_fork[dev], cudaEventDisableTiming) != cudaSuccess) return CZ_ECUDA;
+        if (cudaEventCreateWithFlags(&ev_join[dev], cudaEventDisableTiming) != cudaSuccess) return CZ_ECUDA;
+    }
+    if (cudaEventRecord(ev_fork[dev], st) != cudaSuccess) return CZ_ECUDA;
+    if (cudaStreamWaitEvent(side[dev], ev_fork[dev], 0) != cudaSuccess) return CZ_ECUDA;
+    k_value_mlp<<<(B + VM_POS - 1) / VM_POS, 256, 0, side[dev]>>>(hv_scratch, B, w1t, b1, w2, b2, value);
     if (cudaGetLastError() != cudaSuccess) return CZ_ECUDA;
+    if (cudaEventRecord(ev_join[dev], side[dev]) != cudaSuccess) return CZ_ECUDA;
     dim3 grid((B + 63) / 64, NPAD / 64);
     k_policy_fc<<<grid, 128, smem, st>>>((const __half *)hp_scratch, B, (const __half *)wp, bp, logits);
-    return cudaGetLastError() == cudaSuccess ? CZ_OK : CZ_ECUDA;
+    if (cudaGetLastError() != cudaSuccess) return CZ_ECUDA;
+    if (cudaStreamWaitEvent(st, ev_join[dev], 0) != cudaSuccess) return CZ_ECUDA;
+    return CZ_OK;
 }
 
 }  // extern "C"
