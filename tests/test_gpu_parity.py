@@ -354,3 +354,17 @@ def test_edge_cases_empty_batches_bad_arguments_and_loud_failures(R):
     e2.search(fwd1, 400, nn1, lo1, v1)
     with pytest.raises(EngineError, match="ARENA"):
         e2.raise_on_error()
+
+
+def test_selfplay_full_game_at_1200_playouts_against_reference_vectors(R):
+    """A whole game at the BASELINE playout count, bit-exact against the reference's own (s, pi, z) output."""
+    from cchess_zero_b200.fakenet import FakeNet
+    from cchess_zero_b200.selfplay import SelfPlay
+    g = load_golden("selfplay_1200.json")["games"][0]
+    sp = SelfPlay(4, FakeNet(g["net"]), g["playouts"], seeds=[g["seed"]] * 4, auto_reset=False)
+    sp.capture_graph()
+    out = sp.play_games()
+    for slot, rec in out:
+        assert len(rec) == g["n"] and rec.states == g["states"]
+        assert [float(z) for z in rec.z] == g["z"]
+        assert sha(rec.dense_pi().tobytes()) == g["sha_pi"]

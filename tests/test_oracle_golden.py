@@ -91,3 +91,13 @@ def test_selfplay_tuples_against_reference(i):
     assert sha(np.asarray(r["pis"], dtype=np.float64).tobytes()) == g["sha_pi"]
     for p, sp in zip(r["pis"], g["pi_sparse"]):
         assert [[int(k), float(p[k]).hex()] for k in np.nonzero(p)[0]] == sp
+
+
+def test_selfplay_full_game_at_1200_playouts_against_reference():
+    """One complete game of the reference at the BASELINE playout count (search_threads=1), 77 plies."""
+    g = load_golden("selfplay_1200.json")["games"][0]
+    with np.errstate(all="ignore"):
+        r = O.selfplay_game(g["net"], g["playouts"], np.random.RandomState(g["seed"]))
+    assert len(r["states"]) == g["n"] and r["states"] == g["states"]
+    assert [float(v) for v in r["z"]] == g["z"]
+    assert sha(np.asarray(r["pis"], dtype=np.float64).tobytes()) == g["sha_pi"]
