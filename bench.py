@@ -310,12 +310,19 @@ def run_ours(a, rank, world, local_rank):
         k0 = e.counters()
         evs = []
         lanes = sp.lanes if sp.lanes is not None else [sp]       # a single-lane SelfPlay has the same attribute names
+        side = torch.cuda.Stream()
+        cur = torch.cuda.current_stream()
         for _ in range(a.profile_waves):
             for ln in lanes:
                 x, y = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 x.record(); ln.engine.wave(ln.nn_in, ln.logits, ln.value); y.record()
                 evs.append((x, y))
+                if sp.lanes is None and sp.overlap_movegen:      # same schedule as the captured graph
+                    side.wait_stream(cur)
+                    with torch.cuda.stream(side):
+                        ln.engine.prepare_leaves()
                 ln.forward(ln.nn_in)
+                cur.wait_stream(side)
         torch.cuda.synchronize()
         k1 = e.counters()
         kms = [x.elapsed_time(y) for x, y in evs]
@@ -347,7 +354,8 @@ def run_ours(a, rank, world, local_rank):
                     dtype=a.precision, data="synthetic (seed-0 xavier-initialised network, all games from the start position)",
                     config=dict(workload="%d concurrent self-play games x %d playouts per move, res_block_nums=%d, per GPU" % (B, a.playouts, a.res_blocks),
                                 games_per_gpu=B, playouts=a.playouts, res_block_nums=a.res_blocks, search_threads=1, exploration=True,
-                                cuda_graph=not a.no_graph, lanes=a.lanes, fused_conv_epilogue=plan.fused,
+                                cuda_graph=not a.no_graph, lanes=a.lanes, movegen_under_network=bool(sp.overlap_movegen and not a.no_graph and a.lanes == 1),
+                                fused_conv_epilogue=plan.fused,
                                 network_ends="csrc/cz_net.cu (board-byte first conv, fused heads)" if plan.dtype == torch.uint8 else "library",
                                 l2_policy="working set (trees %.1f GB + activations) exceeds the 126 MB L2" % (c1["max_arena_words"] * 4 * B / 1e9)),
                     e2e=dict(value=e2e_v, unit="expansions/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, wall_ms=wall_ms),

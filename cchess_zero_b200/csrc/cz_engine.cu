@@ -102,6 +102,9 @@ struct Dev {
     int32_t *path_len;
     uint2 *path;
     uint8_t *leaf_board;
+    uint16_t *leaf_moves, *leaf_li;   // [B][128]: move list and (flipped) label index of the pending leaf, filled by k_prepare_leaves
+    int32_t *leaf_n;                  // [B]: number of moves, -1 = not prepared
+    int prepared;                     // 1: k_wave trusts leaf_moves / leaf_li / leaf_n (cz_engine_prepare_leaves ran after the previous wave)
     uint32_t *arena;
     uint8_t *cur;
     uint32_t *alloc, *max_alloc;
@@ -125,6 +128,7 @@ __device__ __forceinline__ uint32_t *arena_of(const Dev &E, int g) {
 struct WarpSmem {
     uint8_t board[96];
     uint16_t moves[136];
+    uint16_t li[128];
     float ps[128];
     cz::MoveScratch scratch;
 };
@@ -153,31 +157,51 @@ __device__ void warp_backup(const Dev &E, int g, uint32_t *ar, int depth, float 
     __syncwarp();
 }
 
-// leaf_node.expand (main.py:175-187) for the pending leaf of game g; returns false on error
-__device__ bool warp_expand(const Dev &E, int g, uint32_t *ar, WarpSmem &S, const float *logits, int pend, int depth, int lane) {
+// Move list of the pending leaf of game g in reference order + the label index of every move (with flip_policy,
+// main.py:1152-1155, folded into the index: rank y -> 9-y for black).  Leaves S.moves[i] / li in S.li[i]; returns n.
+__device__ int warp_leaf_moves(const Dev &E, int g, WarpSmem &S, uint32_t &errf, int lane) {
     const uint32_t *lb = reinterpret_cast<const uint32_t *>(E.leaf_board + (size_t)g * 96);
     if (lane < 24) reinterpret_cast<uint32_t *>(S.board)[lane] = lb[lane];
     __syncwarp();
     const int lside = S.board[90];
     int n = cz::warp_legal_moves(S.board, lside, S.moves, S.scratch, lane);
-    uint32_t errf = 0;
     if (n == 0) errf |= CZ_ERR_NOMOVES;
     if (n > CZ_MAXCHILD) { errf |= CZ_ERR_CHILDREN; n = CZ_MAXCHILD; }
-    const uint32_t cs = (uint32_t)((n + 7) & ~7), size = HDR + 5 * cs;
-    const uint32_t base = E.alloc[g];
-    if ((long long)base + size > E.A) errf |= CZ_ERR_ARENA;
-    const float *lg = logits + (size_t)g * CZ_NLABEL;
     for (int i = lane; i < n; i += 32) {
         const int mv = S.moves[i];
         int src = mv & 127, dst = mv >> 7;
-        if (lside == 1) {  // flip_policy (main.py:1152-1155) folded into the index: rank y -> 9-y
+        if (lside == 1) {
             src = (9 - src / 9) * 9 + src % 9;
             dst = (9 - dst / 9) * 9 + dst % 9;
         }
         int li = E.label_of[src * CZ_NSQ + dst];
         if (li < 0) { errf |= CZ_ERR_NOLABEL; li = 0; }
-        S.ps[i] = __ldg(lg + li);
+        S.li[i] = (uint16_t)li;
     }
+    __syncwarp();
+    return n;
+}
+
+// leaf_node.expand (main.py:175-187) for the pending leaf of game g; returns false on error
+__device__ bool warp_expand(const Dev &E, int g, uint32_t *ar, WarpSmem &S, const float *logits, int pend, int depth, int lane) {
+    uint32_t errf = 0;
+    int n;
+    const float *lg = logits + (size_t)g * CZ_NLABEL;
+    if (E.prepared && E.leaf_n[g] >= 0) {
+        // the move list was generated by k_prepare_leaves while the network was running
+        n = E.leaf_n[g];
+        for (int i = lane; i < n; i += 32) {
+            S.moves[i] = E.leaf_moves[(size_t)g * CZ_MAXCHILD + i];
+            S.ps[i] = __ldg(lg + E.leaf_li[(size_t)g * CZ_MAXCHILD + i]);
+        }
+        if (n == 0) errf |= CZ_ERR_NOMOVES;
+    } else {
+        n = warp_leaf_moves(E, g, S, errf, lane);
+        for (int i = lane; i < n; i += 32) S.ps[i] = __ldg(lg + S.li[i]);
+    }
+    const uint32_t cs = (uint32_t)((n + 7) & ~7), size = HDR + 5 * cs;
+    const uint32_t base = E.alloc[g];
+    if ((long long)base + size > E.A) errf |= CZ_ERR_ARENA;
     errf = __reduce_or_sync(CZ_FULL, errf);
     __syncwarp();
     if (errf) {
@@ -221,6 +245,7 @@ __device__ void store_leaf(const Dev &E, int g, WarpSmem &S, int side, T *nn_in,
     __syncwarp();
     uint32_t *lb = reinterpret_cast<uint32_t *>(E.leaf_board + (size_t)g * 96);
     if (lane < 24) lb[lane] = reinterpret_cast<const uint32_t *>(S.board)[lane];
+    if (lane == 0) E.leaf_n[g] = -1;          // no prepared move list for this leaf yet
     if constexpr (sizeof(T) == 1) {
         // CZ_BOARD: the evaluator reads the side-to-move-canonical board itself (try_flip, main.py:560-574);
         // cz_net_first_conv applies the reference's cell indexing, so no [9][10][14] tensor is written.
@@ -388,6 +413,26 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_wave(Dev E, T *nn_in, 
 
 __constant__ uint8_t c_start[96];   // start position, uploaded by cz_engine_create
 
+// ---- move generation of the pending leaves, off the critical path -------------------------------------------
+// Runs on a side stream underneath the network evaluation of the same leaves: the next k_wave then only gathers
+// the logits.  Same device functions as the in-wave path, so the result is identical by construction.
+__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_prepare_leaves(Dev E) {
+    __shared__ WarpSmem smem[WARPS_PER_BLOCK];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = blockIdx.x * WARPS_PER_BLOCK + w;
+    if (g >= E.B || !E.active[g] || !E.pending[g] || E.leaf_n[g] >= 0) return;
+    WarpSmem &S = smem[w];
+    uint32_t errf = 0;
+    const int n = warp_leaf_moves(E, g, S, errf, lane);
+    errf = __reduce_or_sync(CZ_FULL, errf);
+    if (errf && lane == 0) atomicOr(E.err + g, errf);
+    for (int i = lane; i < n; i += 32) {
+        E.leaf_moves[(size_t)g * CZ_MAXCHILD + i] = S.moves[i];
+        E.leaf_li[(size_t)g * CZ_MAXCHILD + i] = S.li[i];
+    }
+    __syncwarp();
+    if (lane == 0) E.leaf_n[g] = n;
+}
+
 // ---- GameBoard.reload + MCTS_tree.reload -------------------------------------------------
 __global__ void k_reset(Dev E, const uint8_t *mask, const uint8_t *boards, const uint8_t *sides, const int32_t *rr) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
@@ -406,6 +451,7 @@ __global__ void k_reset(Dev E, const uint8_t *mask, const uint8_t *boards, const
     E.pending[g] = 0;
     E.active[g] = 0;
     E.path_len[g] = 0;
+    E.leaf_n[g] = -1;
     E.alloc[g] = 0;
     E.terminal[g] = 0;
     E.winner[g] = -1;
@@ -779,12 +825,13 @@ int cz_engine_create(int n_games, int64_t arena_words, int device, cz_engine **o
     Dev &d = e->d;
     d.B = n_games;
     d.A = arena_words;
+    d.prepared = 0;
     const size_t B = (size_t)n_games;
     int rc = 0;
 #define AL(ptr, cnt) if (!rc) rc = dalloc(e, &ptr, cnt)
     AL(d.root_board, B * 96); AL(d.side, B); AL(d.rr, B); AL(d.ply, B); AL(d.root_N, B); AL(d.root_cnt, B);
     AL(d.root_base, B); AL(d.done, B); AL(d.target, B); AL(d.pending, B); AL(d.active, B); AL(d.path_len, B);
-    AL(d.path, B * MAXD); AL(d.leaf_board, B * 96); AL(d.cur, B); AL(d.alloc, B); AL(d.max_alloc, B);
+    AL(d.path, B * MAXD); AL(d.leaf_board, B * 96); AL(d.leaf_moves, B * CZ_MAXCHILD); AL(d.leaf_li, B * CZ_MAXCHILD); AL(d.leaf_n, B); AL(d.cur, B); AL(d.alloc, B); AL(d.max_alloc, B);
     AL(d.cnt_expand, B); AL(d.cnt_playout, B); AL(d.cnt_L, B); AL(d.cnt_c, B); AL(d.cnt_C, B); AL(d.err, B); AL(d.max_depth, B);
     AL(d.terminal, B); AL(d.winner, B);
     AL(d.st_n, B); AL(d.st_visits, B * CZ_MAXCHILD); AL(d.st_choice, B); AL(d.st_moves, B * CZ_MAXCHILD);
@@ -893,6 +940,14 @@ int cz_engine_select(cz_engine *e, void *stream, void *nn_in, int nn_dtype) {
 int cz_engine_expand_backup(cz_engine *e, void *stream, const float *logits, const float *value) {
     if (!e || !logits || !value) return fail(CZ_EINVAL, "cz_engine_expand_backup: null");
     return launch_wave<true, false>(e, stream, (void *)logits, CZ_F32, logits, value);
+}
+
+int cz_engine_prepare_leaves(cz_engine *e, void *stream) {
+    if (!e) return fail(CZ_EINVAL, "null engine");
+    e->d.prepared = 1;   // from now on k_wave uses the prepared lists when present (leaf_n >= 0), else generates in-wave
+    k_prepare_leaves<<<nblk(e->d.B, WARPS_PER_BLOCK), 32 * WARPS_PER_BLOCK, 0, (cudaStream_t)stream>>>(e->d);
+    CUDA_TRY(cudaGetLastError());
+    return CZ_OK;
 }
 
 int cz_engine_unfinished_async(cz_engine *e, void *stream, int32_t *dev_count) {

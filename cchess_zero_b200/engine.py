@@ -79,6 +79,12 @@ class Engine:
         self.launches += 1
         check(lib().cz_engine_expand_backup(self.h, _stream(), logits.data_ptr(), value.data_ptr()), "cz_engine_expand_backup")
 
+    def prepare_leaves(self, stream=None):
+        """Move generation for the leaves of the last wave, meant for a side stream under the network (see capture_graph)."""
+        self.launches += 1
+        st = _stream() if stream is None else C.c_void_p(stream.cuda_stream)
+        check(lib().cz_engine_prepare_leaves(self.h, st), "cz_engine_prepare_leaves")
+
     def unfinished(self):
         out = C.c_int32(0)
         self.launches += 1

@@ -192,7 +192,7 @@ class SelfPlay:
 
     def __init__(self, n_games, forward, playouts, seeds=None, exploration=True, temperature=1,
                  nn_dtype=torch.float32, arena_words=0, auto_reset=True, device=None, keep_records=True, plan=None,
-                 plan_factory=None, lanes=1):
+                 plan_factory=None, lanes=1, overlap_movegen=True):
         """plan: an InferencePlan / NativePlan (defines the input buffer, writes logits/value in place).
         plan_factory(n) + lanes=2: two half-batches, each with its own engine and plan; the search pipelines them so
         that one half's tree kernel runs under the other half's network (see capture_graph)."""
@@ -240,6 +240,7 @@ class SelfPlay:
         self.plies = 0
         self.waves = 0
         self.graph = None
+        self.overlap_movegen = overlap_movegen
         self._alphas = {}
         rules._init_tables()
 
@@ -326,9 +327,18 @@ class SelfPlay:
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
+        cs = torch.cuda.Stream()
+        side = torch.cuda.Stream()
+        with torch.cuda.graph(g, stream=cs):
             self.engine.wave(self.nn_in, self.logits, self.value)
+            if self.overlap_movegen:
+                # fork: the move generation of the new leaves runs under their network evaluation
+                side.wait_stream(cs)
+                with torch.cuda.stream(side):
+                    self.engine.prepare_leaves()
             self._eval(self.nn_in)
+            if self.overlap_movegen:
+                cs.wait_stream(side)
         self.graph = g
 
     def search(self):

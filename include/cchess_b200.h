@@ -115,6 +115,12 @@ int cz_engine_wave(cz_engine *e, void *stream, void *nn_in, int nn_dtype, const 
 int cz_engine_select(cz_engine *e, void *stream, void *nn_in, int nn_dtype);
 int cz_engine_expand_backup(cz_engine *e, void *stream, const float *logits, const float *value);
 
+/* Optional overlap: generate the move lists (and label indices) of the leaves selected by the last wave.  Launch it
+ * on a side stream while the network evaluates those leaves; the next cz_engine_wave then skips move generation for
+ * every leaf that was prepared (identical results: same device code).  Stream ordering is the caller's job:
+ * after the wave, before the next wave.  Capturable. */
+int cz_engine_prepare_leaves(cz_engine *e, void *stream);
+
 /* Number of games that still have playouts to run or a leaf pending (device->host, synchronises stream). */
 int cz_engine_unfinished(cz_engine *e, void *stream, int32_t *out_count);
 /* Asynchronous form: writes the count to *dev_count (device int32) without synchronising. */
