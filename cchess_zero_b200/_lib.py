@@ -40,6 +40,7 @@ def _sig(L):
     L.cz_engine_select.argtypes = [vp, vp, vp, i32]
     L.cz_engine_expand_backup.argtypes = [vp, vp, vp, vp]
     L.cz_engine_prepare_leaves.argtypes = [vp, vp]
+    L.cz_engine_use_prepared_leaves.argtypes = [vp, i32]
     L.cz_engine_unfinished.argtypes = [vp, vp, vp]
     L.cz_engine_unfinished_async.argtypes = [vp, vp, vp]
     L.cz_engine_root_children.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]

@@ -942,9 +942,14 @@ int cz_engine_expand_backup(cz_engine *e, void *stream, const float *logits, con
     return launch_wave<true, false>(e, stream, (void *)logits, CZ_F32, logits, value);
 }
 
+int cz_engine_use_prepared_leaves(cz_engine *e, int on) {
+    if (!e) return fail(CZ_EINVAL, "null engine");
+    e->d.prepared = on ? 1 : 0;   // read by every wave launched (or captured) afterwards
+    return CZ_OK;
+}
+
 int cz_engine_prepare_leaves(cz_engine *e, void *stream) {
     if (!e) return fail(CZ_EINVAL, "null engine");
-    e->d.prepared = 1;   // from now on k_wave uses the prepared lists when present (leaf_n >= 0), else generates in-wave
     k_prepare_leaves<<<nblk(e->d.B, WARPS_PER_BLOCK), 32 * WARPS_PER_BLOCK, 0, (cudaStream_t)stream>>>(e->d);
     CUDA_TRY(cudaGetLastError());
     return CZ_OK;

@@ -79,6 +79,9 @@ class Engine:
         self.launches += 1
         check(lib().cz_engine_expand_backup(self.h, _stream(), logits.data_ptr(), value.data_ptr()), "cz_engine_expand_backup")
 
+    def use_prepared_leaves(self, on=True):
+        check(lib().cz_engine_use_prepared_leaves(self.h, 1 if on else 0), "cz_engine_use_prepared_leaves")
+
     def prepare_leaves(self, stream=None):
         """Move generation for the leaves of the last wave, meant for a side stream under the network (see capture_graph)."""
         self.launches += 1

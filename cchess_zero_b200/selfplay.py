@@ -329,6 +329,8 @@ class SelfPlay:
         g = torch.cuda.CUDAGraph()
         cs = torch.cuda.Stream()
         side = torch.cuda.Stream()
+        if self.overlap_movegen:
+            self.engine.use_prepared_leaves(True)        # must precede the capture of the wave node
         with torch.cuda.graph(g, stream=cs):
             self.engine.wave(self.nn_in, self.logits, self.value)
             if self.overlap_movegen:

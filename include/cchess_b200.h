@@ -117,9 +117,12 @@ int cz_engine_expand_backup(cz_engine *e, void *stream, const float *logits, con
 
 /* Optional overlap: generate the move lists (and label indices) of the leaves selected by the last wave.  Launch it
  * on a side stream while the network evaluates those leaves; the next cz_engine_wave then skips move generation for
- * every leaf that was prepared (identical results: same device code).  Stream ordering is the caller's job:
+ * every leaf that was prepared (identical results: same device code), provided cz_engine_use_prepared_leaves(e, 1)
+ * was called before that wave was launched / captured.  Stream ordering is the caller's job:
  * after the wave, before the next wave.  Capturable. */
 int cz_engine_prepare_leaves(cz_engine *e, void *stream);
+/* Waves launched (or captured into a graph) after this call use the prepared lists when present (on != 0). */
+int cz_engine_use_prepared_leaves(cz_engine *e, int on);
 
 /* Number of games that still have playouts to run or a leaf pending (device->host, synchronises stream). */
 int cz_engine_unfinished(cz_engine *e, void *stream, int32_t *out_count);
