@@ -43,7 +43,7 @@ def parse():
     ap.add_argument("--res-blocks", type=int, default=7)
     ap.add_argument("--precision", default=os.environ.get("CCHESS_NN_PRECISION", "fp16"))
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--no-overlap-movegen", action="store_true")
+    ap.add_argument("--overlap-movegen", action="store_true", help="leaf move generation on a side stream under the network (measured: no gain)")
     ap.add_argument("--lanes", type=int, default=1, choices=[1, 2], help="2 = pipeline two half-batches (tree kernel under the other half's network)")
     ap.add_argument("--library-ends", action="store_true", help="use cuDNN/cuBLAS for the first conv and the heads instead of csrc/cz_net.cu")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -242,7 +242,7 @@ def run_ours(a, rank, world, local_rank):
     plan = factory(B // a.lanes)
     sp = SelfPlay(B, None, a.playouts, seeds=[rank * B + g for g in range(B)], device=local_rank,
                   auto_reset=True, keep_records=True, plan=plan if a.lanes == 1 else None, plan_factory=factory, lanes=a.lanes,
-                  overlap_movegen=not a.no_overlap_movegen)
+                  overlap_movegen=a.overlap_movegen)
     if not a.no_graph:
         sp.capture_graph()
     e = sp.engine

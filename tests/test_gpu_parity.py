@@ -223,7 +223,8 @@ def test_selfplay_many_games_vs_oracle(graph, O, R):
     from cchess_zero_b200.fakenet import FakeNet
     from cchess_zero_b200.selfplay import SelfPlay
     B, playouts, net = 48, 40, "hash_pos"
-    sp = SelfPlay(B, FakeNet(net), playouts, seeds=[1000 + i for i in range(B)], arena_words=1 << 20, auto_reset=False)
+    sp = SelfPlay(B, FakeNet(net), playouts, seeds=[1000 + i for i in range(B)], arena_words=1 << 20, auto_reset=False,
+                  overlap_movegen=graph)     # the graph variant also exercises the prepared-leaves side stream
     if graph:
         sp.capture_graph()
     out = sp.play_games()
