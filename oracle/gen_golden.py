@@ -10,6 +10,7 @@ it, the CUDA path.  Everything recorded here is an OUTPUT OF THE REFERENCE'S OWN
                  + set-equality against the GUI rules ChessBoard/chessman/*.can_move
   tree.json      MCTS_tree.main with search_threads=1            (main.py:93-206, 337-493)
   selfplay.json  cchess_main.selfplay / get_action               (main.py:1332-1358, 1493-1554)
+  play.json      select_move / get_hint / human_move / check_end  (main.py:1278-1329, 1380-1491), human_color b and w
 The evaluator is one of the deterministic stand-in nets of oracle/ref_harness.py (the TF
 network cannot run here: SURVEY 0.8) -- NN parity is NOT pinned by these files.
 """
@@ -161,10 +162,55 @@ def gen_selfplay(ref):
     return dict(games=games)
 
 
+def gen_play(ref):
+    """Play-mode surface (main.py:1278-1329, 1394-1491): select_move / get_hint / human_move / check_end, both human colours."""
+    import struct
+
+    def fhex(v):
+        return float(v).hex()
+
+    scripts = []
+    for hc, net, playouts, seed in (("b", "hash_pos", 40, 5), ("w", "hash_signed", 32, 8)):
+        m = H.make_cchess_main(H.FAKE_NETS[net], playouts, 1, exploration=False, human_color=hc)
+        np.random.seed(seed)
+        steps = []
+        with H.quiet(), np.errstate(all="ignore"):
+            for rnd in range(5):
+                mv, wr = m.select_move("mcts")
+                steps.append(dict(op="select_move_mcts", move=[int(x) for x in mv], win_rate=fhex(wr), state=m.game_borad.state,
+                                  player=m.game_borad.current_player, rr=m.game_borad.restrict_round))
+                if m.check_end()[0]:
+                    break
+                hint = m.get_hint("mcts", True, lambda: None)
+                steps.append(dict(op="get_hint_mcts", hint=[[a, fhex(p)] for a, p in hint]))
+                a = hint[min(rnd, len(hint) - 1)][0]                  # the human plays the (rnd+1)-th suggestion
+                coord = (ord(a[0]) - 97, int(a[1]), ord(a[2]) - 97, int(a[3]))
+                wr = m.human_move(coord, "mcts")
+                steps.append(dict(op="human_move_mcts", coord=list(coord), win_rate=fhex(wr), state=m.game_borad.state,
+                                  player=m.game_borad.current_player, rr=m.game_borad.restrict_round))
+                ended, who = m.check_end()
+                steps.append(dict(op="check_end", ended=bool(ended), who=who))
+                if ended:
+                    break
+                hint = m.get_hint("net", False, lambda: None)
+                steps.append(dict(op="get_hint_net", hint=[[a, fhex(p)] for a, p in hint]))
+        scripts.append(dict(human_color=hc, net=net, playouts=playouts, seed=seed, steps=steps))
+        print("play", hc, net, len(steps), flush=True)
+    # select_move('net') on its own tree (it does not touch the search tree, main.py:1437-1462)
+    m = H.make_cchess_main(H.FAKE_NETS["hash_pos"], 8, 1, exploration=False)
+    steps = []
+    with H.quiet(), np.errstate(all="ignore"):
+        for _ in range(6):
+            mv, wr = m.select_move("net")
+            steps.append(dict(op="select_move_net", move=[int(x) for x in mv], win_rate=fhex(wr), state=m.game_borad.state))
+    scripts.append(dict(human_color="b", net="hash_pos", playouts=8, seed=None, steps=steps))
+    return dict(scripts=scripts)
+
+
 def main():
     ref = H.load_reference()
     os.makedirs(OUT, exist_ok=True)
-    for name, fn in (("labels", gen_labels), ("movegen", gen_movegen), ("tree", gen_tree), ("selfplay", gen_selfplay)):
+    for name, fn in (("labels", gen_labels), ("movegen", gen_movegen), ("tree", gen_tree), ("selfplay", gen_selfplay), ("play", gen_play)):
         if len(sys.argv) > 1 and name not in sys.argv[1:]:
             continue
         d = fn(ref)

@@ -243,3 +243,43 @@ def test_headless_play_mode_ai_vs_ai(tmp_path, monkeypatch):
         g2 = ChessGame(2, "net", 64, network=g.cchess_engine.policy_value_netowrk)
         g2.start(max_moves=4)
     assert g2.cchess_engine.game_borad.round == 5
+
+
+def test_play_mode_surface_against_reference_vectors(tmp_path, monkeypatch):
+    """select_move / get_hint / human_move / check_end (main.py:1278-1329, 1380-1491) replayed against what the reference
+    itself returned (tests/golden/play.json), for human_color 'b' and 'w' (the rank-flip convention) and the 'net' branches."""
+    monkeypatch.chdir(tmp_path)
+    import contextlib, io
+    from cchess_zero_b200.selfplay import cchess_main
+    from oracle.fakenets_np import FAKE_NETS
+
+    class Net:
+        def __init__(self, f):
+            self.forward = f
+
+    for sc in load_golden("play.json")["scripts"]:
+        m = cchess_main(playout=sc["playouts"], in_search_threads=1, network=Net(FAKE_NETS[sc["net"]]), exploration=False,
+                        human_color=sc["human_color"], log_file=False)
+        if sc["seed"] is not None:
+            np.random.seed(sc["seed"])
+        with contextlib.redirect_stdout(io.StringIO()), np.errstate(all="ignore"):
+            for i, st in enumerate(sc["steps"]):
+                op = st["op"]
+                if op in ("select_move_mcts", "select_move_net"):
+                    mv, wr = m.select_move("mcts" if op.endswith("mcts") else "net")
+                    assert [int(x) for x in mv] == st["move"], (sc["human_color"], i)
+                    assert float(wr).hex() == st["win_rate"], (sc["human_color"], i)
+                    assert m.game_borad.state == st["state"]
+                    if "player" in st:
+                        assert m.game_borad.current_player == st["player"] and m.game_borad.restrict_round == st["rr"]
+                elif op in ("get_hint_mcts", "get_hint_net"):
+                    hint = m.get_hint("mcts" if op.endswith("mcts") else "net", op.endswith("mcts"), lambda: None)
+                    assert [[a, float(p).hex()] for a, p in hint] == st["hint"], (sc["human_color"], i, op)
+                elif op == "human_move_mcts":
+                    wr = m.human_move(tuple(st["coord"]), "mcts")
+                    assert float(wr).hex() == st["win_rate"], (sc["human_color"], i)
+                    assert m.game_borad.state == st["state"] and m.game_borad.current_player == st["player"]
+                    assert m.game_borad.restrict_round == st["rr"]
+                elif op == "check_end":
+                    ended, who = m.check_end()
+                    assert bool(ended) == st["ended"] and who == st["who"]
