@@ -170,3 +170,37 @@ def test_data_parallel_train_step_keeps_replicas_in_sync_gloo(tmp_path):
                         "--master-port", "29533", str(script)], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "DP_OK" in r.stdout
+
+
+def test_train_step_matches_written_out_reference_update_rule():
+    """train_step_module against a float64 restatement of policy_value_network.py:76-126: softmax-CE + MSE + 1e-4*sum(w^2)/2,
+    tf.clip_by_global_norm(100), MomentumOptimizer(momentum 0.9, use_nesterov=True): accum = m*accum + g; w -= lr*(g + m*accum)."""
+    from cchess_zero_b200.net import PolicyValueNet, train_step_module
+    torch.manual_seed(3)
+    net = PolicyValueNet(1)
+    ref = PolicyValueNet(1).double()
+    ref.load_state_dict({k: v.double() for k, v in net.state_dict().items()})
+    opt = torch.optim.SGD(net.parameters(), lr=1e-3, momentum=0.9, nesterov=True)
+    g = torch.Generator().manual_seed(5)
+    x = (torch.rand(10, 9, 10, 14, generator=g) < 0.03).float()
+    pi = torch.softmax(torch.randn(10, 2086, generator=g) * 3, 1)
+    z = torch.sign(torch.randn(10, 1, generator=g))
+    lr, m, c = 0.02, 0.9, 1e-4
+    accum = [torch.zeros_like(p) for p in ref.parameters()]
+    for step in range(3):
+        acc, loss = train_step_module(net, opt, x, pi, z, lr)
+        ref.train()
+        lo, v = ref(x.double())
+        rloss = (-(pi.double() * torch.log_softmax(lo, 1)).sum(1)).mean() + ((v - z.double()) ** 2).mean() \
+            + c * sum((p ** 2).sum() / 2 for p in ref.parameters())
+        grads = torch.autograd.grad(rloss, list(ref.parameters()))
+        gn = torch.sqrt(sum((gr ** 2).sum() for gr in grads))
+        scale = min(1.0, 100.0 / float(gn))
+        with torch.no_grad():
+            for p, gr, a in zip(ref.parameters(), grads, accum):
+                gr = gr * scale
+                a.mul_(m).add_(gr)
+                p.sub_(lr * (gr + m * a))
+        assert abs(loss - float(rloss)) < 1e-4 * max(1.0, abs(float(rloss)))
+    for p, q in zip(net.parameters(), ref.parameters()):
+        assert torch.allclose(p.double(), q, atol=2e-5, rtol=1e-4)
