@@ -104,6 +104,11 @@ struct Dev {
     uint8_t *leaf_board;
     uint16_t *leaf_moves, *leaf_li;   // [B][128]: move list and (flipped) label index of the pending leaf, filled by k_prepare_leaves
     int32_t *leaf_n;                  // [B]: number of moves, -1 = not prepared
+    int K;                            // leaves per game per wave (1 = the reference's search_threads=1 schedule)
+    uint8_t *pendK;                   // [B][K] leaf-parallel mode: per-slot pending flag, path length, path, leaf board
+    int32_t *plenK;
+    uint2 *pathK;
+    uint8_t *leafK;
     int prepared;                     // 1: k_wave trusts leaf_moves / leaf_li / leaf_n (cz_engine_prepare_leaves ran after the previous wave)
     uint32_t *arena;
     uint8_t *cur;
@@ -141,8 +146,8 @@ __device__ __forceinline__ unsigned long long dkey(double s) {
 
 // VL undo + back_up_value along the recorded path (main.py:426-435, 189-194).
 // val = value handed to the deepest edge; sign alternates going up.
-__device__ void warp_backup(const Dev &E, int g, uint32_t *ar, int depth, float val, int lane) {
-    const uint2 *path = E.path + (size_t)g * MAXD;
+// `inflight`: leaf-parallel mode keeps a per-edge count of playouts currently holding a virtual loss on it (META bits 24-30).
+__device__ void warp_backup_path(const uint2 *path, uint32_t *ar, int depth, float val, int lane, bool inflight) {
     for (int d = lane; d < depth; d += 32) {
         const uint2 pe = path[d];
         const uint32_t slot = pe.x, cs = pe.y;
@@ -153,14 +158,18 @@ __device__ void warp_backup(const Dev &E, int g, uint32_t *ar, int depth, float 
         W = __fadd_rn(__fadd_rn(W, 3.0f), v);
         ar[slot + cs] = __float_as_uint(W);
         ar[slot + 2 * cs] = (uint32_t)N;
+        if (inflight) ar[slot + 3 * cs] -= (1u << 24);
     }
     __syncwarp();
+}
+__device__ __forceinline__ void warp_backup(const Dev &E, int g, uint32_t *ar, int depth, float val, int lane) {
+    warp_backup_path(E.path + (size_t)g * MAXD, ar, depth, val, lane, false);
 }
 
 // Move list of the pending leaf of game g in reference order + the label index of every move (with flip_policy,
 // main.py:1152-1155, folded into the index: rank y -> 9-y for black).  Leaves S.moves[i] / li in S.li[i]; returns n.
-__device__ int warp_leaf_moves(const Dev &E, int g, WarpSmem &S, uint32_t &errf, int lane) {
-    const uint32_t *lb = reinterpret_cast<const uint32_t *>(E.leaf_board + (size_t)g * 96);
+__device__ int warp_leaf_moves_at(const Dev &E, const uint8_t *leaf_board, WarpSmem &S, uint32_t &errf, int lane) {
+    const uint32_t *lb = reinterpret_cast<const uint32_t *>(leaf_board);
     if (lane < 24) reinterpret_cast<uint32_t *>(S.board)[lane] = lb[lane];
     __syncwarp();
     const int lside = S.board[90];
@@ -182,12 +191,17 @@ __device__ int warp_leaf_moves(const Dev &E, int g, WarpSmem &S, uint32_t &errf,
     return n;
 }
 
-// leaf_node.expand (main.py:175-187) for the pending leaf of game g; returns false on error
-__device__ bool warp_expand(const Dev &E, int g, uint32_t *ar, WarpSmem &S, const float *logits, int pend, int depth, int lane) {
+__device__ __forceinline__ int warp_leaf_moves(const Dev &E, int g, WarpSmem &S, uint32_t &errf, int lane) {
+    return warp_leaf_moves_at(E, E.leaf_board + (size_t)g * 96, S, errf, lane);
+}
+
+// leaf_node.expand (main.py:175-187) for a pending leaf of game g; returns false on error.
+// lg: that leaf's logits row; path/depth: its recorded path; leaf_board: its board (+ side in byte 90).
+__device__ bool warp_expand_at(const Dev &E, int g, uint32_t *ar, WarpSmem &S, const float *lg, int pend, const uint2 *path, int depth,
+                               const uint8_t *leaf_board, bool allow_prepared, int lane) {
     uint32_t errf = 0;
     int n;
-    const float *lg = logits + (size_t)g * CZ_NLABEL;
-    if (E.prepared && E.leaf_n[g] >= 0) {
+    if (allow_prepared && E.prepared && E.leaf_n[g] >= 0) {
         // the move list was generated by k_prepare_leaves while the network was running
         n = E.leaf_n[g];
         for (int i = lane; i < n; i += 32) {
@@ -196,7 +210,7 @@ __device__ bool warp_expand(const Dev &E, int g, uint32_t *ar, WarpSmem &S, cons
         }
         if (n == 0) errf |= CZ_ERR_NOMOVES;
     } else {
-        n = warp_leaf_moves(E, g, S, errf, lane);
+        n = warp_leaf_moves_at(E, leaf_board, S, errf, lane);
         for (int i = lane; i < n; i += 32) S.ps[i] = __ldg(lg + S.li[i]);
     }
     const uint32_t cs = (uint32_t)((n + 7) & ~7), size = HDR + 5 * cs;
@@ -228,8 +242,9 @@ __device__ bool warp_expand(const Dev &E, int g, uint32_t *ar, WarpSmem &S, cons
             E.root_base[g] = base;
             E.root_cnt[g] = n;
         } else {
-            const uint2 pe = E.path[(size_t)g * MAXD + depth - 1];
-            ar[pe.x + 3 * pe.y] = (ar[pe.x + 3 * pe.y] & 0xFFFFu) | ((uint32_t)n << 16);
+            // META: move (0-15) | n_children (16-23) | in-flight count (24-30, leaf-parallel mode) | claimed (31)
+            const uint2 pe = path[depth - 1];
+            ar[pe.x + 3 * pe.y] = (ar[pe.x + 3 * pe.y] & 0x7F00FFFFu) | ((uint32_t)n << 16);   // links the child, clears `claimed`
             ar[pe.x + 4 * pe.y] = base;
         }
         E.cnt_expand[g] += 1;
@@ -238,18 +253,21 @@ __device__ bool warp_expand(const Dev &E, int g, uint32_t *ar, WarpSmem &S, cons
     __syncwarp();
     return true;
 }
+__device__ __forceinline__ bool warp_expand(const Dev &E, int g, uint32_t *ar, WarpSmem &S, const float *logits, int pend, int depth, int lane) {
+    return warp_expand_at(E, g, ar, S, logits + (size_t)g * CZ_NLABEL, pend, E.path + (size_t)g * MAXD, depth, E.leaf_board + (size_t)g * 96, true, lane);
+}
 
+// row: index of this leaf's row in the network batch (g in one-leaf mode, g*K+slot in leaf-parallel mode)
 template <typename T>
-__device__ void store_leaf(const Dev &E, int g, WarpSmem &S, int side, T *nn_in, int lane) {
+__device__ void store_leaf_at(uint8_t *leaf_board, WarpSmem &S, int side, T *nn_in, size_t row, int lane) {
     if (lane == 0) S.board[90] = (uint8_t)side;
     __syncwarp();
-    uint32_t *lb = reinterpret_cast<uint32_t *>(E.leaf_board + (size_t)g * 96);
+    uint32_t *lb = reinterpret_cast<uint32_t *>(leaf_board);
     if (lane < 24) lb[lane] = reinterpret_cast<const uint32_t *>(S.board)[lane];
-    if (lane == 0) E.leaf_n[g] = -1;          // no prepared move list for this leaf yet
     if constexpr (sizeof(T) == 1) {
         // CZ_BOARD: the evaluator reads the side-to-move-canonical board itself (try_flip, main.py:560-574);
         // cz_net_first_conv applies the reference's cell indexing, so no [9][10][14] tensor is written.
-        uint8_t *o = reinterpret_cast<uint8_t *>(nn_in) + (size_t)g * 96;
+        uint8_t *o = reinterpret_cast<uint8_t *>(nn_in) + row * 96;
         for (int i = lane; i < 96; i += 32) {
             int p = 0;
             if (i < 90) {
@@ -259,8 +277,13 @@ __device__ void store_leaf(const Dev &E, int g, WarpSmem &S, int side, T *nn_in,
             o[i] = (uint8_t)p;
         }
     } else {
-        cz::warp_encode<T>(S.board, side, nn_in + (size_t)g * CZ_ENC_LEN, lane);
+        cz::warp_encode<T>(S.board, side, nn_in + row * CZ_ENC_LEN, lane);
     }
+}
+template <typename T>
+__device__ __forceinline__ void store_leaf(const Dev &E, int g, WarpSmem &S, int side, T *nn_in, int lane) {
+    if (lane == 0) E.leaf_n[g] = -1;          // no prepared move list for this leaf yet
+    store_leaf_at<T>(E.leaf_board + (size_t)g * 96, S, side, nn_in, (size_t)g, lane);
 }
 
 // One wave for one game (one warp).  DO_EXPAND: consume the previous evaluation; DO_SELECT: run playouts
@@ -388,7 +411,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_wave(Dev E, T *nn_in, 
             if (rr >= 60) { tval = 0.0f; break; }        // main.py:415-416
             if (child == NONE) { leaf = true; break; }   // main.py:357: not expanded -> evaluate
             base = child;
-            cnt = (int)(meta >> 16);
+            cnt = (int)((meta >> 16) & 0xFFu);
             parentN = eN + 3;                            // the child's N carries the virtual loss just added
         }
         if (depth > maxdep) maxdep = depth;
@@ -412,6 +435,180 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_wave(Dev E, T *nn_in, 
 }
 
 __constant__ uint8_t c_start[96];   // start position, uploaded by cz_engine_create
+
+// ---- leaf-parallel wave: up to K leaves per game per launch (virtual-loss batching inside one tree) ---------------
+// NOT the reference's coroutine schedule (that one depends on the event loop) and therefore not bit-comparable
+// with search_threads > 1 of the reference; with K = 1 it is exactly the one-leaf kernel above (tested against the oracle).
+// Differences from k_wave: every slot has its own path / leaf board / network row; an edge counts the playouts that
+// currently hold a virtual loss on it (META bits 24-30) so that Q is taken from the loss-free statistics like the reference's
+// stale Q (main.py:403-404 never touches Q); an unexpanded child that is already being evaluated is `claimed` (bit 31) and a
+// second descent that reaches it backs off (the reference waits on now_expanding, main.py:354-355).
+template <typename T>
+__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_wave_multi(Dev E, T *nn_in, const float *logits, const float *value) {
+    __shared__ WarpSmem smem[WARPS_PER_BLOCK];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int g = blockIdx.x * WARPS_PER_BLOCK + w;
+    if (g >= E.B) return;
+    if (!E.active[g]) return;
+    WarpSmem &S = smem[w];
+    uint32_t *ar = arena_of(E, g);
+    const int K = E.K;
+    int done = E.done[g];
+
+    // ---- phase 1: consume the evaluations of the previous wave, slot by slot ----
+    for (int s = 0; s < K; s++) {
+        const size_t idx = (size_t)g * K + s;
+        const int pend = E.pendK[idx];
+        if (!pend) continue;
+        const int depth = E.plenK[idx];
+        const uint2 *path = E.pathK + idx * MAXD;
+        const bool ok = warp_expand_at(E, g, ar, S, logits + idx * CZ_NLABEL, pend, path, depth, E.leafK + idx * 96, false, lane);
+        if (pend == 1) {
+            warp_backup_path(path, ar, depth, ok ? -value[idx] : 0.0f, lane, true);
+            done++;
+            if (lane == 0) E.cnt_playout[g] += 1;
+        }
+        if (lane == 0) E.pendK[idx] = 0;
+        if (!ok && pend == 2) { if (lane == 0) E.active[g] = 0; return; }
+        __syncwarp();
+    }
+    if (lane == 0) E.done[g] = done;
+
+    const int target = E.target[g];
+    const int side0 = E.side[g], rr0 = E.rr[g];
+    const uint32_t *rb = reinterpret_cast<const uint32_t *>(E.root_board + (size_t)g * 96);
+    if (E.root_cnt[g] < 0) {   // root expansion first (main.py:475-487), one slot
+        if (lane < 24) reinterpret_cast<uint32_t *>(S.board)[lane] = rb[lane];
+        __syncwarp();
+        store_leaf_at<T>(E.leafK + (size_t)g * K * 96, S, side0, nn_in, (size_t)g * K, lane);
+        if (lane == 0) { E.pendK[(size_t)g * K] = 2; E.plenK[(size_t)g * K] = 0; }
+        return;
+    }
+
+    // ---- phase 2: up to K descents with virtual loss ----
+    unsigned long long accL = 0, accC = 0;
+    int maxdep = 0, inflight = 0, budget = MAX_INKERNEL_PLAYOUTS + K;
+    bool stop = false;
+    for (int s = 0; s < K && !stop; s++) {
+        const size_t idx = (size_t)g * K + s;
+        uint2 *path = E.pathK + idx * MAXD;
+        while (done + inflight < target && budget-- > 0) {
+            if (lane < 24) reinterpret_cast<uint32_t *>(S.board)[lane] = rb[lane];
+            __syncwarp();
+            int side = side0, rr = rr0, depth = 0;
+            uint32_t base = E.root_base[g];
+            int cnt = E.root_cnt[g];
+            int parentN = E.root_N[g];
+            int outcome = 0;   // 1 leaf, 2 terminal, 3 collision, 4 fault
+            float tval = 0.0f;
+            for (;;) {
+                if (cnt <= 0 || depth >= MAXD) {
+                    if (lane == 0) atomicOr(E.err + g, cnt <= 0 ? CZ_ERR_NOMOVES : CZ_ERR_DEPTH);
+                    outcome = 4;
+                    break;
+                }
+                const uint32_t cs = (uint32_t)((cnt + 7) & ~7);
+                uint32_t *blk = ar + base + HDR;
+                const double sq = __dsqrt_rn((double)parentN);
+                double bs = 0.0;
+                uint32_t bi = NONE, bmeta = 0, bchild = NONE;
+                float bW = 0.f;
+                int bN = 0;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int i = lane + 32 * k;
+                    if (i < cnt) {
+                        const float P = __uint_as_float(blk[i]);
+                        const float W = __uint_as_float(blk[cs + i]);
+                        const int N = (int)blk[2 * cs + i];
+                        const uint32_t meta = blk[3 * cs + i], child = blk[4 * cs + i];
+                        const int c = (int)((meta >> 24) & 0x7Fu);                       // playouts holding a virtual loss here
+                        const int Nr = N - 3 * c;
+                        const float Wr = c ? __fadd_rn(W, (float)(3 * c)) : W;
+                        const float Q = Nr > 0 ? __fdiv_rn(Wr, (float)Nr) : 0.0f;          // Q of the last real backup
+                        const float p5 = __fmul_rn(5.0f, P);
+                        const double U = __ddiv_rn(__dmul_rn((double)p5, sq), (double)(1 + N));
+                        double sc = __dadd_rn((double)Q, U);
+                        if (i > 0 && sc != sc) sc = -INFINITY;
+                        if (k == 0 || sc > bs) { bs = sc; bi = (uint32_t)i; bmeta = meta; bchild = child; bW = W; bN = N; }
+                    }
+                }
+                const bool nan0 = __shfl_sync(CZ_FULL, (int)(bs != bs), 0) != 0;
+                uint32_t e;
+                if (nan0) e = 0;
+                else {
+                    const unsigned long long key = bi == NONE ? 0ull : dkey(__dadd_rn(bs, 0.0));
+                    const uint32_t hi = (uint32_t)(key >> 32), lo = (uint32_t)key;
+                    const uint32_t mhi = __reduce_max_sync(CZ_FULL, hi);
+                    const uint32_t mlo = __reduce_max_sync(CZ_FULL, hi == mhi ? lo : 0u);
+                    e = __reduce_min_sync(CZ_FULL, (bi != NONE && hi == mhi && lo == mlo) ? bi : NONE);
+                }
+                const int owner = e & 31;
+                const uint32_t meta = __shfl_sync(CZ_FULL, bmeta, owner);
+                const uint32_t child = __shfl_sync(CZ_FULL, bchild, owner);
+                const int eN = __shfl_sync(CZ_FULL, bN, owner);
+                const bool claimed = (meta & 0x80000000u) != 0;
+                const int src = meta & 127, dst = (meta >> 7) & 127;
+                const int cap = S.board[dst];
+                const bool term = cap == 1 || cap == 8 || (cap == 0 ? rr + 1 : 0) >= 60;
+                if (child == NONE && claimed && !term) { outcome = 3; break; }     // someone else is evaluating this leaf
+                if (lane == owner) {  // virtual loss + in-flight count (+ claim when this becomes our leaf)
+                    blk[cs + e] = __float_as_uint(__fadd_rn(bW, -3.0f));
+                    blk[2 * cs + e] = (uint32_t)(bN + 3);
+                    blk[3 * cs + e] = (bmeta + (1u << 24)) | ((child == NONE && !term) ? 0x80000000u : 0u);
+                }
+                if (lane == 0) path[depth] = make_uint2(base + HDR + e, cs);
+                depth++;
+                accL += 1; accC += (unsigned)cnt;
+                __syncwarp();
+                if (lane == 0) { S.board[dst] = S.board[src]; S.board[src] = 0; }
+                __syncwarp();
+                side ^= 1;
+                rr = cap == 0 ? rr + 1 : 0;
+                if (cap == 1 || cap == 8) {
+                    const float v = cap == 1 ? (side == 1 ? 1.0f : -1.0f) : (side == 1 ? -1.0f : 1.0f);
+                    tval = -v; outcome = 2;
+                    break;
+                }
+                if (rr >= 60) { tval = 0.0f; outcome = 2; break; }
+                if (child == NONE) { outcome = 1; break; }
+                base = child;
+                cnt = (int)((meta >> 16) & 0xFFu);
+                parentN = eN + 3;
+            }
+            if (depth > maxdep) maxdep = depth;
+            __syncwarp();
+            if (outcome == 1) {
+                store_leaf_at<T>(E.leafK + idx * 96, S, side, nn_in, idx, lane);
+                if (lane == 0) { E.pendK[idx] = 1; E.plenK[idx] = depth; }
+                inflight++;
+                break;                                   // next slot
+            }
+            if (outcome == 3) {                          // back off: take the virtual losses of this partial path back
+                for (int d = lane; d < depth; d += 32) {
+                    const uint2 pe = path[d];
+                    ar[pe.x + pe.y] = __float_as_uint(__fadd_rn(__uint_as_float(ar[pe.x + pe.y]), 3.0f));
+                    ar[pe.x + 2 * pe.y] -= 3u;
+                    ar[pe.x + 3 * pe.y] -= (1u << 24);
+                }
+                __syncwarp();
+                stop = true;
+                break;
+            }
+            warp_backup_path(path, ar, depth, tval, lane, true);   // terminal (or faulted) playout
+            done++;
+            if (lane == 0) E.cnt_playout[g] += 1;
+            if (outcome == 4) { stop = true; break; }
+        }
+        if (!(done + inflight < target)) break;
+    }
+    if (lane == 0) {
+        E.done[g] = done;
+        E.cnt_L[g] += accL;
+        E.cnt_c[g] += accC;
+        if (maxdep > E.max_depth[g]) E.max_depth[g] = maxdep;
+    }
+}
 
 // ---- move generation of the pending leaves, off the critical path -------------------------------------------
 // Runs on a side stream underneath the network evaluation of the same leaves: the next k_wave then only gathers
@@ -451,6 +648,7 @@ __global__ void k_reset(Dev E, const uint8_t *mask, const uint8_t *boards, const
     E.pending[g] = 0;
     E.active[g] = 0;
     E.path_len[g] = 0;
+    if (E.pendK) for (int s = 0; s < E.K; s++) E.pendK[(size_t)g * E.K + s] = 0;
     E.leaf_n[g] = -1;
     E.alloc[g] = 0;
     E.terminal[g] = 0;
@@ -476,7 +674,10 @@ __global__ void k_begin(Dev E, const uint8_t *mask, int playouts) {
 __global__ void k_unfinished(Dev E, int32_t *out) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     int u = 0;
-    if (g < E.B && E.active[g]) u = (E.pending[g] || E.root_cnt[g] < 0 || E.done[g] < E.target[g]) ? 1 : 0;
+    if (g < E.B && E.active[g]) {
+        u = (E.pending[g] || E.root_cnt[g] < 0 || E.done[g] < E.target[g]) ? 1 : 0;
+        if (E.pendK) for (int s = 0; s < E.K; s++) u |= E.pendK[(size_t)g * E.K + s] ? 1 : 0;
+    }
     u = __reduce_add_sync(CZ_FULL, u);
     if ((threadIdx.x & 31) == 0 && u) atomicAdd(out, u);
 }
@@ -524,7 +725,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_play(Dev E) {
     uint32_t alloc = 0;
     int ncnt = -1;
     if (child != NONE) {
-        ncnt = (int)(meta >> 16);
+        ncnt = (int)((meta >> 16) & 0xFFu);
         uint32_t size = HDR + 5 * (uint32_t)((ncnt + 7) & ~7);
         for (uint32_t i = lane; i < size; i += 32) neu[i] = old[child + i];
         alloc = size;
@@ -539,7 +740,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_play(Dev E) {
                 uint32_t oc = NONE, sz = 0;
                 if (i < c) {
                     oc = blk[4 * cs + i];
-                    if (oc != NONE) sz = HDR + 5 * (((blk[3 * cs + i] >> 16) + 7) & ~7u);
+                    if (oc != NONE) sz = HDR + 5 * ((((blk[3 * cs + i] >> 16) & 0xFFu) + 7) & ~7u);
                 }
                 int tot;
                 const uint32_t off = alloc + (uint32_t)cz::warp_excl_scan((int)sz, lane, tot);
@@ -815,7 +1016,16 @@ static int dalloc(cz_engine *e, T **p, size_t count, bool zero = true) {
 }  // extern "C++"
 
 int cz_engine_create(int n_games, int64_t arena_words, int device, cz_engine **out) {
+    return cz_engine_create_ex(n_games, arena_words, device, 1, out);
+}
+
+int cz_engine_leaves(const cz_engine *e) { return e ? e->d.K : CZ_EINVAL; }
+
+int cz_engine_create_ex(int n_games, int64_t arena_words, int device, int leaves, cz_engine **out) {
     if (n_games <= 0 || !out) return fail(CZ_EINVAL, "cz_engine_create: bad arguments");
+    const bool multi = leaves != 1;            // leaves == -1: the leaf-parallel kernel with one slot (test hook)
+    const int K = leaves < 0 ? -leaves : leaves;
+    if (K < 1 || K > 64) return fail(CZ_EINVAL, "cz_engine_create_ex: leaves must be 1..64");
     if (arena_words <= 0) arena_words = 2ll << 20;
     if (arena_words < 4096 || arena_words >= (1ll << 31)) return fail(CZ_EINVAL, "cz_engine_create: arena_words out of range");
     arena_words = (arena_words + 31) & ~31ll;
@@ -826,6 +1036,8 @@ int cz_engine_create(int n_games, int64_t arena_words, int device, cz_engine **o
     d.B = n_games;
     d.A = arena_words;
     d.prepared = 0;
+    d.K = K;
+    d.pendK = nullptr; d.plenK = nullptr; d.pathK = nullptr; d.leafK = nullptr;
     const size_t B = (size_t)n_games;
     int rc = 0;
 #define AL(ptr, cnt) if (!rc) rc = dalloc(e, &ptr, cnt)
@@ -837,6 +1049,7 @@ int cz_engine_create(int n_games, int64_t arena_words, int device, cz_engine **o
     AL(d.st_n, B); AL(d.st_visits, B * CZ_MAXCHILD); AL(d.st_choice, B); AL(d.st_moves, B * CZ_MAXCHILD);
     AL(d.st_w, B * CZ_MAXCHILD); AL(d.st_p, B * CZ_MAXCHILD); AL(d.st_q, B * CZ_MAXCHILD); AL(d.st_count, 8);
     AL(e->d_mask, B); AL(e->d_boards, B * 90); AL(e->d_sides, B); AL(e->d_rr, B);
+    if (multi) { AL(d.pendK, B * K); AL(d.plenK, B * K); AL(d.pathK, B * K * MAXD); AL(d.leafK, B * K * 96); }
     if (!rc) { uint32_t *a = nullptr; rc = dalloc(e, &a, B * 2 * (size_t)arena_words, false); d.arena = a; }
 #undef AL
     if (rc) { cz_engine_destroy(e); return rc; }
@@ -931,14 +1144,27 @@ static int launch_wave(cz_engine *e, void *stream, void *nn_in, int dt, const fl
 
 int cz_engine_wave(cz_engine *e, void *stream, void *nn_in, int nn_dtype, const float *logits, const float *value) {
     if (!e || !nn_in || !logits || !value) return fail(CZ_EINVAL, "cz_engine_wave: null");
+    if (e->d.pendK) {   // leaf-parallel engine
+        dim3 gr(nblk(e->d.B, WARPS_PER_BLOCK)), bl(32 * WARPS_PER_BLOCK);
+        cudaStream_t st = (cudaStream_t)stream;
+        if (nn_dtype == CZ_F32) k_wave_multi<float><<<gr, bl, 0, st>>>(e->d, (float *)nn_in, logits, value);
+        else if (nn_dtype == CZ_BF16) k_wave_multi<__nv_bfloat16><<<gr, bl, 0, st>>>(e->d, (__nv_bfloat16 *)nn_in, logits, value);
+        else if (nn_dtype == CZ_F16) k_wave_multi<__half><<<gr, bl, 0, st>>>(e->d, (__half *)nn_in, logits, value);
+        else if (nn_dtype == CZ_BOARD) k_wave_multi<uint8_t><<<gr, bl, 0, st>>>(e->d, (uint8_t *)nn_in, logits, value);
+        else return fail(CZ_EINVAL, "wave: nn_dtype");
+        CUDA_TRY(cudaGetLastError());
+        return CZ_OK;
+    }
     return launch_wave<true, true>(e, stream, nn_in, nn_dtype, logits, value);
 }
 int cz_engine_select(cz_engine *e, void *stream, void *nn_in, int nn_dtype) {
     if (!e || !nn_in) return fail(CZ_EINVAL, "cz_engine_select: null");
+    if (e->d.pendK) return fail(CZ_EINVAL, "cz_engine_select: leaf-parallel engines only support cz_engine_wave");
     return launch_wave<false, true>(e, stream, nn_in, nn_dtype, nullptr, nullptr);
 }
 int cz_engine_expand_backup(cz_engine *e, void *stream, const float *logits, const float *value) {
     if (!e || !logits || !value) return fail(CZ_EINVAL, "cz_engine_expand_backup: null");
+    if (e->d.pendK) return fail(CZ_EINVAL, "cz_engine_expand_backup: leaf-parallel engines only support cz_engine_wave");
     return launch_wave<true, false>(e, stream, (void *)logits, CZ_F32, logits, value);
 }
 
@@ -1086,7 +1312,7 @@ int cz_engine_tree_signature(cz_engine *e, void *stream, int game, int64_t *out,
         Q = N > 0 ? W / (float)N : 0.0f;
         uint32_t qb;
         memcpy(&qb, &Q, 4);
-        const int nch = child != NONE ? (int)(meta >> 16) : 0;
+        const int nch = child != NONE ? (int)((meta >> 16) & 0xFFu) : 0;
         if (k < cap && out) {
             int64_t *r = out + 6 * k;
             r[0] = L.of[(meta & 127) * CZ_NSQ + ((meta >> 7) & 127)];

@@ -22,13 +22,17 @@ def _stream():
 
 
 class Engine:
-    def __init__(self, n_games, arena_words=0, device=None):
+    def __init__(self, n_games, arena_words=0, device=None, leaves=1):
+        """leaves > 1: leaf-parallel engine (up to `leaves` leaves per game per wave; network rows = n_games*leaves).
+        leaves == -1: the leaf-parallel kernel with one slot (test hook)."""
         if not torch.cuda.is_available():
             raise EngineError("cchess_zero_b200 needs a CUDA device (no CPU fallback exists)")
         self.device = torch.cuda.current_device() if device is None else int(device)
         self.B = int(n_games)
+        self.leaves = abs(int(leaves))
+        self.rows = self.B * self.leaves
         h = C.c_void_p()
-        check(lib().cz_engine_create(self.B, int(arena_words), self.device, C.byref(h)), "cz_engine_create")
+        check(lib().cz_engine_create_ex(self.B, int(arena_words), self.device, int(leaves), C.byref(h)), "cz_engine_create_ex")
         self.h = h
         self.launches = 0   # kernels of csrc/cz_engine.cu launched through this handle
         self._count = torch.zeros(1, dtype=torch.int32, device="cuda:%d" % self.device)

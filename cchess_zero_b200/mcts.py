@@ -51,7 +51,9 @@ class _Root(object):
 
 
 class MCTS_tree(object):
-    def __init__(self, in_state, in_forward, search_threads, arena_words=1 << 21):
+    def __init__(self, in_state, in_forward, search_threads, arena_words=1 << 21, leaf_parallel=1):
+        """leaf_parallel = K > 1 evaluates up to K leaves of this tree per network call (virtual-loss batching; faster moves,
+        deterministic, but no longer the reference's search_threads=1 visit counts).  Default 1 = bit-exact mode."""
         self.noise_eps = 0.25
         self.dirichlet_alpha = 0.3
         # main.py:238 draws from np.random here (a 1-element Dirichlet is always [1.]); kept so that the
@@ -61,25 +63,27 @@ class MCTS_tree(object):
         self.forward = in_forward
         self.virtual_loss = 3
         self.search_threads = search_threads
-        self.engine = Engine(1, arena_words)
+        self.K = max(1, int(leaf_parallel))
+        self.engine = Engine(1, arena_words, leaves=self.K)
         dev = torch.device("cuda", self.engine.device)
         owner = getattr(in_forward, "__self__", None)
-        self._logits = torch.zeros((1, NLABEL), dtype=torch.float32, device=dev)
-        self._value = torch.zeros((1,), dtype=torch.float32, device=dev)
+        K = self.K
+        self._logits = torch.zeros((K, NLABEL), dtype=torch.float32, device=dev)
+        self._value = torch.zeros((K,), dtype=torch.float32, device=dev)
         self._plan = self._graph = None
         if owner is not None and hasattr(owner, "native_plan") and getattr(owner, "precision", "") == "fp16":
             # the evaluator is this package's network: stay on the device (board bytes -> cz_net kernels -> tower) and
             # replay one CUDA graph per playout
-            self._plan = owner.native_plan(1)
-            self._nn_in = self._plan.make_input(1)
+            self._plan = owner.native_plan(K)
+            self._nn_in = self._plan.make_input(K)
             self._dev_forward = lambda x, lo, v: self._plan(x, lo, v)
         else:
             self._dev_forward = getattr(owner, "forward_device", None)
             dt = getattr(owner, "nn_dtype", torch.float32) if self._dev_forward else torch.float32
-            self._nn_in = torch.zeros((1, 9, 10, 14), dtype=dt, device=dev)
-        self._h_in = torch.zeros((1, 9, 10, 14), dtype=torch.float32).pin_memory()
-        self._h_logits = torch.zeros((1, NLABEL), dtype=torch.float32).pin_memory()
-        self._h_value = torch.zeros((1,), dtype=torch.float32).pin_memory()
+            self._nn_in = torch.zeros((K, 9, 10, 14), dtype=dt, device=dev)
+        self._h_in = torch.zeros((K, 9, 10, 14), dtype=torch.float32).pin_memory()
+        self._h_logits = torch.zeros((K, NLABEL), dtype=torch.float32).pin_memory()
+        self._h_value = torch.zeros((K,), dtype=torch.float32).pin_memory()
         self.root = _Root(self)
         self._set_position(in_state, "w", 0)
         rules._init_tables()
@@ -96,8 +100,8 @@ class MCTS_tree(object):
             return
         self._h_in.copy_(nn_in.float(), non_blocking=False)
         probs, value = self.forward(self._h_in.numpy())
-        self._h_logits.copy_(torch.as_tensor(np.asarray(probs, dtype=np.float32).reshape(1, NLABEL)))
-        self._h_value[0] = float(np.asarray(value).reshape(-1)[0])
+        self._h_logits.copy_(torch.as_tensor(np.asarray(probs, dtype=np.float32).reshape(self.K, NLABEL)))
+        self._h_value.copy_(torch.as_tensor(np.asarray(value, dtype=np.float32).reshape(self.K)))
         self._logits.copy_(self._h_logits, non_blocking=True)
         self._value.copy_(self._h_value, non_blocking=True)
 

@@ -469,7 +469,7 @@ from collections import defaultdict, deque
 class cchess_main(object):
 
     def __init__(self, playout=400, in_batch_size=128, exploration=True, in_search_threads=16, processor="cpu",
-                 num_gpus=1, res_block_nums=7, human_color="b", network=None, log_file=True):
+                 num_gpus=1, res_block_nums=7, human_color="b", network=None, log_file=True, leaf_parallel=1):
         from .mcts import MCTS_tree
         from .net import policy_value_network, policy_value_network_gpus
         rules._init_tables()
@@ -491,7 +491,7 @@ class cchess_main(object):
         else:  # `processor` selected CPU/GPU TensorFlow in the reference (main.py:1142); both map to the CUDA net here
             self.policy_value_netowrk = policy_value_network(res_block_nums) if processor == "cpu" else policy_value_network_gpus(num_gpus, res_block_nums)
         self.search_threads = in_search_threads
-        self.mcts = MCTS_tree(self.game_borad.state, self.policy_value_netowrk.forward, self.search_threads)
+        self.mcts = MCTS_tree(self.game_borad.state, self.policy_value_netowrk.forward, self.search_threads, leaf_parallel=leaf_parallel)
         self.exploration = exploration
         self.resign_threshold = -0.8
         self.global_step = 0

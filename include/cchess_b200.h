@@ -83,6 +83,13 @@ typedef struct cz_engine cz_engine;
 /* arena_words: uint32 words of tree storage per game per half (two halves, ping-pong re-rooting);
  * 0 selects the default (2 Mi words = 8 MiB per half). */
 int cz_engine_create(int n_games, int64_t arena_words, int device, cz_engine **out);
+/* Leaf-parallel variant: up to `leaves` (1..64) leaves per game per wave inside one tree (virtual-loss batching; the
+ * search_threads > 1 idea of main.py:337-440 with a deterministic schedule of its own -- not bit-comparable with the
+ * reference's coroutine interleaving).  Network rows are then g*leaves + slot: nn_in [n_games*leaves][...],
+ * logits [n_games*leaves][2086], value [n_games*leaves].  leaves == 1 is cz_engine_create; leaves == -1 runs the
+ * leaf-parallel kernel with a single slot (test hook: must equal the one-leaf kernel bit for bit). */
+int cz_engine_create_ex(int n_games, int64_t arena_words, int device, int leaves, cz_engine **out);
+int cz_engine_leaves(const cz_engine *e);
 int cz_engine_destroy(cz_engine *e);
 int cz_engine_n_games(const cz_engine *e);
 

@@ -283,3 +283,26 @@ def test_play_mode_surface_against_reference_vectors(tmp_path, monkeypatch):
                 elif op == "check_end":
                     ended, who = m.check_end()
                     assert bool(ended) == st["ended"] and who == st["who"]
+
+
+def test_leaf_parallel_move_latency_mode(tmp_path, monkeypatch):
+    """cchess_main(..., leaf_parallel=8): same API, up to 8 leaves of the one tree per network call."""
+    monkeypatch.chdir(tmp_path)
+    import contextlib, io, time
+    from cchess_zero_b200.net import policy_value_network
+    from cchess_zero_b200.selfplay import cchess_main
+    pv = policy_value_network(res_block_nums=7)
+    lat = {}
+    for K in (1, 8):
+        m = cchess_main(playout=400, in_search_threads=16, network=pv, exploration=False, log_file=False, leaf_parallel=K)
+        np.random.seed(0)
+        ts = []
+        with contextlib.redirect_stdout(io.StringIO()):
+            for _ in range(5):
+                t0 = time.perf_counter()
+                m.select_move("mcts")
+                ts.append(time.perf_counter() - t0)
+        lat[K] = min(ts[1:])
+        assert m.game_borad.round == 6
+    print("move latency 400 playouts: K=1 %.4f s, K=8 %.4f s" % (lat[1], lat[8]))
+    assert lat[8] < lat[1]

@@ -117,17 +117,17 @@ def test_fakenets_match_oracle(O, R):
         assert np.array_equal(v.cpu().numpy(), ov.reshape(-1)), kind
 
 
-def _run_cases(cases, net, R, split=False, graph=False):
+def _run_cases(cases, net, R, split=False, graph=False, leaves=1):
     """cases: list of dict(board, side, rr, playouts).  Returns the engine after searching."""
     from cchess_zero_b200.engine import Engine
     from cchess_zero_b200.fakenet import FakeNet
     B = len(cases)
-    e = Engine(B, arena_words=1 << 20)
+    e = Engine(B, arena_words=1 << 20, leaves=leaves)
     e.reset(None, np.stack([c["board"] for c in cases]), [c["side"] for c in cases], [c["rr"] for c in cases])
     fn = FakeNet(net)
-    nn_in = torch.zeros((B, 9, 10, 14), device="cuda")
-    logits = torch.zeros((B, 2086), device="cuda")
-    value = torch.zeros((B,), device="cuda")
+    nn_in = torch.zeros((e.rows, 9, 10, 14), device="cuda")
+    logits = torch.zeros((e.rows, 2086), device="cuda")
+    value = torch.zeros((e.rows,), device="cuda")
     pl = np.array([c["playouts"] for c in cases])
     for p in np.unique(pl):
         e.begin_search(int(p), (pl == p).astype(np.uint8))
@@ -369,3 +369,65 @@ def test_selfplay_full_game_at_1200_playouts_against_reference_vectors(R):
         assert len(rec) == g["n"] and rec.states == g["states"]
         assert [float(z) for z in rec.z] == g["z"]
         assert sha(rec.dense_pi().tobytes()) == g["sha_pi"]
+
+
+def _check_tree_invariants(sig):
+    """sig: DFS records (label, N, Wbits, Pbits, Qbits, n_children).  For every expanded node entered through an edge with N
+    visits: the first visit expanded it, every later visit went on to one child -> sum(children N) == N - 1; no leftover
+    virtual loss anywhere (it would break the identity by multiples of 3)."""
+    pos = 0
+
+    def node(n_children):
+        nonlocal pos
+        tot = 0
+        for _ in range(n_children):
+            lab, N, _, _, _, nc = sig[pos]
+            pos += 1
+            tot += int(N)
+            if nc > 0:
+                s = node(int(nc))
+                assert s == int(N) - 1, (lab, N, s)
+        return tot
+
+    # root: find its child count = number of top-level records
+    top = 0
+    i = 0
+    def skip(i):
+        nc = int(sig[i][5]); i += 1
+        for _ in range(nc):
+            i = skip(i)
+        return i
+    while i < len(sig):
+        i = skip(i); top += 1
+    return node(top)
+
+
+def test_leaf_parallel_kernel_with_one_slot_equals_reference_vectors(R):
+    """k_wave_multi with K = 1 must be the one-leaf kernel: same golden trees of the reference, bit for bit."""
+    for net in ("hash_pos", "hash_signed", "mod17"):
+        cases = [c for c in load_golden("tree.json")["cases"] if c["net"] == net and c["playouts"] <= 600]
+        e = _run_cases([dict(board=R.state_to_board(c["state"]), side=0 if c["player"] == "w" else 1, rr=c["rr"],
+                             playouts=c["playouts"]) for c in cases], net, R, leaves=-1)
+        for g, c in enumerate(cases):
+            assert sha(e.tree_signature(g).tobytes()) == c["sha_sig"], c["note"]
+
+
+@pytest.mark.parametrize("K", [4, 16])
+def test_leaf_parallel_search_conserves_visits_and_is_deterministic(K, O, R):
+    boards, sides = _random_positions(O, 2, 31)
+    sel = [i for i in range(0, len(boards), 9) if (boards[i] == 1).any() and (boards[i] == 8).any()][:24]
+    cases = [dict(board=boards[i], side=int(sides[i]), rr=int(i % 50), playouts=300) for i in sel]
+    sigs = []
+    for rep in range(2):
+        e = _run_cases(cases, "hash_pos", R, leaves=K)
+        rc = e.root_children()
+        for g in range(len(cases)):
+            sig = e.tree_signature(g)
+            assert rc["visits"][g, : rc["n"][g]].sum() == 300              # every playout passes exactly one root child
+            assert _check_tree_invariants(sig) == 300
+            if rep == 0:
+                sigs.append(sig)
+            else:
+                assert np.array_equal(sig, sigs[g])                         # deterministic schedule
+        c = e.counters()
+        assert c["n_playout"] == 300 * len(cases)
