@@ -164,7 +164,8 @@ class Engine:
         while True:
             self.wave(nn_in, logits, value)
             waves += 1
-            if waves > playouts and (waves - playouts) % check_every == 0 and self.unfinished() == 0:
+            first = playouts // self.leaves
+            if waves > first and (waves - first) % check_every == 0 and self.unfinished() == 0:
                 break
             forward_dev(nn_in)
             if waves > 4 * playouts + 64:

@@ -172,7 +172,7 @@ class MCTS_tree(object):
             self._graph.replay()
             self.engine.launches += 1
             waves += 1
-            if waves > playouts and self.engine.unfinished() == 0:
+            if waves > playouts // self.K and self.engine.unfinished() == 0:      # K leaves per wave: fewer waves needed
                 break
             if waves > 4 * playouts + 64:
                 self.engine.raise_on_error()
