@@ -7,6 +7,12 @@ np.random.choice(p = 0.75*pi + 0.25*Dirichlet(0.3)) on a legacy MT19937 RandomSt
 RandomState per game slot stands in for the reference's global np.random.  The device
 produces the integer visit counts; everything before them (select / expand / backup / encode /
 move generation / re-rooting) runs in csrc/cz_engine.cu."""
+import os
+import pickle
+import random
+import time
+from collections import defaultdict, deque
+
 import numpy as np
 import torch
 
@@ -460,10 +466,25 @@ class SelfPlay:
 # exactly the call sequence of the reference, so main.py's train loop runs unchanged on top of it.
 # For throughput use SelfPlay (thousands of games per GPU); `selfplay_many` bridges the two.
 # =================================================================================================
-import os
-import random
-import time
-from collections import defaultdict, deque
+def save_replay(path, data_buffer, extra=None):
+    """Persist the replay deque (main.py:1138-1139 keeps it in memory only) together with the global numpy / python RNG
+    states, so that a training run can resume exactly where it stopped.  Atomic: write + rename."""
+    blob = dict(data=list(data_buffer), maxlen=getattr(data_buffer, "maxlen", None), np_state=np.random.get_state(),
+                py_state=random.getstate(), extra=dict(extra or {}))
+    tmp = path + ".tmp"
+    with open(tmp, "wb") as f:
+        pickle.dump(blob, f, protocol=pickle.HIGHEST_PROTOCOL)
+    os.replace(tmp, path)
+
+
+def load_replay(path, restore_rng=True):
+    """-> (deque, extra).  With restore_rng the numpy / python global RNGs continue from the saved point."""
+    with open(path, "rb") as f:
+        blob = pickle.load(f)
+    if restore_rng:
+        np.random.set_state(blob["np_state"])
+        random.setstate(blob["py_state"])
+    return deque(blob["data"], maxlen=blob["maxlen"]), blob["extra"]
 
 
 class cchess_main(object):
@@ -537,6 +558,15 @@ class cchess_main(object):
         if self.log_file:
             self.log_file.write(msg + "\n")
             self.log_file.flush()
+
+    def save_state(self, path):
+        """Replay buffer + lr multiplier + step + RNG states (the reference checkpoints only the network weights)."""
+        save_replay(path, self.data_buffer, dict(lr_multiplier=self.lr_multiplier, global_step=self.global_step))
+
+    def load_state(self, path):
+        self.data_buffer, extra = load_replay(path)
+        self.lr_multiplier = extra.get("lr_multiplier", self.lr_multiplier)
+        self.global_step = extra.get("global_step", self.global_step)
 
     def run(self, max_batches=None):  # main.py:1224-1248
         batch_iter = 0

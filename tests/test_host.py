@@ -204,3 +204,24 @@ def test_train_step_matches_written_out_reference_update_rule():
         assert abs(loss - float(rloss)) < 1e-4 * max(1.0, abs(float(rloss)))
     for p, q in zip(net.parameters(), ref.parameters()):
         assert torch.allclose(p.double(), q, atol=2e-5, rtol=1e-4)
+
+
+def test_replay_persistence_round_trip_and_rng_resume(tmp_path):
+    import random
+    from collections import deque
+    from cchess_zero_b200.selfplay import load_replay, save_replay
+    buf = deque(maxlen=50)
+    rng = np.random.RandomState(0)
+    for i in range(60):
+        buf.append((rng.rand(9, 10, 14).astype(np.float32), rng.rand(2086), float(i % 3 - 1)))
+    np.random.seed(11); random.seed(12)
+    np.random.rand(5); random.random()
+    p = str(tmp_path / "replay.pkl")
+    save_replay(p, buf, dict(lr_multiplier=1.5, global_step=7))
+    expect_np, expect_py = np.random.rand(3), random.random()       # what the run would have drawn next
+    np.random.seed(999); random.seed(999)
+    buf2, extra = load_replay(p)
+    assert extra == dict(lr_multiplier=1.5, global_step=7) and buf2.maxlen == 50 and len(buf2) == 50
+    for a, b in zip(buf, buf2):
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[2] == b[2]
+    assert np.array_equal(np.random.rand(3), expect_np) and random.random() == expect_py
