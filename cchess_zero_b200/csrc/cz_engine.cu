@@ -33,6 +33,7 @@
 #define HDR 8
 #define WARPS_PER_BLOCK 4
 #define MAX_INKERNEL_PLAYOUTS 16
+#define MAX_WPB 10                 // warps per CTA of the wave kernels (10 * sizeof(WarpSmem) < 48 KB)
 
 namespace {
 
@@ -288,11 +289,14 @@ __device__ __forceinline__ void store_leaf(const Dev &E, int g, WarpSmem &S, int
 
 // One wave for one game (one warp).  DO_EXPAND: consume the previous evaluation; DO_SELECT: run playouts
 // until the next leaf.
+// Launch shape: one CTA per SM whenever the games fit (warps per CTA = ceil(B / #SMs), <= MAX_WPB), so that every SM carries
+// the same number of game-warps; shared memory is sized per launch (sizeof(WarpSmem) per warp).
 template <typename T, bool DO_EXPAND, bool DO_SELECT>
-__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_wave(Dev E, T *nn_in, const float *logits, const float *value) {
-    __shared__ WarpSmem smem[WARPS_PER_BLOCK];
+__global__ void __launch_bounds__(32 * MAX_WPB, 1) k_wave(Dev E, T *nn_in, const float *logits, const float *value) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    WarpSmem *smem = reinterpret_cast<WarpSmem *>(smem_raw);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int g = blockIdx.x * WARPS_PER_BLOCK + w;
+    const int g = blockIdx.x * (blockDim.x >> 5) + w;
     if (g >= E.B) return;
     if (!E.active[g]) return;
     WarpSmem &S = smem[w];
@@ -444,10 +448,11 @@ __constant__ uint8_t c_start[96];   // start position, uploaded by cz_engine_cre
 // stale Q (main.py:403-404 never touches Q); an unexpanded child that is already being evaluated is `claimed` (bit 31) and a
 // second descent that reaches it backs off (the reference waits on now_expanding, main.py:354-355).
 template <typename T>
-__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_wave_multi(Dev E, T *nn_in, const float *logits, const float *value) {
-    __shared__ WarpSmem smem[WARPS_PER_BLOCK];
+__global__ void __launch_bounds__(32 * MAX_WPB, 1) k_wave_multi(Dev E, T *nn_in, const float *logits, const float *value) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    WarpSmem *smem = reinterpret_cast<WarpSmem *>(smem_raw);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int g = blockIdx.x * WARPS_PER_BLOCK + w;
+    const int g = blockIdx.x * (blockDim.x >> 5) + w;
     if (g >= E.B) return;
     if (!E.active[g]) return;
     WarpSmem &S = smem[w];
@@ -836,6 +841,7 @@ inline int nblk(int n, int per) { return (n + per - 1) / per; }
 struct cz_engine {
     Dev d;
     int device;
+    int wpb = WARPS_PER_BLOCK;   // warps per CTA of the wave kernels: ceil(B / #SMs) clamped to [1, MAX_WPB]
     std::vector<void *> allocs;
     // pinned host staging
     int32_t *h_n = nullptr, *h_visits = nullptr, *h_choice = nullptr, *h_i32 = nullptr;
@@ -1037,6 +1043,12 @@ int cz_engine_create_ex(int n_games, int64_t arena_words, int device, int leaves
     d.A = arena_words;
     d.prepared = 0;
     d.K = K;
+    {
+        int sms = 148;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sms <= 0) sms = 148;
+        int w = (n_games + sms - 1) / sms;
+        e->wpb = w < 1 ? 1 : (w > MAX_WPB ? MAX_WPB : w);
+    }
     d.pendK = nullptr; d.plenK = nullptr; d.pathK = nullptr; d.leafK = nullptr;
     const size_t B = (size_t)n_games;
     int rc = 0;
@@ -1130,12 +1142,13 @@ int cz_engine_begin_search(cz_engine *e, void *stream, const uint8_t *mask, int 
 extern "C++" {
 template <bool X, bool S>
 static int launch_wave(cz_engine *e, void *stream, void *nn_in, int dt, const float *logits, const float *value) {
-    dim3 gr(nblk(e->d.B, WARPS_PER_BLOCK)), bl(32 * WARPS_PER_BLOCK);
+    dim3 gr(nblk(e->d.B, e->wpb)), bl(32 * e->wpb);
+    const size_t sm = (size_t)e->wpb * sizeof(WarpSmem);
     cudaStream_t st = (cudaStream_t)stream;
-    if (dt == CZ_F32) k_wave<float, X, S><<<gr, bl, 0, st>>>(e->d, (float *)nn_in, logits, value);
-    else if (dt == CZ_BF16) k_wave<__nv_bfloat16, X, S><<<gr, bl, 0, st>>>(e->d, (__nv_bfloat16 *)nn_in, logits, value);
-    else if (dt == CZ_F16) k_wave<__half, X, S><<<gr, bl, 0, st>>>(e->d, (__half *)nn_in, logits, value);
-    else if (dt == CZ_BOARD) k_wave<uint8_t, X, S><<<gr, bl, 0, st>>>(e->d, (uint8_t *)nn_in, logits, value);
+    if (dt == CZ_F32) k_wave<float, X, S><<<gr, bl, sm, st>>>(e->d, (float *)nn_in, logits, value);
+    else if (dt == CZ_BF16) k_wave<__nv_bfloat16, X, S><<<gr, bl, sm, st>>>(e->d, (__nv_bfloat16 *)nn_in, logits, value);
+    else if (dt == CZ_F16) k_wave<__half, X, S><<<gr, bl, sm, st>>>(e->d, (__half *)nn_in, logits, value);
+    else if (dt == CZ_BOARD) k_wave<uint8_t, X, S><<<gr, bl, sm, st>>>(e->d, (uint8_t *)nn_in, logits, value);
     else return fail(CZ_EINVAL, "wave: nn_dtype");
     CUDA_TRY(cudaGetLastError());
     return CZ_OK;
@@ -1145,12 +1158,13 @@ static int launch_wave(cz_engine *e, void *stream, void *nn_in, int dt, const fl
 int cz_engine_wave(cz_engine *e, void *stream, void *nn_in, int nn_dtype, const float *logits, const float *value) {
     if (!e || !nn_in || !logits || !value) return fail(CZ_EINVAL, "cz_engine_wave: null");
     if (e->d.pendK) {   // leaf-parallel engine
-        dim3 gr(nblk(e->d.B, WARPS_PER_BLOCK)), bl(32 * WARPS_PER_BLOCK);
+        dim3 gr(nblk(e->d.B, e->wpb)), bl(32 * e->wpb);
+        const size_t sm = (size_t)e->wpb * sizeof(WarpSmem);
         cudaStream_t st = (cudaStream_t)stream;
-        if (nn_dtype == CZ_F32) k_wave_multi<float><<<gr, bl, 0, st>>>(e->d, (float *)nn_in, logits, value);
-        else if (nn_dtype == CZ_BF16) k_wave_multi<__nv_bfloat16><<<gr, bl, 0, st>>>(e->d, (__nv_bfloat16 *)nn_in, logits, value);
-        else if (nn_dtype == CZ_F16) k_wave_multi<__half><<<gr, bl, 0, st>>>(e->d, (__half *)nn_in, logits, value);
-        else if (nn_dtype == CZ_BOARD) k_wave_multi<uint8_t><<<gr, bl, 0, st>>>(e->d, (uint8_t *)nn_in, logits, value);
+        if (nn_dtype == CZ_F32) k_wave_multi<float><<<gr, bl, sm, st>>>(e->d, (float *)nn_in, logits, value);
+        else if (nn_dtype == CZ_BF16) k_wave_multi<__nv_bfloat16><<<gr, bl, sm, st>>>(e->d, (__nv_bfloat16 *)nn_in, logits, value);
+        else if (nn_dtype == CZ_F16) k_wave_multi<__half><<<gr, bl, sm, st>>>(e->d, (__half *)nn_in, logits, value);
+        else if (nn_dtype == CZ_BOARD) k_wave_multi<uint8_t><<<gr, bl, sm, st>>>(e->d, (uint8_t *)nn_in, logits, value);
         else return fail(CZ_EINVAL, "wave: nn_dtype");
         CUDA_TRY(cudaGetLastError());
         return CZ_OK;
