@@ -62,6 +62,138 @@ __global__ void __launch_bounds__(256) k_first_conv(const uint8_t *__restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------
+// first convolution on the 5th-generation tensor cores (tcgen05 + TMEM), one 128-cell tile per CTA.
+//   D[128 cells][128 ch] (f32, TMEM) = A[128][144] . B[144][128],  K = 9 taps x 16 "piece slots"
+//   A is ONE-HOT and never exists in global memory: thread r builds row r (its cell's 3x3 neighbourhood, one 16-wide
+//   slot per tap with a 1.0 at the piece code; code 0 = empty / off-board hits an all-zero weight row) straight into
+//   shared memory in the canonical K-major no-swizzle UMMA layout; B (the folded conv weights, same layout, prepared once
+//   on the host) is copied from L2.  One elected thread issues 9 tcgen05.mma (M128 N128 K16, kind::f16, f32 accumulate),
+//   commits to an mbarrier; the four warps read their TMEM lane quarter back with tcgen05.ld, add bias, ReLU, store fp16.
+// Shared-memory operand layout (both A and B): [k-chunk of 8 halves (18)][8-row group (16)][row in group (8)][8 halves]
+//   -> core matrix = 128 contiguous bytes, SBO (next 8-row group) = 128 B, LBO (next k-chunk) = 2048 B.
+// ------------------------------------------------------------------------------------------
+constexpr int TC_TILE_BYTES = 18 * 16 * 128;   // 36 864 B per operand
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint64_t umma_desc_kmajor_noswizzle(uint32_t smem_addr) {
+    // cute::UMMA::SmemDescriptor (mma_sm100_desc.hpp): start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout_type=0 (no swizzle) [61,64)
+    return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)(2048u >> 4) << 16) | ((uint64_t)(128u >> 4) << 32) | (1ull << 46);
+}
+
+__global__ void __launch_bounds__(128) k_first_conv_tc(const uint8_t *__restrict__ boards, int B, const uint4 *__restrict__ wB /* TC_TILE_BYTES */,
+                                                        const float *__restrict__ bias /* [128] */, __half *__restrict__ out /* [B][90][128] */) {
+    extern __shared__ __align__(128) unsigned char smem_tc[];
+    unsigned char *sA = smem_tc, *sB = smem_tc + TC_TILE_BYTES;
+    __shared__ __align__(8) uint64_t mbar;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const long long total = (long long)B * 90;
+    const long long c = (long long)blockIdx.x * 128 + tid;          // this thread's cell = row `tid` of the tile
+
+    if (warp == 0) {   // TMEM: 128 columns x 128 lanes of f32 accumulators
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(128u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&mbar)), "r"(1u));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // B operand: straight copy of the pre-arranged weights
+    for (int i = tid; i < TC_TILE_BYTES / 16; i += 128) reinterpret_cast<uint4 *>(sB)[i] = __ldg(wB + i);
+    // A operand: one-hot row of this thread's cell
+    {
+        int pc[9];
+#pragma unroll
+        for (int t = 0; t < 9; t++) pc[t] = 0;
+        if (c < total) {
+            const int pos = (int)(c / 90), cell = (int)(c - (long long)pos * 90);
+            const int r = cell / 10, f = cell - r * 10;
+            const uint8_t *bd = boards + (size_t)pos * 96;
+#pragma unroll
+            for (int t = 0; t < 9; t++) {
+                const int rr = r + t / 3 - 1, ff = f + t % 3 - 1;
+                if (rr >= 0 && rr < 9 && ff >= 0 && ff < 10) pc[t] = bd[rr * 9 + ff];    // the reference's cell <- s[rank*9+file]
+            }
+        }
+        unsigned char *rowp = sA + (tid >> 3) * 128 + (tid & 7) * 16;
+#pragma unroll
+        for (int t = 0; t < 9; t++) {
+            const uint32_t one = 0x3C00u << ((pc[t] & 1) * 16);      // fp16 1.0 in the low or high half of a word
+            const int w = pc[t] >> 1;                                  // word 0..7 inside the 16-wide slot
+            uint4 lo, hi;
+            lo.x = w == 0 ? one : 0u; lo.y = w == 1 ? one : 0u; lo.z = w == 2 ? one : 0u; lo.w = w == 3 ? one : 0u;
+            hi.x = w == 4 ? one : 0u; hi.y = w == 5 ? one : 0u; hi.z = w == 6 ? one : 0u; hi.w = w == 7 ? one : 0u;
+            *reinterpret_cast<uint4 *>(rowp + (2 * t) * 2048) = lo;
+            *reinterpret_cast<uint4 *>(rowp + (2 * t + 1) * 2048) = hi;
+        }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy smem writes -> visible to the tensor core
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_slot;
+
+    if (tid == 0) {
+        // instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1<<4), a/b F16 K-major, N=128 (16<<17), M=128 (8<<24)
+        const uint32_t idesc = (1u << 4) | (16u << 17) | (8u << 24);
+        const uint64_t da = umma_desc_kmajor_noswizzle(smem_u32(sA)), db = umma_desc_kmajor_noswizzle(smem_u32(sB));
+#pragma unroll
+        for (int t = 0; t < 9; t++) {
+            const uint64_t a = da + (uint64_t)((t * 4096) >> 4), b = db + (uint64_t)((t * 4096) >> 4);   // two k-chunks per MMA
+            const uint32_t acc = t > 0 ? 1u : 0u;
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                         ::"r"(tmem), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mbar)) : "memory");
+    }
+    // wait for the MMAs (phase 0 of the mbarrier)
+    {
+        const uint32_t bar = smem_u32(&mbar);
+        asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
+                     ::"r"(bar), "r"(0u) : "memory");
+    }
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // epilogue: warp w owns TMEM lanes 32w..32w+31 = tile rows; thread = one row, 4 x 32 columns
+    {
+        __half *orow = out + (size_t)c * 128;
+#pragma unroll 1
+        for (int q = 0; q < 4; q++) {
+            uint32_t v[32];
+            const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(q * 32);
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                         "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                           "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                           "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                           "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                         : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (c < total) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    uint4 o;
+                    __half2 *oh = reinterpret_cast<__half2 *>(&o);
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const int ch = q * 32 + j * 8 + k * 2;
+                        const float a0 = __uint_as_float(v[j * 8 + k * 2]) + __ldg(bias + ch);
+                        const float a1 = __uint_as_float(v[j * 8 + k * 2 + 1]) + __ldg(bias + ch + 1);
+                        oh[k] = __floats2half2_rn(fmaxf(a0, 0.f), fmaxf(a1, 0.f));
+                    }
+                    *reinterpret_cast<uint4 *>(orow + q * 32 + j * 8) = o;
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128u));
+}
+
+// ------------------------------------------------------------------------------------------
 // heads, stage 1: conv1x1 (128 -> 3) + bias + ReLU.  One CTA per position; all loads of a warp are issued first.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_head_conv(const __half *__restrict__ x /* [B][90][128] */, int B, const float *__restrict__ wh /* [3][128] */,
@@ -221,6 +353,16 @@ int cz_net_first_conv(const uint8_t *canon_boards, int B, const void *w1, const 
     if (!canon_boards || !w1 || !b1 || !out || B <= 0) return CZ_EINVAL;
     k_first_conv<<<B, 256, 0, (cudaStream_t)stream>>>(canon_boards, B, reinterpret_cast<const __half *>(w1), reinterpret_cast<const float4 *>(b1),
                                                       reinterpret_cast<__half *>(out));
+    return cudaGetLastError() == cudaSuccess ? CZ_OK : CZ_ECUDA;
+}
+
+int cz_net_first_conv_tc(const uint8_t *canon_boards, int B, const void *w_umma, const float *b1, void *out, void *stream) {
+    if (!canon_boards || !w_umma || !b1 || !out || B <= 0) return CZ_EINVAL;
+    const int smem = 2 * TC_TILE_BYTES;   // 73 728 B > 48 KB default: opt in
+    if (cudaFuncSetAttribute(k_first_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return CZ_ECUDA;
+    const long long tiles = ((long long)B * 90 + 127) / 128;
+    k_first_conv_tc<<<(unsigned)tiles, 128, smem, (cudaStream_t)stream>>>(canon_boards, B, reinterpret_cast<const uint4 *>(w_umma), b1,
+                                                                         reinterpret_cast<__half *>(out));
     return cudaGetLastError() == cudaSuccess ? CZ_OK : CZ_ECUDA;
 }
 

@@ -191,10 +191,13 @@ class NativePlan:
     precision = "fp16"
     dtype = torch.uint8
 
-    def __init__(self, net, max_batch):
+    def __init__(self, net, max_batch, first_conv=None):
+        """first_conv: "gather" (CUDA-core gather-add, k_first_conv) or "tc" (tcgen05 + TMEM, k_first_conv_tc)."""
         import ctypes as C
         from ._lib import lib
         self._C, self._lib = C, lib()
+        self.first_conv = first_conv or os.environ.get("CCHESS_FIRST_CONV", "gather")
+        assert self.first_conv in ("gather", "tc")
         base = InferencePlan(net, "fp16")
         self.blocks, self.fused, self._base = base.blocks, base.fused, base
         dev = base.w_in[0].device
@@ -202,6 +205,11 @@ class NativePlan:
             w, b = base.w_in                                                    # folded conv_in: [128,14,3,3] fp16
             self.w1 = w.float().permute(2, 3, 1, 0).reshape(9, 14, 128).to(torch.float16).contiguous()
             self.b1 = b.float().contiguous()
+            # tensor-core variant: K = tap*16 + piece code (codes 0 / 15 are zero rows), canonical K-major UMMA tile
+            # [k-chunk (18)][8-channel group (16)][channel in group (8)][k in chunk (8)]
+            wpad = torch.zeros((9, 16, 128), dtype=torch.float16, device=dev)
+            wpad[:, 1:15, :] = self.w1
+            self.w1_umma = wpad.reshape(18, 8, 16, 8).permute(0, 2, 3, 1).contiguous()
             wh, bh = base.w_head                                                 # [3,128,1,1]
             self.wh = wh.float().reshape(3, 128).contiguous()
             self.bh = bh.float().contiguous()
@@ -226,9 +234,12 @@ class NativePlan:
         B = boards.shape[0]
         assert B <= self.max_batch and boards.dtype == torch.uint8 and logits_out.dtype == torch.float32
         st = self._C.c_void_p(torch.cuda.current_stream().cuda_stream)
-        rc = self._lib.cz_net_first_conv(boards.data_ptr(), B, self.w1.data_ptr(), self.b1.data_ptr(), self.x1.data_ptr(), st)
+        if self.first_conv == "tc":
+            rc = self._lib.cz_net_first_conv_tc(boards.data_ptr(), B, self.w1_umma.data_ptr(), self.b1.data_ptr(), self.x1.data_ptr(), st)
+        else:
+            rc = self._lib.cz_net_first_conv(boards.data_ptr(), B, self.w1.data_ptr(), self.b1.data_ptr(), self.x1.data_ptr(), st)
         if rc:
-            raise RuntimeError("cz_net_first_conv failed (%d)" % rc)
+            raise RuntimeError("cz_net_first_conv (%s) failed (%d)" % (self.first_conv, rc))
         x = self.x1[:B].permute(0, 3, 1, 2)                                     # NCHW view of NHWC memory = channels_last
         for c1, c2 in self.blocks:
             y = self._base._conv_relu(x, c1, 1)
@@ -325,10 +336,10 @@ class policy_value_network(object):
             self._plan = InferencePlan(self.net, self.precision)
         return self._plan
 
-    def native_plan(self, max_batch):
+    def native_plan(self, max_batch, first_conv=None):
         """fp16 plan with the hand-written first-conv / head kernels (engine path); see NativePlan."""
         self.net.eval()
-        return NativePlan(self.net, max_batch)
+        return NativePlan(self.net, max_batch, first_conv)
 
     @property
     def nn_dtype(self):
