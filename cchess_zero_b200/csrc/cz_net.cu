@@ -81,15 +81,18 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor_noswizzle(uint32_t smem_add
     return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)(2048u >> 4) << 16) | ((uint64_t)(128u >> 4) << 32) | (1ull << 46);
 }
 
+// Persistent: each CTA copies B and allocates TMEM once, then walks tiles blockIdx.x, +gridDim.x, ... (two CTAs per SM so that one
+// CTA's epilogue overlaps the other's operand build).  The bias rides in the GEMM: slot 15 of the centre tap is a constant 1 in A
+// and the bias row in B, so the epilogue is ReLU + fp16 convert only.
 __global__ void __launch_bounds__(128) k_first_conv_tc(const uint8_t *__restrict__ boards, int B, const uint4 *__restrict__ wB /* TC_TILE_BYTES */,
-                                                        const float *__restrict__ bias /* [128] */, __half *__restrict__ out /* [B][90][128] */) {
+                                                        __half *__restrict__ out /* [B][90][128] */) {
     extern __shared__ __align__(128) unsigned char smem_tc[];
     unsigned char *sA = smem_tc, *sB = smem_tc + TC_TILE_BYTES;
     __shared__ __align__(8) uint64_t mbar;
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5;
     const long long total = (long long)B * 90;
-    const long long c = (long long)blockIdx.x * 128 + tid;          // this thread's cell = row `tid` of the tile
+    const long long tiles = (total + 127) / 128;
 
     if (warp == 0) {   // TMEM: 128 columns x 128 lanes of f32 accumulators
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(128u));
@@ -99,10 +102,20 @@ __global__ void __launch_bounds__(128) k_first_conv_tc(const uint8_t *__restrict
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&mbar)), "r"(1u));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    // B operand: straight copy of the pre-arranged weights
-    for (int i = tid; i < TC_TILE_BYTES / 16; i += 128) reinterpret_cast<uint4 *>(sB)[i] = __ldg(wB + i);
-    // A operand: one-hot row of this thread's cell
-    {
+    for (int i = tid; i < TC_TILE_BYTES / 16; i += 128) reinterpret_cast<uint4 *>(sB)[i] = __ldg(wB + i);   // B operand, once
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_slot;
+    // instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1<<4), a/b F16 K-major, N=128 (16<<17), M=128 (8<<24)
+    const uint32_t idesc = (1u << 4) | (16u << 17) | (8u << 24);
+    const uint64_t da = umma_desc_kmajor_noswizzle(smem_u32(sA)), db = umma_desc_kmajor_noswizzle(smem_u32(sB));
+    unsigned char *rowp = sA + (tid >> 3) * 128 + (tid & 7) * 16;
+    uint32_t phase = 0;
+
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const long long c = tile * 128 + tid;                       // this thread's cell = row `tid` of the tile
+        // ---- A operand: one-hot row of this thread's cell ----
         int pc[9];
 #pragma unroll
         for (int t = 0; t < 9; t++) pc[t] = 0;
@@ -116,7 +129,6 @@ __global__ void __launch_bounds__(128) k_first_conv_tc(const uint8_t *__restrict
                 if (rr >= 0 && rr < 9 && ff >= 0 && ff < 10) pc[t] = bd[rr * 9 + ff];    // the reference's cell <- s[rank*9+file]
             }
         }
-        unsigned char *rowp = sA + (tid >> 3) * 128 + (tid & 7) * 16;
 #pragma unroll
         for (int t = 0; t < 9; t++) {
             const uint32_t one = 0x3C00u << ((pc[t] & 1) * 16);      // fp16 1.0 in the low or high half of a word
@@ -124,39 +136,33 @@ __global__ void __launch_bounds__(128) k_first_conv_tc(const uint8_t *__restrict
             uint4 lo, hi;
             lo.x = w == 0 ? one : 0u; lo.y = w == 1 ? one : 0u; lo.z = w == 2 ? one : 0u; lo.w = w == 3 ? one : 0u;
             hi.x = w == 4 ? one : 0u; hi.y = w == 5 ? one : 0u; hi.z = w == 6 ? one : 0u; hi.w = w == 7 ? one : 0u;
+            if (t == 4) hi.w |= 0x3C000000u;                           // slot 15 of the centre tap: constant 1 -> bias row of B
             *reinterpret_cast<uint4 *>(rowp + (2 * t) * 2048) = lo;
             *reinterpret_cast<uint4 *>(rowp + (2 * t + 1) * 2048) = hi;
         }
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy smem writes -> visible to the tensor core
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem = tmem_slot;
-
-    if (tid == 0) {
-        // instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1<<4), a/b F16 K-major, N=128 (16<<17), M=128 (8<<24)
-        const uint32_t idesc = (1u << 4) | (16u << 17) | (8u << 24);
-        const uint64_t da = umma_desc_kmajor_noswizzle(smem_u32(sA)), db = umma_desc_kmajor_noswizzle(smem_u32(sB));
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic-proxy smem writes -> visible to the tensor core
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (tid == 0) {
 #pragma unroll
-        for (int t = 0; t < 9; t++) {
-            const uint64_t a = da + (uint64_t)((t * 4096) >> 4), b = db + (uint64_t)((t * 4096) >> 4);   // two k-chunks per MMA
-            const uint32_t acc = t > 0 ? 1u : 0u;
-            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-                         ::"r"(tmem), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+            for (int t = 0; t < 9; t++) {
+                const uint64_t a = da + (uint64_t)((t * 4096) >> 4), b = db + (uint64_t)((t * 4096) >> 4);   // two k-chunks per MMA
+                const uint32_t acc = t > 0 ? 1u : 0u;
+                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                             "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                             ::"r"(tmem), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mbar)) : "memory");
         }
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mbar)) : "memory");
-    }
-    // wait for the MMAs (phase 0 of the mbarrier)
-    {
-        const uint32_t bar = smem_u32(&mbar);
-        asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
-                     ::"r"(bar), "r"(0u) : "memory");
-    }
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    // epilogue: warp w owns TMEM lanes 32w..32w+31 = tile rows; thread = one row, 4 x 32 columns
-    {
+        {   // wait for this tile's MMAs
+            const uint32_t bar = smem_u32(&mbar);
+            asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
+                         ::"r"(bar), "r"(phase) : "memory");
+            phase ^= 1u;
+        }
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // ---- epilogue: warp w owns TMEM lanes 32w..32w+31 = tile rows; thread = one row, 4 x 32 columns ----
         __half *orow = out + (size_t)c * 128;
 #pragma unroll 1
         for (int q = 0; q < 4; q++) {
@@ -177,19 +183,17 @@ __global__ void __launch_bounds__(128) k_first_conv_tc(const uint8_t *__restrict
                     uint4 o;
                     __half2 *oh = reinterpret_cast<__half2 *>(&o);
 #pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        const int ch = q * 32 + j * 8 + k * 2;
-                        const float a0 = __uint_as_float(v[j * 8 + k * 2]) + __ldg(bias + ch);
-                        const float a1 = __uint_as_float(v[j * 8 + k * 2 + 1]) + __ldg(bias + ch + 1);
-                        oh[k] = __floats2half2_rn(fmaxf(a0, 0.f), fmaxf(a1, 0.f));
-                    }
+                    for (int k = 0; k < 4; k++)
+                        oh[k] = __floats2half2_rn(fmaxf(__uint_as_float(v[j * 8 + k * 2]), 0.f), fmaxf(__uint_as_float(v[j * 8 + k * 2 + 1]), 0.f));
                     *reinterpret_cast<uint4 *>(orow + q * 32 + j * 8) = o;
                 }
             }
         }
+        // the next tile overwrites A (its MMAs are complete: mbarrier) and the accumulators (every warp must have drained its lanes)
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128u));
 }
 
@@ -361,8 +365,12 @@ int cz_net_first_conv_tc(const uint8_t *canon_boards, int B, const void *w_umma,
     const int smem = 2 * TC_TILE_BYTES;   // 73 728 B > 48 KB default: opt in
     if (cudaFuncSetAttribute(k_first_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return CZ_ECUDA;
     const long long tiles = ((long long)B * 90 + 127) / 128;
-    k_first_conv_tc<<<(unsigned)tiles, 128, smem, (cudaStream_t)stream>>>(canon_boards, B, reinterpret_cast<const uint4 *>(w_umma), b1,
-                                                                         reinterpret_cast<__half *>(out));
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long grid = tiles < 2LL * sms ? tiles : 2LL * sms;    // persistent: two CTAs per SM
+    (void)b1;                                                         // the bias is row (centre tap, slot 15) of w_umma
+    k_first_conv_tc<<<(unsigned)grid, 128, smem, (cudaStream_t)stream>>>(canon_boards, B, reinterpret_cast<const uint4 *>(w_umma),
+                                                                        reinterpret_cast<__half *>(out));
     return cudaGetLastError() == cudaSuccess ? CZ_OK : CZ_ECUDA;
 }
 

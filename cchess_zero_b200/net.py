@@ -209,6 +209,7 @@ class NativePlan:
             # [k-chunk (18)][8-channel group (16)][channel in group (8)][k in chunk (8)]
             wpad = torch.zeros((9, 16, 128), dtype=torch.float16, device=dev)
             wpad[:, 1:15, :] = self.w1
+            wpad[4, 15, :] = self.b1.to(torch.float16)       # bias rides in the GEMM: A has a constant 1 in (centre tap, slot 15)
             self.w1_umma = wpad.reshape(18, 8, 16, 8).permute(0, 2, 3, 1).contiguous()
             wh, bh = base.w_head                                                 # [3,128,1,1]
             self.wh = wh.float().reshape(3, 128).contiguous()

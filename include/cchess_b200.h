@@ -175,7 +175,8 @@ int cz_engine_tree_signature(cz_engine *e, void *stream, int game, int64_t *out,
 int cz_net_first_conv(const uint8_t *canon_boards, int B, const void *w1, const float *b1, void *out, void *stream);
 /* Same result on the tcgen05 tensor cores: the one-hot im2col matrix is built in shared memory, the accumulators live in
  * TMEM.  w_umma: dev fp16, the weights in the canonical K-major UMMA layout [18 k-chunks][16 groups][8 channels][8 k]
- * with k = tap*16 + piece code (codes 0 and 15 are zero rows); 36 864 bytes.  b1: dev f32 [128]. */
+ * with k = tap*16 + piece code (code 0 rows are zero; row (centre tap, code 15) holds the bias, every other code-15 row is
+ * zero); 36 864 bytes.  b1 is ignored (kept for signature symmetry with cz_net_first_conv). */
 int cz_net_first_conv_tc(const uint8_t *canon_boards, int B, const void *w_umma, const float *b1, void *out, void *stream);
 int cz_net_heads(const void *x, int B, const float *wh, const float *bh, const float *w1t, const float *b1, const float *w2, float b2,
                  const void *wp, const float *bp, void *hp_scratch, float *hv_scratch, float *logits, float *value, void *stream);
