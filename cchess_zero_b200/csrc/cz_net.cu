@@ -162,8 +162,11 @@ __global__ void __launch_bounds__(128) k_first_conv_tc(const uint8_t *__restrict
             phase ^= 1u;
         }
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // ---- epilogue: warp w owns TMEM lanes 32w..32w+31 = tile rows; thread = one row, 4 x 32 columns ----
-        __half *orow = out + (size_t)c * 128;
+        // ---- epilogue: warp w owns TMEM lanes 32w..32w+31 = tile rows; thread = one row, 4 x 32 columns.  The fp16 row is
+        // staged in shared memory (the A tile is dead once the mbarrier fired) with an XOR swizzle on the 16-byte chunk index,
+        // then written with fully coalesced 512-byte warp stores (two rows per instruction). ----
+        unsigned char *stage = sA + warp * (32 * 256);                 // this warp's 32 rows x 256 B
+        const int lane = tid & 31;
 #pragma unroll 1
         for (int q = 0; q < 4; q++) {
             uint32_t v[32];
@@ -177,15 +180,27 @@ __global__ void __launch_bounds__(128) k_first_conv_tc(const uint8_t *__restrict
                            "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                          : "r"(taddr));
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (c < total) {
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    uint4 o;
-                    __half2 *oh = reinterpret_cast<__half2 *>(&o);
+            for (int j = 0; j < 4; j++) {
+                uint4 o;
+                __half2 *oh = reinterpret_cast<__half2 *>(&o);
 #pragma unroll
-                    for (int k = 0; k < 4; k++)
-                        oh[k] = __floats2half2_rn(fmaxf(__uint_as_float(v[j * 8 + k * 2]), 0.f), fmaxf(__uint_as_float(v[j * 8 + k * 2 + 1]), 0.f));
-                    *reinterpret_cast<uint4 *>(orow + q * 32 + j * 8) = o;
+                for (int k = 0; k < 4; k++)
+                    oh[k] = __floats2half2_rn(fmaxf(__uint_as_float(v[j * 8 + k * 2]), 0.f), fmaxf(__uint_as_float(v[j * 8 + k * 2 + 1]), 0.f));
+                const int chunk = q * 4 + j;
+                *reinterpret_cast<uint4 *>(stage + lane * 256 + ((chunk ^ (lane & 15)) << 4)) = o;
+            }
+        }
+        __syncwarp();
+        {
+            const long long row0 = tile * 128 + warp * 32;             // first cell of this warp's 32 rows
+            const int half = lane >> 4, ch = lane & 15;
+#pragma unroll 4
+            for (int i = 0; i < 16; i++) {
+                const int r = 2 * i + half;
+                if (row0 + r < total) {
+                    const uint4 o = *reinterpret_cast<const uint4 *>(stage + r * 256 + ((ch ^ (r & 15)) << 4));
+                    *reinterpret_cast<uint4 *>(out + (size_t)(row0 + r) * 128 + ch * 8) = o;
                 }
             }
         }
