@@ -81,8 +81,8 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor_noswizzle(uint32_t smem_add
     return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)(2048u >> 4) << 16) | ((uint64_t)(128u >> 4) << 32) | (1ull << 46);
 }
 
-// Persistent: each CTA copies B and allocates TMEM once, then walks tiles blockIdx.x, +gridDim.x, ... (two CTAs per SM so that one
-// CTA's epilogue overlaps the other's operand build).  The bias rides in the GEMM: slot 15 of the centre tap is a constant 1 in A
+// Persistent: each CTA copies B and allocates TMEM once, then walks tiles blockIdx.x, +gridDim.x, ... (three CTAs per SM so that one
+// CTA's epilogue overlaps the others' operand build).  The bias rides in the GEMM: slot 15 of the centre tap is a constant 1 in A
 // and the bias row in B, so the epilogue is ReLU + fp16 convert only.
 __global__ void __launch_bounds__(128) k_first_conv_tc(const uint8_t *__restrict__ boards, int B, const uint4 *__restrict__ wB /* TC_TILE_BYTES */,
                                                         __half *__restrict__ out /* [B][90][128] */) {
@@ -113,10 +113,8 @@ __global__ void __launch_bounds__(128) k_first_conv_tc(const uint8_t *__restrict
     unsigned char *rowp = sA + (tid >> 3) * 128 + (tid & 7) * 16;
     uint32_t phase = 0;
 
-    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        const long long c = tile * 128 + tid;                       // this thread's cell = row `tid` of the tile
-        // ---- A operand: one-hot row of this thread's cell ----
-        int pc[9];
+    // piece codes of the 3x3 neighbourhood of cell c (0 = empty / outside the board / beyond the batch)
+    auto load_codes = [&](long long c, int (&pc)[9]) {
 #pragma unroll
         for (int t = 0; t < 9; t++) pc[t] = 0;
         if (c < total) {
@@ -126,9 +124,15 @@ __global__ void __launch_bounds__(128) k_first_conv_tc(const uint8_t *__restrict
 #pragma unroll
             for (int t = 0; t < 9; t++) {
                 const int rr = r + t / 3 - 1, ff = f + t % 3 - 1;
-                if (rr >= 0 && rr < 9 && ff >= 0 && ff < 10) pc[t] = bd[rr * 9 + ff];    // the reference's cell <- s[rank*9+file]
+                if (rr >= 0 && rr < 9 && ff >= 0 && ff < 10) pc[t] = __ldg(bd + rr * 9 + ff);   // the reference's cell <- s[rank*9+file]
             }
         }
+    };
+    int pc[9], pcn[9];
+    load_codes((long long)blockIdx.x * 128 + tid, pc);
+
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        // ---- A operand: one-hot row of this thread's cell (row `tid` of the tile) ----
 #pragma unroll
         for (int t = 0; t < 9; t++) {
             const uint32_t one = 0x3C00u << ((pc[t] & 1) * 16);      // fp16 1.0 in the low or high half of a word
@@ -155,6 +159,7 @@ __global__ void __launch_bounds__(128) k_first_conv_tc(const uint8_t *__restrict
             }
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mbar)) : "memory");
         }
+        load_codes((tile + gridDim.x) * 128 + tid, pcn);             // next tile's board bytes fly while the tensor core works
         {   // wait for this tile's MMAs
             const uint32_t bar = smem_u32(&mbar);
             asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
@@ -208,6 +213,8 @@ __global__ void __launch_bounds__(128) k_first_conv_tc(const uint8_t *__restrict
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+        for (int t = 0; t < 9; t++) pc[t] = pcn[t];
     }
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128u));
 }
@@ -382,7 +389,7 @@ int cz_net_first_conv_tc(const uint8_t *canon_boards, int B, const void *w_umma,
     const long long tiles = ((long long)B * 90 + 127) / 128;
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const long long grid = tiles < 2LL * sms ? tiles : 2LL * sms;    // persistent: two CTAs per SM
+    const long long grid = tiles < 3LL * sms ? tiles : 3LL * sms;    // persistent: three CTAs per SM (3 x 74 KB smem, 3 x 128 TMEM columns)
     (void)b1;                                                         // the bias is row (centre tap, slot 15) of w_umma
     k_first_conv_tc<<<(unsigned)grid, 128, smem, (cudaStream_t)stream>>>(canon_boards, B, reinterpret_cast<const uint4 *>(w_umma),
                                                                         reinterpret_cast<__half *>(out));
