@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--res-blocks", type=int, default=7)
     ap.add_argument("--precision", default=os.environ.get("CCHESS_NN_PRECISION", "fp16"))
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--first-conv", default=None, choices=["gather", "tc"], help="first-layer kernel: CUDA-core gather-add or tcgen05/TMEM")
     ap.add_argument("--overlap-movegen", action="store_true", help="leaf move generation on a side stream under the network (measured: no gain)")
     ap.add_argument("--lanes", type=int, default=1, choices=[1, 2], help="2 = pipeline two half-batches (tree kernel under the other half's network)")
     ap.add_argument("--library-ends", action="store_true", help="use cuDNN/cuBLAS for the first conv and the heads instead of csrc/cz_net.cu")
@@ -238,7 +239,7 @@ def run_ours(a, rank, world, local_rank):
     B = a.games
     pv = policy_value_network(a.res_blocks, precision=a.precision, device=local_rank, seed=0)
     native = a.precision == "fp16" and not a.library_ends
-    factory = (lambda n: pv.native_plan(n)) if native else (lambda n: pv.plan())
+    factory = (lambda n: pv.native_plan(n, a.first_conv)) if native else (lambda n: pv.plan())
     plan = factory(B // a.lanes)
     sp = SelfPlay(B, None, a.playouts, seeds=[rank * B + g for g in range(B)], device=local_rank,
                   auto_reset=True, keep_records=True, plan=plan if a.lanes == 1 else None, plan_factory=factory, lanes=a.lanes,
@@ -358,7 +359,7 @@ def run_ours(a, rank, world, local_rank):
                                 games_per_gpu=B, playouts=a.playouts, res_block_nums=a.res_blocks, search_threads=1, exploration=True,
                                 cuda_graph=not a.no_graph, lanes=a.lanes, movegen_under_network=bool(sp.overlap_movegen and not a.no_graph and a.lanes == 1),
                                 fused_conv_epilogue=plan.fused,
-                                network_ends="csrc/cz_net.cu (board-byte first conv, fused heads)" if plan.dtype == torch.uint8 else "library",
+                                network_ends=("csrc/cz_net.cu (board-byte first conv [%s], fused heads)" % plan.first_conv) if plan.dtype == torch.uint8 else "library",
                                 l2_policy="working set (trees %.1f GB + activations) exceeds the 126 MB L2" % (c1["max_arena_words"] * 4 * B / 1e9)),
                     e2e=dict(value=e2e_v, unit="expansions/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, wall_ms=wall_ms),
                     gpu_launches=int(tot_launch), clocks=clk, roofline=roof, cpu_baseline=cpu,
