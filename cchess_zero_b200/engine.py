@@ -8,7 +8,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import BF16, BOARD, F16, F32, MAXCHILD, NLABEL, EngineError, check, lib
+from ._lib import BF16, BOARD, F16, F32, MAXCHILD, EngineError, check, lib
 
 _DT = {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16, torch.uint8: BOARD}
 

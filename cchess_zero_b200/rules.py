@@ -7,7 +7,7 @@ import ctypes as C
 
 import numpy as np
 
-from ._lib import ENC_LEN, MAXCHILD, NLABEL, EngineError, check, lib
+from ._lib import MAXCHILD, NLABEL, EngineError, check, lib
 
 START_STATE = "RNBAKABNR/9/1C5C1/P1P1P1P1P/9/9/p1p1p1p1p/1c5c1/9/rnbakabnr"  # main.py:585
 pieces_order = "KARBNPCkarbnpc"  # main.py:208

@@ -164,8 +164,6 @@ def gen_selfplay(ref):
 
 def gen_play(ref):
     """Play-mode surface (main.py:1278-1329, 1394-1491): select_move / get_hint / human_move / check_end, both human colours."""
-    import struct
-
     def fhex(v):
         return float(v).hex()
 
