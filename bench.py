@@ -333,8 +333,14 @@ def run_ours(a, rank, world, local_rank):
         per_launch = ab / len(kms)
         avg_ms = float(np.mean(kms))
         achieved = per_launch / (avg_ms * 1e-3) / 1e9
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, "profiles", "kwave_traffic.json")
+        if os.path.exists(tpath):        # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture, scaled to this launch size
+            tj = json.load(open(tpath))
+            traffic = (tj["dram_bytes_read_per_launch"] + tj["dram_bytes_write_per_launch"]) * (B // a.lanes) / tj["games_per_launch"]
+            traffic_src = tj["source"]
         roof = dict(kernel="k_wave (expand+backup+select+encode, one warp per game; %d games per launch)" % (B // a.lanes), bound="hbm", achieved=achieved, peak=hbm, unit="GB/s",
-                    frac=achieved / hbm, traffic=None, peak_source=peak_src, avg_launch_ms=avg_ms, p50_launch_ms=float(np.median(kms)), max_launch_ms=float(np.max(kms)),
+                    frac=achieved / hbm, traffic=traffic, traffic_source=traffic_src, peak_source=peak_src, avg_launch_ms=avg_ms, p50_launch_ms=float(np.median(kms)), max_launch_ms=float(np.max(kms)),
                     algorithmic_bytes_per_launch=per_launch,
                     bytes_per_expansion=ab / max(1, d["n_expand"]), launches_timed=len(kms),
                     note="latency-bound pointer-chasing kernel: HBM fraction is reported as required, the binding limits are per-warp dependent loads and the network")
