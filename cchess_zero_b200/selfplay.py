@@ -198,7 +198,7 @@ class SelfPlay:
 
     def __init__(self, n_games, forward, playouts, seeds=None, exploration=True, temperature=1,
                  nn_dtype=torch.float32, arena_words=0, auto_reset=True, device=None, keep_records=True, plan=None,
-                 plan_factory=None, lanes=1, overlap_movegen=False):
+                 plan_factory=None, lanes=1, overlap_movegen=False, engine=None):
         """plan: an InferencePlan / NativePlan (defines the input buffer, writes logits/value in place).
         plan_factory(n) + lanes=2: two half-batches, each with its own engine and plan; the search pipelines them so
         that one half's tree kernel runs under the other half's network (see capture_graph)."""
@@ -218,8 +218,10 @@ class SelfPlay:
             self.engine = _MultiEngine(self.lanes, n_games)
             self.nn_in, self.logits, self.value, forward = None, None, None, None
         else:
-            self.engine = Engine(n_games, arena_words, device)
-            dev = torch.device("cuda", self.engine.device)
+            # `engine`: an object with the Engine interface (tests drive the host loop with a CPU stand-in); the product
+            # always constructs the CUDA engine here
+            self.engine = engine if engine is not None else Engine(n_games, arena_words, device)
+            dev = torch.device("cuda", self.engine.device) if engine is None else torch.device(getattr(engine, "torch_device", "cpu"))
             if plan is None and plan_factory is not None:
                 plan = plan_factory(n_games)
             self.logits = torch.zeros((n_games, NLABEL), dtype=torch.float32, device=dev)
