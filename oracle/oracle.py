@@ -38,6 +38,7 @@ def lib():
         L.co_tree_reload.argtypes = [C.c_void_p, C.c_void_p]
         L.co_tree_search.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, FWD_FN, C.c_void_p]
         L.co_tree_search_fake.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.co_tree_search_multi.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
         L.co_tree_root_children.argtypes = [C.c_void_p] + [C.c_void_p] * 5
         L.co_tree_update.argtypes = [C.c_void_p, C.c_int]
         L.co_tree_root_board.argtypes = [C.c_void_p, C.c_void_p]
@@ -167,6 +168,10 @@ class Tree:
             return lib().co_tree_search(self.h, side, rr, playouts, self._cb, None)
         nid = NET_IDS[net] if isinstance(net, str) else int(net)
         return lib().co_tree_search_fake(self.h, side, rr, playouts, nid)
+
+    def search_multi(self, side, rr, playouts, K, net):
+        """cchess_zero_b200's own leaf-parallel schedule (K leaves per wave), serial specification; see cchess_oracle.c."""
+        return lib().co_tree_search_multi(self.h, side, rr, playouts, int(K), NET_IDS[net] if isinstance(net, str) else int(net))
 
     def root_children(self):
         mv = np.zeros(136, dtype=np.uint16)

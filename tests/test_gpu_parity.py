@@ -431,3 +431,19 @@ def test_leaf_parallel_search_conserves_visits_and_is_deterministic(K, O, R):
                 assert np.array_equal(sig, sigs[g])                         # deterministic schedule
         c = e.counters()
         assert c["n_playout"] == 300 * len(cases)
+
+
+@pytest.mark.parametrize("K", [2, 4, 16])
+def test_leaf_parallel_kernel_equals_its_serial_specification(K, O, R):
+    """k_wave_multi against oracle co_tree_search_multi (an independent serial implementation of the same schedule):
+    full trees bit for bit, over positions with captures, draws and king captures in reach."""
+    boards, sides = _random_positions(O, 3, 57)
+    sel = [i for i in range(0, len(boards), 7) if (boards[i] == 1).any() and (boards[i] == 8).any()][:40]
+    rng = np.random.RandomState(K)
+    cases = [dict(board=boards[i], side=int(sides[i]), rr=int(rng.choice([0, 7, 55, 58])), playouts=int(rng.choice([100, 260, 400]))) for i in sel]
+    for net in ("hash_pos", "hash_signed"):
+        e = _run_cases(cases, net, R, leaves=K)
+        for g, c in enumerate(cases):
+            t = O.Tree(c["board"])
+            assert t.search_multi(c["side"], c["rr"], c["playouts"], K, net) == 0
+            assert np.array_equal(t.signature(), e.tree_signature(g)), (net, K, g)

@@ -101,3 +101,17 @@ def test_selfplay_full_game_at_1200_playouts_against_reference():
     assert len(r["states"]) == g["n"] and r["states"] == g["states"]
     assert [float(v) for v in r["z"]] == g["z"]
     assert sha(np.asarray(r["pis"], dtype=np.float64).tobytes()) == g["sha_pi"]
+
+
+def test_leaf_parallel_spec_with_one_slot_is_the_reference_search():
+    """oracle co_tree_search_multi (the serial spec of the package's own K-leaves-per-wave schedule) must degenerate to the
+    reference-pinned search for K = 1; for K > 1 it must conserve visits."""
+    for net in ("hash_pos", "hash_signed", "mod17"):
+        a, b = O.Tree(), O.Tree()
+        a.search(0, 0, 300, net)
+        assert b.search_multi(0, 0, 300, 1, net) == 0
+        assert np.array_equal(a.signature(), b.signature())
+    for K in (2, 4, 16, 64):
+        t = O.Tree()
+        assert t.search_multi(0, 0, 500, K, "hash_pos") == 0
+        assert t.root_children()[1].sum() == 500 and t.stats()["n_playout"] == 500
