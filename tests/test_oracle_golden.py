@@ -115,3 +115,32 @@ def test_leaf_parallel_spec_with_one_slot_is_the_reference_search():
         t = O.Tree()
         assert t.search_multi(0, 0, 500, K, "hash_pos") == 0
         assert t.root_children()[1].sum() == 500 and t.stats()["n_playout"] == 500
+
+
+def test_rules_are_symmetric_under_the_colour_flip():
+    """Domain property (size independent): flipping the board (rows reversed, colours swapped, try_flip main.py:560-574) and the side
+    to move maps the legal-move SET onto its rank mirror; captures and king-capture terminals map onto each other."""
+    rng = np.random.RandomState(8)
+    b, side = O.from_state(O.START), 0
+    checked = 0
+    for _ in range(3000):
+        mv = O.legal_moves(b, side)
+        fb = O.flip_board(b)
+        fm = O.legal_moves(fb, side ^ 1)
+
+        def mirror(m):
+            s, d = int(m) & 127, int(m) >> 7
+            return ((9 - s // 9) * 9 + s % 9) | (((9 - d // 9) * 9 + d % 9) << 7)
+        assert sorted(mirror(m) for m in mv) == sorted(int(m) for m in fm)
+        checked += 1
+        if len(mv) == 0:
+            b, side = O.from_state(O.START), 0
+            continue
+        m = mv[rng.randint(len(mv))]
+        nb, cap = O.apply_move(b, m)
+        nfb, fcap = O.apply_move(fb, mirror(m))
+        assert np.array_equal(O.flip_board(nb), nfb) and (cap == 0) == (fcap == 0)
+        b, side = nb, side ^ 1
+        if cap in (1, 8):
+            b, side = O.from_state(O.START), 0
+    assert checked == 3000
