@@ -447,3 +447,49 @@ def test_leaf_parallel_kernel_equals_its_serial_specification(K, O, R):
             t = O.Tree(c["board"])
             assert t.search_multi(c["side"], c["rr"], c["playouts"], K, net) == 0
             assert np.array_equal(t.signature(), e.tree_signature(g)), (net, K, g)
+
+
+def test_rules_flip_symmetry_on_a_quarter_million_positions(R):
+    """Size-independent property of the CUDA rules at scale, no oracle involved: for every position reached by 4096 random
+    games, moves(flip(board), other side) is the rank mirror of moves(board, side) as a set, encode(board, 'b') equals
+    encode(flip(board), 'w'), and a move and its mirror capture alike."""
+    from cchess_zero_b200.selfplay import _flip_board
+    G, plies = 4096, 60
+    rng = np.random.RandomState(2)
+    boards = np.tile(R.state_to_board(R.START_STATE), (G, 1))
+    sides = np.zeros(G, dtype=np.uint8)
+    n_checked = 0
+
+    def mirror(mv):
+        s, d = mv & 127, mv >> 7
+        return (((9 - s // 9) * 9 + s % 9) | (((9 - d // 9) * 9 + d % 9) << 7)).astype(np.uint16)
+
+    def flip_all(b):
+        f = b.reshape(-1, 10, 9)[:, ::-1, :].copy()
+        red, blk = (f >= 1) & (f <= 7), f >= 8
+        f[red] += 7; f[blk] -= 7
+        return f.reshape(-1, 90)
+
+    for ply in range(plies):
+        mv, cnt = R.legal_moves_batch(boards, sides)
+        fb = flip_all(boards)
+        assert np.array_equal(fb[:3], np.stack([_flip_board(b) for b in boards[:3]]))
+        fmv, fcnt = R.legal_moves_batch(fb, sides ^ 1)
+        assert np.array_equal(cnt, fcnt)
+        valid = np.arange(128)[None, :] < cnt[:, None]
+        a = np.where(valid, mirror(mv), 0xFFFF); b = np.where(valid, fmv, 0xFFFF)
+        assert np.array_equal(np.sort(a, axis=1), np.sort(b, axis=1))
+        if ply % 10 == 0:
+            black = sides == 1
+            if black.any():
+                assert np.array_equal(R.encode_batch(boards[black], sides[black]), R.encode_batch(fb[black], sides[black] ^ 1))
+        n_checked += G
+        pick = (rng.rand(G) * np.maximum(cnt, 1)).astype(np.int64)
+        chosen = mv[np.arange(G), pick]
+        nb, cap = R.apply_moves_batch(boards, chosen)
+        nfb, fcap = R.apply_moves_batch(fb, mirror(chosen))
+        assert np.array_equal(flip_all(nb), nfb) and np.array_equal(cap == 0, fcap == 0)
+        dead = (cap == 1) | (cap == 8) | (cnt == 0)
+        boards, sides = nb, sides ^ 1
+        boards[dead] = R.state_to_board(R.START_STATE); sides[dead] = 0
+    assert n_checked == G * plies
