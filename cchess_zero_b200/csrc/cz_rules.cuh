@@ -12,21 +12,24 @@
 #include <stdint.h>
 
 #define CZ_FULL 0xffffffffu
+// pure per-lane functions are also compiled for the host so that the CPU test tier can run THIS source against the golden vectors
+// (tests/host_rules_harness.cu); the qualifier does not change the device code
+#define CZ_HD __host__ __device__ __forceinline__
 
 namespace cz {
 
 // piece kinds after folding colour: 1..7 = K A R B N P C  (pieces_order, main.py:208)
 enum { K_ = 1, A_ = 2, R_ = 3, B_ = 4, N_ = 5, P_ = 6, C_ = 7 };
 
-__device__ __forceinline__ bool piece_red(int p) { return p >= 1 && p <= 7; }
-__device__ __forceinline__ int piece_kind(int p) { return p > 7 ? p - 7 : p; }
+CZ_HD bool piece_red(int p) { return p >= 1 && p <= 7; }
+CZ_HD int piece_kind(int p) { return p > 7 ? p - 7 : p; }
 
 // Generates the moves of the piece on `sq` for `side` (0 red / 1 black) in reference order into
 // out[0..17] (a piece has at most 17 moves) and returns the count.
 // Kings are handled here too (palace steps); the flying-general capture is appended by the caller.
 #define CZ_OK_TARGET(q) ((q) == 0 || (piece_red(q) != red))            /* validate_move, main.py:727-740 */
 #define CZ_EMIT(dst) do { out[n] = (uint16_t)(sq | ((dst) << 7)); n++; } while (0)
-__device__ __forceinline__ int gen_piece(const uint8_t *b, int sq, int side, uint16_t *out) {
+CZ_HD int gen_piece(const uint8_t *b, int sq, int side, uint16_t *out) {
     const int p = b[sq];
     if (p == 0) return 0;
     const bool red = piece_red(p);
@@ -188,19 +191,19 @@ __device__ __noinline__ int warp_legal_moves(const uint8_t *b, int side, uint16_
 }
 
 // swap colour of a piece code (try_flip's swapcase, main.py:566-572)
-__device__ __forceinline__ int swap_colour(int p) { return p == 0 ? 0 : (p <= 7 ? p + 7 : p - 7); }
+CZ_HD int swap_colour(int p) { return p == 0 ? 0 : (p <= 7 ? p + 7 : p - 7); }
 
-template <typename T> __device__ __forceinline__ T enc_one();
-template <> __device__ __forceinline__ float enc_one<float>() { return 1.0f; }
-template <> __device__ __forceinline__ __nv_bfloat16 enc_one<__nv_bfloat16>() { return __float2bfloat16(1.0f); }
-template <> __device__ __forceinline__ __half enc_one<__half>() { return __float2half(1.0f); }
+template <typename T> CZ_HD T enc_one();
+template <> CZ_HD float enc_one<float>() { return 1.0f; }
+template <> CZ_HD __nv_bfloat16 enc_one<__nv_bfloat16>() { return __float2bfloat16(1.0f); }
+template <> CZ_HD __half enc_one<__half>() { return __float2half(1.0f); }
 
 // Warp-cooperative generate_inputs (main.py:531-557): flip for black (rows reversed, colours
 // swapped), then T[rank][file][plane] for rank < 9, file < 10 reads board cell rank*9+file --
 // the reference's indexing, which drops squares 82..89 and reads 8 cells twice.
 // out: 1260 elements of T in global memory (row of the NN batch), 16-byte aligned.
 template <typename T>
-__device__ void warp_encode(const uint8_t *b, int side, T *out, int lane) {
+__host__ __device__ void warp_encode(const uint8_t *b, int side, T *out, int lane) {
     constexpr int VEC = 16 / sizeof(T);           // elements per 16-byte store
     constexpr int NV = 1260 / VEC;                // 315 (f32) or 157.5 -> handled below
     static_assert(1260 % (VEC / 2) == 0, "row must be a multiple of 8 bytes");

@@ -308,3 +308,32 @@ def test_selfplay_host_loop_on_cpu_stand_in_engine_matches_reference_vectors():
     for (slot, rec), g in zip(out, games):
         assert rec.states == g["states"] and [float(z) for z in rec.z] == g["z"]
         assert hashlib.sha256(rec.dense_pi().tobytes()).hexdigest()[:16] == g["sha_pi"]
+
+
+def test_device_rule_source_compiled_for_host_matches_reference_vectors(tmp_path):
+    """The product's own per-lane rule code (csrc/cz_rules.cuh: gen_piece, warp_encode) compiled for the HOST by nvcc and run
+    against the golden vectors of the reference -- a CPU-tier check of the very source the kernels are built from."""
+    import ctypes as C
+    import shutil
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from conftest import load_golden
+    from oracle import oracle as O
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    so = str(tmp_path / "libhostrules.so")
+    r = subprocess.run([nvcc, "-std=c++17", "-O1", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC", "-shared", "-o", so,
+                        os.path.join(ROOT, "tests", "host_rules_harness.cu")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    L = C.CDLL(so)
+    recs = load_golden("movegen.json.gz")["records"]
+    out = np.zeros(160, dtype=np.uint16)
+    enc = np.zeros((9, 10, 14), dtype=np.float32)
+    for r_ in recs[::3]:
+        b = O.from_state(r_["state"])
+        side = 0 if r_["player"] == "w" else 1
+        n = L.hr_legal_moves(b.ctypes.data_as(C.c_void_p), side, out.ctypes.data_as(C.c_void_p))
+        assert " ".join(O.move_str(m) for m in out[:n]) == r_["moves"], r_["state"]
+        L.hr_encode_f32(b.ctypes.data_as(C.c_void_p), side, enc.ctypes.data_as(C.c_void_p))
+        assert [int(i) for i in np.nonzero(enc.reshape(-1))[0]] == r_["enc"]
