@@ -140,6 +140,35 @@ def gen_tree(ref):
     return dict(cases=cases)
 
 
+def gen_tree_extra(ref, n_cases=72, seed=77):
+    """More search trees from the reference: positions sampled along seeded random games (opening to bare endgames), both
+    sides to move, restrict_round near and far from the 60-ply rule.  Pins the oracle only (CPU test)."""
+    rng = random.Random(seed)
+    nets = ("hash_pos", "hash_signed", "mod17")
+    cases = []
+    while len(cases) < n_cases:
+        state, player = START, "w"
+        plies = rng.randint(0, 220)
+        for _ in range(plies):
+            mv = ref.GameBoard.get_legal_moves(state, player)
+            state = ref.GameBoard.sim_do_action(rng.choice(mv), state)
+            player = "b" if player == "w" else "w"
+            if "K" not in state or "k" not in state:
+                break
+        if "K" not in state or "k" not in state:
+            continue
+        net = nets[len(cases) % 3]
+        rr = rng.choice([0, 1, 10, 40, 55, 57, 58, 59])
+        playouts = rng.choice([60, 120, 200, 300])
+        t = H.make_mcts(H.FAKE_NETS[net], 1, state)
+        with np.errstate(all="ignore"):
+            t.main(state, player, rr, playouts)
+        sig = np.asarray(H.tree_signature(t.root, ref), dtype=np.int64).reshape(-1, 6)
+        cases.append(dict(net=net, state=state, player=player, rr=rr, playouts=playouts, n_nodes=int(sig.shape[0]), sha_sig=sha(sig.tobytes())))
+        print("tree_extra", len(cases), net, player, rr, playouts, sig.shape[0], flush=True)
+    return dict(cases=cases)
+
+
 def gen_selfplay(ref):
     games = []
     for net, playouts, seed in [("hash_pos", 30, 7), ("hash_signed", 20, 3), ("hash_pos", 60, 11),
@@ -208,7 +237,7 @@ def gen_play(ref):
 def main():
     ref = H.load_reference()
     os.makedirs(OUT, exist_ok=True)
-    for name, fn in (("labels", gen_labels), ("movegen", gen_movegen), ("tree", gen_tree), ("selfplay", gen_selfplay), ("play", gen_play)):
+    for name, fn in (("labels", gen_labels), ("movegen", gen_movegen), ("tree", gen_tree), ("selfplay", gen_selfplay), ("play", gen_play), ("tree_extra", gen_tree_extra)):
         if len(sys.argv) > 1 and name not in sys.argv[1:]:
             continue
         d = fn(ref)

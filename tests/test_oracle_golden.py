@@ -144,3 +144,14 @@ def test_rules_are_symmetric_under_the_colour_flip():
         if cap in (1, 8):
             b, side = O.from_state(O.START), 0
     assert checked == 3000
+
+
+def test_tree_extra_cases_against_reference():
+    """72 more search trees of the reference (random-play positions from opening to bare endgames, both colours, rr up to 59)."""
+    g = load_golden("tree_extra.json")
+    assert len(g["cases"]) >= 60
+    for c in g["cases"]:
+        t = O.Tree(O.from_state(c["state"]))
+        t.search(0 if c["player"] == "w" else 1, c["rr"], c["playouts"], c["net"])
+        sig = t.signature()
+        assert sig.shape[0] == c["n_nodes"] and sha(sig.tobytes()) == c["sha_sig"], (c["state"], c["player"], c["rr"])
