@@ -190,11 +190,12 @@ class _MultiEngine:
 
 
 class SelfPlay:
-    """n_games concurrent self-play games on one engine.
+    """n_games concurrent self-play games on one engine, advanced in lock-step plies by step().
 
-    forward_dev(nn_in) -> None must write logits f32 [B,2086] / value f32 [B] into the tensors handed to
-    it at construction time via `bind(nn_in, logits, value)`; or pass a callable returning (logits, value)
-    device tensors (they are copied into the static buffers)."""
+    Evaluator: pass `plan` (an InferencePlan / NativePlan: it owns the input buffer layout and writes logits / value in
+    place), or `forward` = a callable (nn_in) -> (logits [B,2086] f32, value [B] f32) device tensors, which are copied
+    into the static buffers the engine reads.  Finished games accumulate in `finished` (slot, GameRecord); long runs
+    should drain them with pop_finished()."""
 
     def __init__(self, n_games, forward, playouts, seeds=None, exploration=True, temperature=1,
                  nn_dtype=torch.float32, arena_words=0, auto_reset=True, device=None, keep_records=True, plan=None,
@@ -451,6 +452,11 @@ class SelfPlay:
             else:
                 self.live[[g for g, _ in done_now]] = False
         return dict(choice=choice, win_rate=win_rate, finished=done_now, status=st)
+
+    def pop_finished(self):
+        """Hand over (and forget) the games finished so far: keeps memory flat in long self-play runs."""
+        out, self.finished = self.finished, []
+        return out
 
     def play_games(self, max_plies=100000):
         """Every slot plays ONE game to the end (auto_reset must be False)."""

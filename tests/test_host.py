@@ -308,6 +308,7 @@ def test_selfplay_host_loop_on_cpu_stand_in_engine_matches_reference_vectors():
     for (slot, rec), g in zip(out, games):
         assert rec.states == g["states"] and [float(z) for z in rec.z] == g["z"]
         assert hashlib.sha256(rec.dense_pi().tobytes()).hexdigest()[:16] == g["sha_pi"]
+    assert len(sp.pop_finished()) == len(games) and sp.finished == [] and sp.pop_finished() == []
 
 
 def test_device_rule_source_compiled_for_host_matches_reference_vectors(tmp_path):
