@@ -338,3 +338,27 @@ def test_device_rule_source_compiled_for_host_matches_reference_vectors(tmp_path
         assert " ".join(O.move_str(m) for m in out[:n]) == r_["moves"], r_["state"]
         L.hr_encode_f32(b.ctypes.data_as(C.c_void_p), side, enc.ctypes.data_as(C.c_void_p))
         assert [int(i) for i in np.nonzero(enc.reshape(-1))[0]] == r_["enc"]
+
+
+def test_selfplay_auto_reset_path_on_cpu_stand_in_engine():
+    """The bench's mode: finished games are emitted with z and their slots restart from the start position; every finished
+    game must equal what the oracle plays with the same slot RNG stream continued across games."""
+    from cchess_zero_b200.selfplay import SelfPlay
+    B, P, net = 6, 8, "hash_pos"
+    eng = _OracleEngine(B, net)
+    sp = SelfPlay(B, lambda x: None, P, seeds=[40 + i for i in range(B)], auto_reset=True, engine=eng)
+    with np.errstate(all="ignore"):
+        for _ in range(260):
+            sp.step()
+    done = sp.pop_finished()
+    assert len(done) >= B                      # every slot finished at least one game (60-ply rule bounds game length)
+    first = {}
+    for slot, rec in done:
+        first.setdefault(slot, rec)
+        assert rec.z is not None and len(rec.z) == len(rec) and rec.winner in ("w", "b", "t")
+        assert rec.states[0] == "RNBAKABNR/9/1C5C1/P1P1P1P1P/9/9/p1p1p1p1p/1c5c1/9/rnbakabnr"
+    from oracle import oracle as O
+    for slot, rec in first.items():            # first game of each slot == the oracle's game with that seed
+        with np.errstate(all="ignore"):
+            r = O.selfplay_game(net, P, np.random.RandomState(40 + slot))
+        assert rec.states == r["states"] and np.array_equal(rec.z, r["z"]) and np.array_equal(rec.dense_pi(), r["pis"])
