@@ -362,3 +362,24 @@ def test_selfplay_auto_reset_path_on_cpu_stand_in_engine():
         with np.errstate(all="ignore"):
             r = O.selfplay_game(net, P, np.random.RandomState(40 + slot))
         assert rec.states == r["states"] and np.array_equal(rec.z, r["z"]) and np.array_equal(rec.dense_pi(), r["pis"])
+
+
+def test_torch_stand_in_nets_match_oracle_on_cpu():
+    """cchess_zero_b200/fakenet.py (torch integer ops, used on the device in the GPU tests) evaluated on CPU tensors against
+    the oracle's C restatement and the numpy original."""
+    from cchess_zero_b200.fakenet import FakeNet
+    from oracle import oracle as O
+    from oracle.fakenets_np import FAKE_NETS
+    rng = np.random.RandomState(1)
+    xs, b, side = [], O.from_state(O.START), 0
+    for _ in range(40):
+        xs.append(O.encode(b, side))
+        mv = O.legal_moves(b, side)
+        b, cap = O.apply_move(b, mv[rng.randint(len(mv))]); side ^= 1
+    x = np.stack(xs)
+    for kind in ("hash_signed", "hash_pos", "mod17"):
+        lo, v = FakeNet(kind, device="cpu")(torch.from_numpy(x))
+        olo, ov = O.fake_forward(kind, x)
+        nlo, nv = FAKE_NETS[kind](x)
+        assert np.array_equal(lo.numpy(), olo) and np.array_equal(v.numpy(), ov.reshape(-1))
+        assert np.array_equal(nlo, olo) and np.array_equal(nv, ov)
