@@ -383,3 +383,31 @@ def test_torch_stand_in_nets_match_oracle_on_cpu():
         nlo, nv = FAKE_NETS[kind](x)
         assert np.array_equal(lo.numpy(), olo) and np.array_equal(v.numpy(), ov.reshape(-1))
         assert np.array_equal(nlo, olo) and np.array_equal(nv, ov)
+
+
+def test_pytorch_network_matches_independent_numpy_restatement_of_the_tf_graph():
+    """cchess_zero_b200.net.PolicyValueNet (CPU, fp64) against oracle/net_numpy.py, a separately written NHWC / TF-layout
+    evaluation of policy_value_network.py:45-74, 151-162 (SAME padding, BN without gamma/beta, (h,w,c) flatten, logits, tanh)."""
+    from cchess_zero_b200.net import PolicyValueNet
+    from oracle import net_numpy as NN
+    from oracle import oracle as O
+    torch.manual_seed(2)
+    net = PolicyValueNet(3).double().eval()
+    with torch.no_grad():   # non-trivial biases and moving statistics
+        for m in net.modules():
+            if isinstance(m, (torch.nn.Conv2d, torch.nn.Linear)):
+                m.bias.uniform_(-0.2, 0.2)
+            if hasattr(m, "running_var"):
+                m.running_var.uniform_(0.5, 2.0); m.running_mean.uniform_(-0.3, 0.3)
+    rng = np.random.RandomState(0)
+    xs, b, side = [], O.from_state(O.START), 0
+    for _ in range(12):
+        xs.append(O.encode(b, side))
+        mv = O.legal_moves(b, side)
+        b, _ = O.apply_move(b, mv[rng.randint(len(mv))]); side ^= 1
+    x = np.stack(xs).astype(np.float64)
+    with torch.no_grad():
+        tl, tv = net(torch.from_numpy(x))
+    nl, nv = NN.forward(x, NN.tf_params_from_torch(net), 3)
+    assert nl.shape == (12, 2086) and nv.shape == (12, 1)
+    assert np.abs(tl.numpy() - nl).max() < 1e-10 and np.abs(tv.numpy() - nv).max() < 1e-10
