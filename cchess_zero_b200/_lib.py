@@ -61,11 +61,15 @@ def lib():
     if _lib is None:
         from . import build as _build
 
-        try:
-            _build.build()
-        except Exception as e:  # stale/missing and not buildable
-            if not os.path.exists(LIB_PATH):
-                raise EngineError("libcchess_b200.so is missing and could not be built: %s" % e)
+        # Under torchrun (RANK set) several ranks import at once: never race nvcc there -- use the library that
+        # __graft_entry__.build() / `python -m cchess_zero_b200.build` produced.  CCHESS_NO_REBUILD=1 forces the same.
+        distributed = "RANK" in os.environ or os.environ.get("CCHESS_NO_REBUILD", "0") == "1"
+        if not (distributed and os.path.exists(LIB_PATH)):
+            try:
+                _build.build()
+            except Exception as e:  # stale/missing and not buildable
+                if not os.path.exists(LIB_PATH):
+                    raise EngineError("libcchess_b200.so is missing and could not be built: %s" % e)
         L = C.CDLL(LIB_PATH)
         _sig(L)
         _lib = L

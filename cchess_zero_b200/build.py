@@ -22,12 +22,16 @@ def needs_build():
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
-    cmd = [NVCC] + FLAGS + ["-o", LIB] + SRC
+    tmp = "%s.tmp.%d" % (LIB, os.getpid())          # build beside the target, then rename: never a half-written library
+    cmd = [NVCC] + FLAGS + ["-o", tmp] + SRC
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or r.returncode:
         sys.stderr.write(r.stdout + r.stderr)
     if r.returncode:
+        if os.path.exists(tmp):
+            os.remove(tmp)
         raise RuntimeError("nvcc failed: " + " ".join(cmd))
+    os.replace(tmp, LIB)
     return LIB
 
 
