@@ -1,20 +1,32 @@
 #!/usr/bin/env python
-"""bench.py -- MCTS node-expansions/sec of batched self-play (BASELINE.json metric).
+"""bench.py -- MCTS node-expansions/sec and self-play games/hour of batched self-play (BASELINE.json metric).
 
   python bench.py --gpus N --steps K --warmup W          our arm (one rank per GPU under torchrun)
-  python bench.py --impl reference ...                    CPU arm: the oracle port of the reference's path
+  python bench.py --impl reference ...                    CPU arm: the UNMODIFIED reference's self-play on the host cores
 
 A "step" is one ply of EVERY concurrent game: a full MCTS_tree.main of `--playouts` playouts per game
 (select / encode / network / expand / backup waves), then get_action's host-side move choice and the
-re-root.  Workload = BASELINE.json configs[1]: 1024 concurrent games x 1200 playouts, res_block_nums=7,
+re-root.  Main workload = BASELINE.json configs[1]: 1024 concurrent games x 1200 playouts, res_block_nums=7,
 per GPU (weak scaling).  Expansions are counted by the engine (calls of expand), not inferred.
 
 value : expansions / device time of the search waves (CUDA events, state resident in HBM)
-e2e   : expansions / time of the whole SelfPlay.step() loop through the public API, including the
-        per-ply device->host read of root statistics / status and host->device write of the chosen
-        moves, host move sampling and tuple recording.
+e2e   : expansions / time of the whole SelfPlay.step() loop through the public API, including the per-ply
+        device->host read of root statistics / status, host->device write of the chosen moves, host move
+        sampling, tuple recording and (N > 1) the NCCL gather of the finished games' tuples.
+
+Further bounded legs, reported under `extra` of the same JSON line (each can be switched off with --legs):
+  precision : the same workload in tf32 and fp32 (a few plies each)         -> extra.by_precision      (N = 1)
+  config3   : BASELINE configs[2] per-rank shape, 512 games x 1600 playouts -> extra.config3
+  config4   : BASELINE configs[3], 19 residual blocks                       -> extra.config4           (N = 1)
+  config5   : BASELINE configs[4], play-mode move latency p50/p95 through get_hint + select_move (ChessGame.py:153-181)
+                                                                             -> extra.config5           (N = 1)
+  soak      : every game slot plays on for >= 3 mean game lengths; games/hour from plies/s and the measured
+              game-length distribution (no short-game selection bias)       -> extra.games_per_hour
+  cpu       : the reference's own CPU self-play beside it                    -> cpu_baseline             (N = 1)
 """
 import argparse
+import contextlib
+import io
 import json
 import os
 import subprocess
@@ -30,6 +42,7 @@ import torch  # noqa: E402
 
 METRIC = "mcts_node_expansions_per_sec"
 FLOPS_PER_EVAL = {7: 375.4e6, 19: 1012.4e6}
+ALL_LEGS = "precision,config3,config4,config5,soak,cpu"
 
 
 def parse():
@@ -47,9 +60,13 @@ def parse():
     ap.add_argument("--overlap-movegen", action="store_true", help="leaf move generation on a side stream under the network (measured: no gain)")
     ap.add_argument("--lanes", type=int, default=1, choices=[1, 2], help="2 = pipeline two half-batches (tree kernel under the other half's network)")
     ap.add_argument("--library-ends", action="store_true", help="use cuDNN/cuBLAS for the first conv and the heads instead of csrc/cz_net.cu")
+    ap.add_argument("--legs", default=os.environ.get("CCHESS_BENCH_LEGS", ALL_LEGS), help="comma list of extra legs (%s) or 'none'" % ALL_LEGS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--cpu-seconds", type=float, default=20.0)
+    ap.add_argument("--soak-plies", type=int, default=150)
     ap.add_argument("--profile-waves", type=int, default=200, help="waves timed individually for the roofline line")
+    ap.add_argument("--arena-words", type=int, default=0)
+    ap.add_argument("--kwave-capture", action="store_true", help="ncu helper: play --warmup plies (deep trees), then run --profile-waves eager waves and exit")
     return ap.parse_args()
 
 
@@ -114,22 +131,18 @@ def algorithmic_bytes(c0, c1, enc_bytes):
 
 
 # ---------------------------------------------------------------------------------------------
+# CPU arms.  Both are test/baseline infrastructure under oracle/ (the only place bench.py may execute it).
+#   reference : oracle/ref_cpu_arm.py -- the UNMODIFIED reference's cchess_main.selfplay(), search_threads=16, one process per core
+#   port      : the C oracle port driving lock-step trees + torch CPU net (kept as a second, labelled figure)
+# ---------------------------------------------------------------------------------------------
 def host_cores():
-    """Cores this process may really use: affinity mask, capped by the cgroup CPU quota when there is one."""
-    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    try:
-        q = open("/sys/fs/cgroup/cpu.max").read().split()
-        if q[0] != "max":
-            n = max(1, min(n, int(float(q[0]) / float(q[1]) + 0.5)))
-    except Exception:
-        pass
-    return n
+    from oracle import ref_cpu_arm
+    return ref_cpu_arm.usable_cores()
 
 
-class CpuArm:
-    """The reference's path on the host cores: the C oracle port (oracle/cchess_oracle.c) drives n_games trees in
-    lock-step (one leaf per game per wave, search_threads=1 semantics) and the same seed-0 network is evaluated by
-    PyTorch on the CPU.  The thread count is calibrated (a few candidates, one wave each) and the best is kept."""
+class PortArm:
+    """The oracle C port (oracle/cchess_oracle.c) drives n_games trees in lock-step (one leaf per game per wave,
+    search_threads=1 semantics) and the same seed-0 network is evaluated by PyTorch on the CPU, all host threads."""
 
     def __init__(self, n_games, playouts, res_blocks, threads=None):
         import ctypes as C
@@ -146,12 +159,8 @@ class CpuArm:
         self.nn_in = np.zeros((n_games, 9, 10, 14), dtype=np.float32)
         self.pending = np.zeros(n_games, dtype=np.uint8)
         self.cores = host_cores()
-        self.wave_s = None
-        if threads is None:
-            self.calibrate()
-        else:
-            self.threads = threads
-            torch.set_num_threads(threads)
+        self.threads = threads or self.cores
+        torch.set_num_threads(self.threads)
 
     def _p(self, a):
         return a.ctypes.data_as(self.C.c_void_p)
@@ -165,157 +174,185 @@ class CpuArm:
         v = np.ascontiguousarray(v.numpy().reshape(-1), dtype=np.float32)
         L.co_batch_finish(self.arr, self.B, p(lo), p(v), p(self.pending), self.threads)
 
-    def calibrate(self):
-        cands = sorted({c for c in (self.cores, self.cores // 2, 64, 32, 16, 8) if 1 <= c <= self.cores}, reverse=True)
-        best, best_t = cands[0], None
-        for c in cands:
-            self.threads = c
-            torch.set_num_threads(c)
-            t0 = time.perf_counter(); self.wave(); dt = time.perf_counter() - t0
-            if best_t is None or dt < best_t:
-                best, best_t = c, dt
-        self.threads, self.wave_s = best, best_t
-        torch.set_num_threads(best)
-
     def expansions(self):
         return sum(t.stats()["n_expand"] for t in self.trees)
 
-    def run(self, seconds=None, waves=None):
+    def run(self, seconds):
+        self.wave()                                            # warm-up wave (root expansions, allocator)
         e0, t0, n = self.expansions(), time.perf_counter(), 0
-        while True:
+        while time.perf_counter() - t0 < seconds or n < 2:
             self.wave(); n += 1
-            if (waves is not None and n >= waves) or (waves is None and time.perf_counter() - t0 >= seconds):
-                break
         dt = time.perf_counter() - t0
-        return dict(value=(self.expansions() - e0) / dt, seconds=dt, waves=n)
+        return dict(value=(self.expansions() - e0) / dt, seconds=dt, waves=n, games=self.B, threads=self.threads)
 
 
-def sized_cpu_arm(max_games, playouts, res_blocks, wave_budget_s):
-    """Probe with 64 games (also calibrates the thread count), then size the sample so that one lock-step wave of the
-    sample costs about wave_budget_s on this host.  Keeps every CPU leg bounded whatever the box's core count is."""
-    probe = CpuArm(min(64, max_games), playouts, res_blocks)
-    per_game = max(probe.wave_s, 1e-4) / probe.B
-    n = int(min(max_games, max(32, wave_budget_s / per_game)))
-    n = 1 << (n.bit_length() - 1)                                   # power of two <= n
-    if n <= probe.B:
-        return probe
-    return CpuArm(min(n, max_games), playouts, res_blocks, threads=probe.threads)
+def port_figure(playouts, res_blocks, seconds):
+    arm = PortArm(256, playouts, res_blocks)
+    r = arm.run(seconds)
+    return dict(value=r["value"], unit="expansions/s", kind="port", cores=arm.threads,
+                sample="%d games x %d lock-step waves (%.1f s) from the start position, oracle C port (search_threads=1 schedule) + torch CPU fp32 net, %d threads"
+                       % (r["games"], r["waves"], r["seconds"], arm.threads))
+
+
+def reference_cpu(steps, warmup, playouts, res_blocks, budget_s, tree_only=True):
+    """cpu_baseline dict measured with the unmodified reference; falls back to the port (labelled) when the staged reference is absent."""
+    from oracle import ref_cpu_arm
+    if ref_cpu_arm.available() is None:
+        f = port_figure(playouts, res_blocks, min(budget_s, 15.0))
+        f["note"] = "staged reference (oracle/_ref/reference) not found on this box: oracle port timed instead"
+        return f, None
+    r = ref_cpu_arm.run(steps, warmup, playouts, res_blocks, 16, budget_s)
+    out = dict(value=r["value"], unit="expansions/s", cores=r["cores"], kind="reference", sample=r["sample"], search_threads=16,
+               mean_nn_batch=r["mean_nn_batch"], usable_cores=r["usable_cores"], quota=r["quota"], timed_s=r["timed_s"])
+    if tree_only:
+        t = ref_cpu_arm.run(2, 1, playouts, res_blocks, 16, 8.0, net="zero")
+        out["tree_only_value"] = t["value"]                     # zero-cost evaluator: shows the network substitution hides nothing
+    return out, r
 
 
 def run_reference(a, rank, world):
-    """--impl reference: rank 0 times the CPU arm (oracle port; the Python reference cannot travel), other ranks exit 0.
-    Each step is a bounded sample of the workload: `waves_per_step` lock-step waves of a sample of the games, the sample
-    sized so that the whole --steps/--warmup run takes about two minutes."""
+    """--impl reference: rank 0 times the reference's own CPU self-play on the host cores; other ranks exit 0."""
     if rank != 0:
         return
-    waves_per_step = max(1, int(os.environ.get("CCHESS_REF_WAVES_PER_STEP", "2")))
-    total_budget = float(os.environ.get("CCHESS_REF_SECONDS", "120"))
-    wave_budget = total_budget / max(1, (a.steps + a.warmup) * waves_per_step)
-    arm = sized_cpu_arm(a.games, a.playouts, a.res_blocks, wave_budget)
-    if a.warmup:
-        arm.run(waves=a.warmup * waves_per_step)
-    r = arm.run(waves=a.steps * waves_per_step)
-    v = r["value"]
-    sample = "%d of the %d games x %d lock-step waves per step (first waves of the %d-playout search from the start position), oracle C port + torch CPU fp32 net, %d threads (calibrated) of %d usable cores" % (
-        arm.B, a.games, waves_per_step, a.playouts, arm.threads, arm.cores)
+    budget = float(os.environ.get("CCHESS_REF_SECONDS", "150"))
+    cpu, r = reference_cpu(a.steps, a.warmup, a.playouts, a.res_blocks, budget, tree_only=True)
+    v = cpu["value"]
+    ms = r["ms_per_step"] if r is not None else None
+    try:
+        cpu["port_value"] = port_figure(a.playouts, a.res_blocks, 8.0)
+    except Exception as e:  # the labelled second figure must never break the arm
+        cpu["port_value"] = dict(error=str(e))
     line = dict(metric=METRIC, value=v, unit="expansions/s", n_gpus=a.gpus, steps=a.steps, warmup=a.warmup,
-                ms_per_step=r["seconds"] / a.steps * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
-                data="synthetic", impl="reference",
-                config=dict(workload="%d concurrent self-play games x %d playouts, res_block_nums=%d" % (a.games, a.playouts, a.res_blocks),
-                            games_per_gpu=a.games, playouts=a.playouts, res_block_nums=a.res_blocks),
-                cpu_baseline=dict(value=v, unit="expansions/s", cores=arm.threads, kind="port", sample=sample),
+                ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                data="synthetic (seed-0 xavier-initialised network, games from the start position)", impl="reference",
+                config=dict(workload="%d concurrent self-play games x %d playouts per move, res_block_nums=%d, per GPU" % (a.games, a.playouts, a.res_blocks),
+                            games_per_gpu=a.games, playouts=a.playouts, res_block_nums=a.res_blocks, search_threads=16,
+                            note="the reference plays one game per process; a step is a bounded sample (a fixed quota of expansions per process) of that workload"),
+                cpu_baseline=cpu,
                 e2e=dict(value=v, unit="expansions/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line), flush=True)
 
 
 # ---------------------------------------------------------------------------------------------
-def run_ours(a, rank, world, local_rank):
-    from cchess_zero_b200.net import policy_value_network
-    from cchess_zero_b200.selfplay import SelfPlay
-    import torch.distributed as dist
+class Runner:
+    """One SelfPlay instance + timing helpers; every leg of our arm goes through it."""
 
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    B = a.games
-    pv = policy_value_network(a.res_blocks, precision=a.precision, device=local_rank, seed=0)
-    native = a.precision == "fp16" and not a.library_ends
-    factory = (lambda n: pv.native_plan(n, a.first_conv)) if native else (lambda n: pv.plan())
-    plan = factory(B // a.lanes)
-    sp = SelfPlay(B, None, a.playouts, seeds=[rank * B + g for g in range(B)], device=local_rank,
-                  auto_reset=True, keep_records=True, plan=plan if a.lanes == 1 else None, plan_factory=factory, lanes=a.lanes,
-                  overlap_movegen=a.overlap_movegen)
-    if not a.no_graph:
-        sp.capture_graph()
-    e = sp.engine
+    def __init__(self, a, rank, world, local_rank, games, playouts, res_blocks, precision, pv=None, arena_words=None):
+        from cchess_zero_b200.net import policy_value_network
+        from cchess_zero_b200.selfplay import SelfPlay
+        self.a, self.rank, self.world, self.dev = a, rank, world, torch.device("cuda", local_rank)
+        self.B, self.playouts, self.res_blocks, self.precision = games, playouts, res_blocks, precision
+        with contextlib.redirect_stdout(io.StringIO()):
+            self.pv = pv or policy_value_network(res_blocks, precision=precision, device=local_rank, seed=0)
+        native = precision == "fp16" and not a.library_ends
+        pvx = self.pv
+        if pv is not None and pv.precision != precision:        # same weights, another arithmetic
+            from cchess_zero_b200.net import InferencePlan
+            factory = lambda n: InferencePlan(pvx.net, precision)  # noqa: E731
+        else:
+            factory = (lambda n: pvx.native_plan(n, a.first_conv)) if native else (lambda n: pvx.plan())
+        self.plan = factory(games // a.lanes)
+        self.sp = SelfPlay(games, None, playouts, seeds=[rank * games + g for g in range(games)], device=local_rank,
+                           auto_reset=True, keep_records=True, plan=self.plan if a.lanes == 1 else None, plan_factory=factory, lanes=a.lanes,
+                           overlap_movegen=a.overlap_movegen, arena_words=a.arena_words if arena_words is None else arena_words)
+        if not a.no_graph:
+            self.sp.capture_graph()
+        self.search_ms = []
+        self._orig_search = self.sp.search
 
-    def barrier():
+        def timed_search():
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            w = self._orig_search()
+            e1.record()
+            self.search_ms.append((e0, e1))
+            return w
+        self.sp.search = timed_search
+        self.gather = None
         if world > 1:
+            from cchess_zero_b200.distributed import AsyncTupleGather
+            self.gather = AsyncTupleGather(self.dev)
+        self.tuples_gathered = 0
+
+    def barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
             dist.barrier()
         torch.cuda.synchronize()
 
-    search_ms = []
-    orig_search = sp.search
+    def close(self):
+        self.sp.search = self._orig_search
+        eng = self.sp.engine
+        for l in (self.sp.lanes or []):
+            l.engine.close()
+        if hasattr(eng, "close"):
+            eng.close()
+        self.sp = None
+        torch.cuda.empty_cache()
 
-    def timed_search():
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        w = orig_search()
-        e1.record()
-        search_ms.append((e0, e1))
-        return w
-    sp.search = timed_search
+    def plies(self, steps, warmup, clocks=None, on_step=None):
+        """warmup untimed plies, then exactly `steps` timed plies bracketed by barrier + synchronize; max over ranks."""
+        import torch.distributed as dist
+        sp, e = self.sp, self.sp.engine
+        for _ in range(warmup):
+            out = sp.step()
+            if on_step:
+                on_step(out)
+        self.barrier()
+        if clocks is not None:
+            clocks.start()
+        self.search_ms.clear()
+        c0, l0 = e.counters(), e.launches
+        waves0, fin0 = sp.waves, len(sp.finished)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        t0 = time.perf_counter()
+        ev0.record()
+        for _ in range(steps):
+            out = sp.step()
+            if self.gather is not None:                         # previous step's gather completes here, under this step's search
+                tb = self.gather.finish()
+                if tb is not None:
+                    self.tuples_gathered += len(tb)
+                self.gather.start([r for _, r in out["finished"]])
+            if on_step:
+                on_step(out)
+        if self.gather is not None:
+            tb = self.gather.finish()
+            self.tuples_gathered += len(tb) if tb is not None else 0
+        ev1.record()
+        self.barrier()
+        wall = time.perf_counter() - t0
+        clk = clocks.stop() if clocks is not None else None
+        c1 = e.raise_on_error()
+        e2e_ms = ev0.elapsed_time(ev1)
+        dev_ms = sum(x.elapsed_time(y) for x, y in self.search_ms)
+        t = torch.tensor([dev_ms, e2e_ms, wall * 1e3], dtype=torch.float64, device=self.dev)
+        n = torch.tensor([c1["n_expand"] - c0["n_expand"], e.launches - l0, len(sp.finished) - fin0,
+                          sum(len(r) for _, r in sp.finished[fin0:])], dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(n, op=dist.ReduceOp.SUM)
+        dev_ms, e2e_ms, wall_ms = [float(x) for x in t]
+        tot_exp, tot_launch, games_done, tuples_done = [float(x) for x in n]
+        return dict(dev_ms=dev_ms, e2e_ms=e2e_ms, wall_ms=wall_ms, expansions=tot_exp, launches=tot_launch, games_done=games_done,
+                    tuples_done=tuples_done, waves=sp.waves - waves0, steps=steps, c0=c0, c1=c1, clocks=clk,
+                    value=tot_exp / (dev_ms * 1e-3), e2e=tot_exp / (e2e_ms * 1e-3))
 
-    gathered = 0
-    for _ in range(a.warmup):
-        sp.step()
-    barrier()
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
-        clocks.start()
-    search_ms.clear()
-    c0 = e.counters()
-    l0 = e.launches
-    waves0, fin0 = sp.waves, len(sp.finished)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    t0 = time.perf_counter()
-    ev0.record()
-    for _ in range(a.steps):
-        out = sp.step()
-        if world > 1:
-            gathered += gather_tuples(out["finished"], dev, world)
-    ev1.record()
-    barrier()
-    wall = time.perf_counter() - t0
-    clk = clocks.stop() if rank == 0 else None
-    c1 = e.raise_on_error()
-    e2e_ms = ev0.elapsed_time(ev1)
-    dev_ms = sum(x.elapsed_time(y) for x, y in search_ms)
-    n_exp = c1["n_expand"] - c0["n_expand"]
-    launches = e.launches - l0
-    # max time over ranks, sum of expansions
-    t = torch.tensor([dev_ms, e2e_ms, wall * 1e3], dtype=torch.float64, device=dev)
-    n = torch.tensor([n_exp, launches, len(sp.finished) - fin0, sum(len(r) for _, r in sp.finished[fin0:])], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(n, op=dist.ReduceOp.SUM)
-    dev_ms, e2e_ms, wall_ms = [float(x) for x in t]
-    tot_exp, tot_launch, games_done, tuples_done = [float(x) for x in n]
-
-    # ---- roofline of the dominant kernel of OUR code (k_wave), timed live per launch ----
-    roof = None
-    cpu = None
-    if rank == 0:
+    def kwave_roofline(self, n_waves):
+        """k_wave timed per launch with CUDA events on the launching stream, in situ (the trees are those of the plies played so far)."""
+        a, sp, e = self.a, self.sp, self.sp.engine
         hbm, peak_src, _ = measured_peaks()
+        plan = self.plan
         enc_bytes = 96 if plan.dtype == torch.uint8 else 1260 * (4 if plan.dtype == torch.float32 else 2)
-        sp.search = orig_search
-        e.begin_search(a.playouts)
+        sp.search = self._orig_search
+        e.begin_search(self.playouts)
         k0 = e.counters()
         evs = []
         lanes = sp.lanes if sp.lanes is not None else [sp]       # a single-lane SelfPlay has the same attribute names
         side = torch.cuda.Stream()
         cur = torch.cuda.current_stream()
-        for _ in range(a.profile_waves):
+        for _ in range(n_waves):
             for ln in lanes:
                 x, y = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 x.record(); ln.engine.wave(ln.nn_in, ln.logits, ln.value); y.record()
@@ -335,53 +372,187 @@ def run_ours(a, rank, world, local_rank):
         achieved = per_launch / (avg_ms * 1e-3) / 1e9
         traffic, traffic_src = None, None
         tpath = os.path.join(ROOT, "profiles", "kwave_traffic.json")
-        if os.path.exists(tpath):        # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture, scaled to this launch size
+        if os.path.exists(tpath):        # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of an in-situ launch, per launch
             tj = json.load(open(tpath))
-            traffic = (tj["dram_bytes_read_per_launch"] + tj["dram_bytes_write_per_launch"]) * (B // a.lanes) / tj["games_per_launch"]
+            traffic = (tj["dram_bytes_read_per_launch"] + tj["dram_bytes_write_per_launch"]) * (self.B // a.lanes) / tj["games_per_launch"]
             traffic_src = tj["source"]
-        roof = dict(kernel="k_wave (expand+backup+select+encode, one warp per game; %d games per launch)" % (B // a.lanes), bound="hbm", achieved=achieved, peak=hbm, unit="GB/s",
-                    frac=achieved / hbm, traffic=traffic, traffic_source=traffic_src, peak_source=peak_src, avg_launch_ms=avg_ms, p50_launch_ms=float(np.median(kms)), max_launch_ms=float(np.max(kms)),
-                    algorithmic_bytes_per_launch=per_launch,
-                    bytes_per_expansion=ab / max(1, d["n_expand"]), launches_timed=len(kms),
+        return dict(kernel="k_wave (expand+backup+select+encode, one warp per game; %d games per launch)" % (self.B // a.lanes), bound="hbm",
+                    achieved=achieved, peak=hbm, unit="GB/s", frac=achieved / hbm, traffic=traffic, traffic_source=traffic_src, peak_source=peak_src,
+                    avg_launch_ms=avg_ms, p50_launch_ms=float(np.median(kms)), max_launch_ms=float(np.max(kms)),
+                    algorithmic_bytes_per_launch=per_launch, bytes_per_expansion=ab / max(1, d["n_expand"]), launches_timed=len(kms),
                     note="latency-bound pointer-chasing kernel: HBM fraction is reported as required, the binding limits are per-warp dependent loads and the network")
-        if not a.no_cpu_baseline and world == 1:      # reported baseline: rank 0, N=1 only
-            arm = sized_cpu_arm(B, a.playouts, a.res_blocks, wave_budget_s=a.cpu_seconds / 5.0)
-            r = arm.run(seconds=a.cpu_seconds)
-            cpu = dict(value=r["value"], unit="expansions/s", cores=arm.threads, kind="port",
-                       sample="%d of the %d games x %d lock-step waves (%.1f s) from the start position, oracle C port + torch CPU fp32 net, %d threads (calibrated) of %d usable cores" % (
-                           arm.B, B, r["waves"], r["seconds"], arm.threads, arm.cores))
+
+
+def leg_precision(a, rank, world, local_rank, pv):
+    """The main workload in the other arithmetics, same weights: tf32 and fp32 (the reference's own arithmetic is fp32)."""
+    out = {}
+    for prec, steps in (("tf32", 2), ("fp32", 1)):
+        r = Runner(a, rank, world, local_rank, a.games, a.playouts, a.res_blocks, prec, pv=pv, arena_words=1 << 20)
+        m = r.plies(steps, 1)
+        out[prec] = dict(value=m["value"], e2e=m["e2e"], plies_timed=steps, ms_per_step=m["e2e_ms"] / steps,
+                         nn_tflops=m["expansions"] * FLOPS_PER_EVAL.get(a.res_blocks, 0) / (m["dev_ms"] * 1e-3) / 1e12 / world)
+        r.close()
+    return out
+
+
+def leg_config(a, rank, world, local_rank, games, playouts, res_blocks, steps, warmup, label, pv=None):
+    r = Runner(a, rank, world, local_rank, games, playouts, res_blocks, a.precision, pv=pv, arena_words=1 << 20)
+    m = r.plies(steps, warmup)
+    out = dict(workload=label, value=m["value"], e2e=m["e2e"], unit="expansions/s", n_gpus=world, plies_timed=steps, ms_per_step=m["e2e_ms"] / steps,
+               dtype=a.precision, nn_tflops_per_gpu=m["expansions"] * FLOPS_PER_EVAL.get(res_blocks, 0) / (m["dev_ms"] * 1e-3) / 1e12 / world)
+    r.close()
+    return out
+
+
+def leg_config5(a, local_rank, pv):
+    """BASELINE configs[4]: ai_count=2 play mode, mcts vs mcts, 1200 playouts.  One tree; per move the game_mode_2 sequence of
+    ChessGame.change_player (ChessGame.py:153-181): get_hint('mcts') -- which runs a full search when the new root is not expanded
+    (main.py:1281-1284) -- then perform_AI -> select_move('mcts') (another `playouts` playouts on the re-used root)."""
+    from cchess_zero_b200.selfplay import cchess_main
+    out = {}
+    for K, moves in ((1, 12), (8, 24)):
+        with contextlib.redirect_stdout(io.StringIO()):
+            m = cchess_main(playout=a.playouts, in_search_threads=16, network=pv, exploration=False, log_file=False, leaf_parallel=K)
+        np.random.seed(0)
+        lat, hint_s = [], []
+        with contextlib.redirect_stdout(io.StringIO()):
+            for i in range(moves + 2):
+                t0 = time.perf_counter()
+                m.get_hint("mcts", True, lambda: None)
+                t1 = time.perf_counter()
+                m.select_move("mcts")
+                t2 = time.perf_counter()
+                if i >= 2:
+                    lat.append(t2 - t0); hint_s.append(t1 - t0)
+                if m.check_end()[0]:
+                    m.game_borad.reload(); m.mcts.reload()
+        lat = np.array(lat)
+        out["leaf_parallel_%d" % K] = dict(
+            p50_s=float(np.median(lat)), p95_s=float(np.percentile(lat, 95)), mean_s=float(lat.mean()), max_s=float(lat.max()), moves=len(lat),
+            get_hint_share=float(np.sum(hint_s) / np.sum(lat)), playouts_per_s=a.playouts / float(np.median(lat)),
+            semantics="bit-exact search_threads=1 schedule" if K == 1 else "virtual-loss batching of %d leaves per network call (deterministic, not the K=1 visit counts)" % K)
+        m.mcts.engine.close()
+    out["config"] = "1 game, mcts vs mcts, %d playouts, res_block_nums=%d, exploration off, per move get_hint('mcts') + select_move('mcts')" % (a.playouts, a.res_blocks)
+    return out
+
+
+def leg_soak(runner, plies):
+    """games/hour without selection bias.  All slots restart from the start position at ply 0 of the soak; L = length of the
+    FIRST game of every slot, observed exactly up to the window T (longer ones are censored at T), so
+    E[min(L, T)] = sum_{t<T} S(t) is unbiased; with the censored share small it is the mean game length.
+    games/hour = plies/s * 3600 / plies_per_game (renewal rate), plies/s measured end to end over the soak."""
+    sp = runner.sp
+    sp.engine.reset()
+    st = sp.engine.status(boards=True)
+    sp.boards, sp.sides = st["boards"], st["side"]
+    from cchess_zero_b200.selfplay import GameRecord
+    sp.records = [GameRecord() for _ in range(sp.B)]
+    sp.keep_records = False                                    # lengths only: keeps the soak's host memory flat
+    first_len = np.full(sp.B, -1, dtype=np.int64)
+    all_len = []
+
+    def on_step(out):
+        for g, rec in out["finished"]:
+            all_len.append(len(rec))
+            if first_len[g] < 0:
+                first_len[g] = len(rec)
+        sp.pop_finished()
+    gather, runner.gather = runner.gather, None               # the soak measures lengths only: no tuples to ship
+    m = runner.plies(plies, 0, on_step=on_step)
+    runner.gather = gather
+    sp.keep_records = True
+    T = plies
+    obs = first_len[first_len >= 0]
+    censored = int((first_len < 0).sum())
+    lens = np.concatenate([obs, np.full(censored, T)])
+    mean_trunc = float(lens.mean())                              # E[min(L, T)]
+    plies_per_s = runner.world * sp.B * plies / (m["e2e_ms"] * 1e-3)
+    ok = T >= 3 * mean_trunc and censored <= 0.05 * sp.B
+    return dict(games_per_hour=(plies_per_s * 3600.0 / mean_trunc) if ok else None, plies_per_s=plies_per_s, window_plies=T,
+                plies_per_game=mean_trunc, first_games_observed=int(len(obs)), first_games_censored_at_window=censored,
+                length_percentiles={str(p): float(np.percentile(obs, p)) for p in (5, 25, 50, 75, 95)} if len(obs) else None,
+                all_games_finished=len(all_len) * 1.0, value=m["value"], e2e=m["e2e"],
+                valid=bool(ok), rule="reported only when the window is >= 3 x E[min(L,T)] and <= 5 % of the first games are censored",
+                note="seed-0 (untrained) network: games end by king capture or the 60-ply no-capture rule (main.py:1532-1545)")
+
+
+# ---------------------------------------------------------------------------------------------
+def run_ours(a, rank, world, local_rank):
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    legs = set() if a.legs == "none" else set(x for x in a.legs.split(",") if x)
+    if a.no_cpu_baseline:
+        legs.discard("cpu")
+    main = Runner(a, rank, world, local_rank, a.games, a.playouts, a.res_blocks, a.precision)
+    sp, e, plan = main.sp, main.sp.engine, main.plan
+
+    if a.kwave_capture:                                          # helper for ncu: deep trees first, then eager waves
+        for _ in range(a.warmup):
+            sp.step()
+        main.kwave_roofline(a.profile_waves)
+        return
+
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    m = main.plies(a.steps, a.warmup, clocks=clocks)
+    roof = main.kwave_roofline(a.profile_waves) if rank == 0 else None
+    if world > 1:
+        dist.barrier()
+    c1 = m["c1"]
+    extra = dict(expansions=m["expansions"], waves_per_step=m["waves"] / a.steps, games_finished_in_timed_region=m["games_done"],
+                 tuples_all_gathered=main.tuples_gathered, tuple_gather_bytes=main.gather.bytes_gathered if main.gather else 0,
+                 nn_tflops=m["expansions"] * FLOPS_PER_EVAL.get(a.res_blocks, 0) / (m["dev_ms"] * 1e-3) / 1e12 / world,
+                 max_arena_words=c1["max_arena_words"], max_depth=c1["max_depth"],
+                 mean_L=(c1["sum_L"] - m["c0"]["sum_L"]) / max(1, c1["n_playout"] - m["c0"]["n_playout"]),
+                 mean_children=(c1["sum_C"] - m["c0"]["sum_C"]) / max(1, c1["n_expand"] - m["c0"]["n_expand"]))
+    if "soak" in legs:
+        s = leg_soak(main, a.soak_plies)
+        extra["soak"] = s
+        extra["games_per_hour"] = s["games_per_hour"]
+        extra["plies_per_game"] = s["plies_per_game"]
+    else:
+        extra["games_per_hour"] = None                           # never extrapolated from the few games that end inside a short window
+    pv = main.pv
+    main.close()
+    if "config3" in legs:
+        extra["config3"] = leg_config(a, rank, world, local_rank, 512, 1600, 7, 3, 2,
+                                      "BASELINE configs[2] per-rank shape: 512 concurrent games x 1600 playouts per GPU, res_block_nums=7 (4096 games at 8 GPUs)",
+                                      pv=pv if a.res_blocks == 7 else None)
+    if world == 1:
+        if "precision" in legs:
+            extra["by_precision"] = dict(fp16=dict(value=m["value"], e2e=m["e2e"], plies_timed=a.steps, ms_per_step=m["e2e_ms"] / a.steps)) \
+                if a.precision == "fp16" else {}
+            extra["by_precision"].update(leg_precision(a, rank, world, local_rank, pv))
+            pp = os.path.join(ROOT, "profiles", "r02_nn_precision_scaled.json")
+            if os.path.exists(pp):
+                extra["by_precision"]["error_vs_fp64_at_realistic_logit_scale"] = json.load(open(pp))
+        if "config4" in legs:
+            extra["config4"] = leg_config(a, rank, world, local_rank, a.games, a.playouts, 19, 3, 2,
+                                          "BASELINE configs[3]: %d games x %d playouts, res_block_nums=19" % (a.games, a.playouts))
+        if "config5" in legs:
+            extra["config5"] = leg_config5(a, local_rank, pv)
+    cpu = None
+    if rank == 0 and world == 1 and "cpu" in legs:
+        try:
+            cpu, _ = reference_cpu(3, 1, a.playouts, a.res_blocks, a.cpu_seconds, tree_only=False)
+        except Exception as ex:
+            cpu = dict(error=str(ex)[-300:])
 
     if rank == 0:
-        value = tot_exp / (dev_ms * 1e-3)
-        e2e_v = tot_exp / (e2e_ms * 1e-3)
-        plies_per_game = tuples_done / games_done if games_done else None
-        games_per_hour = (world * B * a.steps / (e2e_ms * 1e-3) * 3600.0 / plies_per_game) if plies_per_game else None
+        B = a.games
         h2d = B * 4 + B          # chosen child indices + search mask
-        d2h = B * 4 + B * 128 * (2 + 4 + 4 + 4 + 4) + B * (1 + 1 + 4 + 4 + 1 + 90) + 4 * (sp.waves - waves0) // max(1, a.steps) // max(1, a.playouts)
-        line = dict(metric=METRIC, value=value, unit="expansions/s", n_gpus=world, steps=a.steps, warmup=a.warmup,
-                    ms_per_step=e2e_ms / a.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+        d2h = B * 4 + B * 128 * (2 + 4 + 4 + 4 + 4) + B * (1 + 1 + 4 + 4 + 1 + 90) + 4 * m["waves"] // max(1, a.steps) // max(1, a.playouts)
+        line = dict(metric=METRIC, value=m["value"], unit="expansions/s", n_gpus=world, steps=a.steps, warmup=a.warmup,
+                    ms_per_step=m["e2e_ms"] / a.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
                     dtype=a.precision, data="synthetic (seed-0 xavier-initialised network, all games from the start position)",
                     config=dict(workload="%d concurrent self-play games x %d playouts per move, res_block_nums=%d, per GPU" % (B, a.playouts, a.res_blocks),
                                 games_per_gpu=B, playouts=a.playouts, res_block_nums=a.res_blocks, search_threads=1, exploration=True,
-                                cuda_graph=not a.no_graph, lanes=a.lanes, movegen_under_network=bool(sp.overlap_movegen and not a.no_graph and a.lanes == 1),
+                                cuda_graph=not a.no_graph, lanes=a.lanes, movegen_under_network=bool(a.overlap_movegen and not a.no_graph and a.lanes == 1),
                                 fused_conv_epilogue=plan.fused,
                                 network_ends=("csrc/cz_net.cu (board-byte first conv [%s], fused heads)" % plan.first_conv) if plan.dtype == torch.uint8 else "library",
                                 l2_policy="working set (trees %.1f GB + activations) exceeds the 126 MB L2" % (c1["max_arena_words"] * 4 * B / 1e9)),
-                    e2e=dict(value=e2e_v, unit="expansions/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, wall_ms=wall_ms),
-                    gpu_launches=int(tot_launch), clocks=clk, roofline=roof, cpu_baseline=cpu,
-                    extra=dict(expansions=tot_exp, waves_per_step=(sp.waves - waves0) / a.steps, games_finished=games_done,
-                               plies_per_finished_game=plies_per_game, games_per_hour=games_per_hour, tuples_all_gathered=gathered,
-                               nn_tflops=tot_exp * FLOPS_PER_EVAL.get(a.res_blocks, 0) / (dev_ms * 1e-3) / 1e12 / world,
-                               max_arena_words=c1["max_arena_words"], max_depth=c1["max_depth"],
-                               mean_L=(c1["sum_L"] - c0["sum_L"]) / max(1, c1["n_playout"] - c0["n_playout"]),
-                               mean_children=(c1["sum_C"] - c0["sum_C"]) / max(1, n_exp)))
+                    e2e=dict(value=m["e2e"], unit="expansions/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, wall_ms=m["wall_ms"]),
+                    gpu_launches=int(m["launches"]), clocks=m["clocks"], roofline=roof, cpu_baseline=cpu, extra=extra)
         print(json.dumps(line), flush=True)
-
-
-def gather_tuples(finished, dev, world, cap=2048):
-    """NCCL all_gather of the (s, pi, z) tuples of the games that ended this step."""
-    from cchess_zero_b200.distributed import all_gather_tuples
-    return len(all_gather_tuples([r for _, r in finished], dev, cap))
 
 
 def main():

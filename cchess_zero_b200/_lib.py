@@ -52,7 +52,7 @@ def _sig(L):
     L.cz_engine_tree_signature.argtypes = [vp, vp, i32, vp, i64, vp]
     L.cz_net_first_conv.argtypes = [vp, i32, vp, vp, vp, vp]
     L.cz_net_first_conv_tc.argtypes = [vp, i32, vp, vp, vp, vp]
-    L.cz_net_heads.argtypes = [vp, i32, vp, vp, vp, vp, vp, C.c_float, vp, vp, vp, vp, vp, vp, vp]
+    L.cz_net_heads.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
 
 
 def lib():

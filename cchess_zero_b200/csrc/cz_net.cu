@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(256) k_head_conv(const __half *__restrict__ x 
 // heads, stage 2a: value MLP 90 -> 256 ReLU -> 1 tanh (policy_value_network.py:73-74), 4 positions per CTA
 constexpr int VM_POS = 4;
 __global__ void __launch_bounds__(256) k_value_mlp(const float *__restrict__ hv /* [B][96] */, int B, const float *__restrict__ w1t /* [90][256] */,
-                                                    const float *__restrict__ b1, const float *__restrict__ w2, float b2, float *__restrict__ value) {
+                                                    const float *__restrict__ b1, const float *__restrict__ w2, const float *__restrict__ b2, float *__restrict__ value) {
     __shared__ float sh[VM_POS][96];
     __shared__ float red[VM_POS][8];
     const int p0 = blockIdx.x * VM_POS, t = threadIdx.x, warp = t >> 5, lane = t & 31;
@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(256) k_value_mlp(const float *__restrict__ hv 
     }
     __syncthreads();
     if (t < VM_POS && p0 + t < B) {
-        float s = b2;
+        float s = __ldg(b2);
 #pragma unroll
         for (int wq = 0; wq < 8; wq++) s += red[t][wq];
         value[p0 + t] = tanhf(s);
@@ -396,9 +396,9 @@ int cz_net_first_conv_tc(const uint8_t *canon_boards, int B, const void *w_umma,
     return cudaGetLastError() == cudaSuccess ? CZ_OK : CZ_ECUDA;
 }
 
-int cz_net_heads(const void *x, int B, const float *wh, const float *bh, const float *w1t, const float *b1, const float *w2, float b2,
+int cz_net_heads(const void *x, int B, const float *wh, const float *bh, const float *w1t, const float *b1, const float *w2, const float *b2,
                  const void *wp, const float *bp, void *hp_scratch, float *hv_scratch, float *logits, float *value, void *stream) {
-    if (!x || !wh || !bh || !w1t || !b1 || !w2 || !wp || !bp || !hp_scratch || !hv_scratch || !logits || !value || B <= 0) return CZ_EINVAL;
+    if (!x || !wh || !bh || !w1t || !b1 || !w2 || !b2 || !wp || !bp || !hp_scratch || !hv_scratch || !logits || !value || B <= 0) return CZ_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
     const int smem = 2 * 64 * LDS_ROW * (int)sizeof(__half);   // 51200 B > the 48 KB default: opt in (per device, so every call)
     if (cudaFuncSetAttribute(k_policy_fc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return CZ_ECUDA;

@@ -146,6 +146,7 @@ class MCTS_tree(object):
             self.engine.set_root_meta([side], [restrict_round])
             self._side, self._rr = side, restrict_round
         if self._plan is not None:
+            self._plan.refresh_if_stale()      # the evaluator was trained / restored since the last search: new weights into the captured graph
             self._search_graph(playouts)
         else:
             self.engine.search(self._eval, playouts, self._nn_in, self._logits, self._value)

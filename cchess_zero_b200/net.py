@@ -98,10 +98,20 @@ class InferencePlan:
     fp32 / tf32 / bf16 / fp16.  Takes the engine's NHWC batch as-is (its NCHW view is already
     channels_last) and returns float32 logits / value on the device."""
 
-    def __init__(self, net, precision="fp32", fused=True):
+    def __init__(self, net, precision="fp32", fused=True, owner=None):
         assert precision in _DT
         self.precision = precision
         self.dtype = _DT[precision]
+        self.net = net
+        self.owner = owner                      # policy_value_network whose weights_version tells when the folded copies are stale
+        self.version = getattr(owner, "weights_version", 0)
+        self._assign(self._fold_all(net))
+        self.fused = bool(fused) and self._probe_fused()
+        if os.environ.get("CCHESS_CUDNN_BENCHMARK", "0") == "1":
+            torch.backends.cudnn.benchmark = True     # let cuDNN time its engines for the (fixed) tower shapes
+
+    def _fold_all(self, net):
+        """Folded copies of the weights (BN into the convolutions), in this plan's dtype / memory format."""
         dt = self.dtype
 
         def fold(conv, bn):
@@ -111,17 +121,37 @@ class InferencePlan:
             return w.to(dt).contiguous(memory_format=torch.channels_last), b.to(dt).contiguous()
 
         with torch.no_grad():
-            self.w_in = fold(net.conv_in, net.bn_in)
-            self.blocks = [(fold(b.c1, b.b1), fold(b.c2, b.b2)) for b in net.blocks]
             wp, bp = fold(net.p_conv, net.p_bn)
             wv, bv = fold(net.v_conv, net.v_bn)
-            self.w_head = (torch.cat([wp, wv], 0).contiguous(memory_format=torch.channels_last), torch.cat([bp, bv], 0).contiguous())
-            self.p_fc = (net.p_fc.weight.detach().to(dt).contiguous(), net.p_fc.bias.detach().to(dt).contiguous())
-            self.v_fc1 = (net.v_fc1.weight.detach().float().contiguous(), net.v_fc1.bias.detach().float().contiguous())
-            self.v_fc2 = (net.v_fc2.weight.detach().float().contiguous(), net.v_fc2.bias.detach().float().contiguous())
-        self.fused = bool(fused) and self._probe_fused()
-        if os.environ.get("CCHESS_CUDNN_BENCHMARK", "0") == "1":
-            torch.backends.cudnn.benchmark = True     # let cuDNN time its engines for the (fixed) tower shapes
+            return dict(
+                w_in=fold(net.conv_in, net.bn_in),
+                blocks=[(fold(b.c1, b.b1), fold(b.c2, b.b2)) for b in net.blocks],
+                w_head=(torch.cat([wp, wv], 0).contiguous(memory_format=torch.channels_last), torch.cat([bp, bv], 0).contiguous()),
+                p_fc=(net.p_fc.weight.detach().to(dt).contiguous(), net.p_fc.bias.detach().to(dt).contiguous()),
+                v_fc1=(net.v_fc1.weight.detach().float().contiguous(), net.v_fc1.bias.detach().float().contiguous()),
+                v_fc2=(net.v_fc2.weight.detach().float().contiguous(), net.v_fc2.bias.detach().float().contiguous()))
+
+    def _assign(self, d):
+        self.w_in, self.blocks, self.w_head, self.p_fc, self.v_fc1, self.v_fc2 = d["w_in"], d["blocks"], d["w_head"], d["p_fc"], d["v_fc1"], d["v_fc2"]
+
+    def refresh(self):
+        """Re-fold the (trained / restored) weights INTO the existing tensors, so that CUDA graphs that captured this
+        plan keep evaluating with the current weights (MCTS_tree and SelfPlay hold such graphs across train_step)."""
+        d = self._fold_all(self.net)
+        with torch.no_grad():
+            for name in ("w_in", "w_head", "p_fc", "v_fc1", "v_fc2"):
+                for dst, src in zip(getattr(self, name), d[name]):
+                    dst.copy_(src)
+            for (c1, c2), (n1, n2) in zip(self.blocks, d["blocks"]):
+                for dst, src in zip(c1 + c2, n1 + n2):
+                    dst.copy_(src)
+        self.version = getattr(self.owner, "weights_version", self.version)
+
+    def refresh_if_stale(self):
+        if self.owner is not None and self.owner.weights_version != self.version:
+            self.refresh()
+            return True
+        return False
 
     def _probe_fused(self):
         try:
@@ -191,41 +221,62 @@ class NativePlan:
     precision = "fp16"
     dtype = torch.uint8
 
-    def __init__(self, net, max_batch, first_conv=None):
+    def __init__(self, net, max_batch, first_conv=None, owner=None):
         """first_conv: "gather" (CUDA-core gather-add, k_first_conv) or "tc" (tcgen05 + TMEM, k_first_conv_tc)."""
         import ctypes as C
         from ._lib import lib
         self._C, self._lib = C, lib()
         self.first_conv = first_conv or os.environ.get("CCHESS_FIRST_CONV", "gather")
         assert self.first_conv in ("gather", "tc")
-        base = InferencePlan(net, "fp16")
+        base = InferencePlan(net, "fp16", owner=owner)
         self.blocks, self.fused, self._base = base.blocks, base.fused, base
+        self.net, self.owner, self.version = net, owner, base.version
         dev = base.w_in[0].device
-        with torch.no_grad():
-            w, b = base.w_in                                                    # folded conv_in: [128,14,3,3] fp16
-            self.w1 = w.float().permute(2, 3, 1, 0).reshape(9, 14, 128).to(torch.float16).contiguous()
-            self.b1 = b.float().contiguous()
-            # tensor-core variant: K = tap*16 + piece code (codes 0 / 15 are zero rows), canonical K-major UMMA tile
-            # [k-chunk (18)][8-channel group (16)][channel in group (8)][k in chunk (8)]
-            wpad = torch.zeros((9, 16, 128), dtype=torch.float16, device=dev)
-            wpad[:, 1:15, :] = self.w1
-            wpad[4, 15, :] = self.b1.to(torch.float16)       # bias rides in the GEMM: A has a constant 1 in (centre tap, slot 15)
-            self.w1_umma = wpad.reshape(18, 8, 16, 8).permute(0, 2, 3, 1).contiguous()
-            wh, bh = base.w_head                                                 # [3,128,1,1]
-            self.wh = wh.float().reshape(3, 128).contiguous()
-            self.bh = bh.float().contiguous()
-            self.w1t = net.v_fc1.weight.detach().float().t().contiguous()        # [90,256]
-            self.bv1 = net.v_fc1.bias.detach().float().contiguous()
-            self.w2 = net.v_fc2.weight.detach().float().reshape(256).contiguous()
-            self.b2 = float(net.v_fc2.bias.detach().float().item())
-            self.wp = torch.zeros((2112, 192), dtype=torch.float16, device=dev)
-            self.wp[:NLABEL, :180] = net.p_fc.weight.detach().to(torch.float16)
-            self.bp = torch.zeros((2112,), dtype=torch.float32, device=dev)
-            self.bp[:NLABEL] = net.p_fc.bias.detach().float()
+        for k, v in self._derive().items():
+            setattr(self, k, v)
         self.max_batch = max_batch
         self.x1 = torch.empty((max_batch, 9, 10, 128), dtype=torch.float16, device=dev)
         self.hp = torch.zeros((max_batch, 192), dtype=torch.float16, device=dev)
         self.hv = torch.zeros((max_batch, 96), dtype=torch.float32, device=dev)
+
+    def _derive(self):
+        """Kernel-layout copies of the ends' weights, derived from the folded base plan."""
+        net, base = self.net, self._base
+        dev = base.w_in[0].device
+        with torch.no_grad():
+            w, b = base.w_in                                                    # folded conv_in: [128,14,3,3] fp16
+            w1 = w.float().permute(2, 3, 1, 0).reshape(9, 14, 128).to(torch.float16).contiguous()
+            b1 = b.float().contiguous()
+            # tensor-core variant: K = tap*16 + piece code (codes 0 / 15 are zero rows), canonical K-major UMMA tile
+            # [k-chunk (18)][8-channel group (16)][channel in group (8)][k in chunk (8)]
+            wpad = torch.zeros((9, 16, 128), dtype=torch.float16, device=dev)
+            wpad[:, 1:15, :] = w1
+            wpad[4, 15, :] = b1.to(torch.float16)            # bias rides in the GEMM: A has a constant 1 in (centre tap, slot 15)
+            wh, bh = base.w_head                                                 # [3,128,1,1]
+            wp = torch.zeros((2112, 192), dtype=torch.float16, device=dev)
+            wp[:NLABEL, :180] = net.p_fc.weight.detach().to(torch.float16)
+            bp = torch.zeros((2112,), dtype=torch.float32, device=dev)
+            bp[:NLABEL] = net.p_fc.bias.detach().float()
+            return dict(w1=w1, b1=b1, w1_umma=wpad.reshape(18, 8, 16, 8).permute(0, 2, 3, 1).contiguous(),
+                        wh=wh.float().reshape(3, 128).contiguous(), bh=bh.float().contiguous(),
+                        w1t=net.v_fc1.weight.detach().float().t().contiguous(),        # [90,256]
+                        bv1=net.v_fc1.bias.detach().float().contiguous(),
+                        w2=net.v_fc2.weight.detach().float().reshape(256).contiguous(),
+                        b2t=net.v_fc2.bias.detach().float().reshape(1).contiguous(), wp=wp, bp=bp)
+
+    def refresh(self):
+        """New weights into the SAME device tensors (captured CUDA graphs stay valid); see InferencePlan.refresh."""
+        self._base.refresh()
+        with torch.no_grad():
+            for k, v in self._derive().items():
+                getattr(self, k).copy_(v)
+        self.version = self._base.version
+
+    def refresh_if_stale(self):
+        if self.owner is not None and self.owner.weights_version != self.version:
+            self.refresh()
+            return True
+        return False
 
     def make_input(self, B):
         return torch.zeros((B, 96), dtype=torch.uint8, device=self.x1.device)
@@ -248,7 +299,7 @@ class NativePlan:
         if not x.is_contiguous(memory_format=torch.channels_last):
             x = x.contiguous(memory_format=torch.channels_last)
         rc = self._lib.cz_net_heads(x.data_ptr(), B, self.wh.data_ptr(), self.bh.data_ptr(), self.w1t.data_ptr(), self.bv1.data_ptr(),
-                                    self.w2.data_ptr(), self.b2, self.wp.data_ptr(), self.bp.data_ptr(), self.hp.data_ptr(), self.hv.data_ptr(),
+                                    self.w2.data_ptr(), self.b2t.data_ptr(), self.wp.data_ptr(), self.bp.data_ptr(), self.hp.data_ptr(), self.hv.data_ptr(),
                                     logits_out.data_ptr(), value_out.data_ptr(), st)
         if rc:
             raise RuntimeError("cz_net_heads failed (%d)" % rc)
@@ -309,11 +360,13 @@ class policy_value_network(object):
     """Drop-in for the reference class of the same name (policy_value_network.py:8-214):
     forward(positions) -> (logits np [B,2086] f32, value np [B,1] f32); train_step; save; restore."""
 
-    def __init__(self, res_block_nums=7, precision=None, device=None, seed=0, update_moving_stats=False):
+    save_dir = "./models"        # policy_value_network.py:12; the gpus variant overrides it BEFORE train_restore() runs
+
+    def __init__(self, res_block_nums=7, precision=None, device=None, seed=0, update_moving_stats=False, save_dir=None):
         if not torch.cuda.is_available():
             raise RuntimeError("policy_value_network needs a CUDA device")
         self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
-        self.save_dir = "./models"
+        self.save_dir = save_dir or type(self).save_dir
         self.filters_size = 128
         self.prob_size = NLABEL
         self.c_l2 = 0.0001
@@ -321,26 +374,29 @@ class policy_value_network(object):
         self.global_norm = 100
         self.global_step = 0
         self.precision = precision or os.environ.get("CCHESS_NN_PRECISION", "fp16")
-        g = torch.Generator(device="cpu")
         if seed is not None:
             torch.manual_seed(seed)
         self.net = PolicyValueNet(res_block_nums, self.filters_size, update_moving_stats).to(self.device)
         self.net = self.net.to(memory_format=torch.channels_last)
         self.opt = torch.optim.SGD(self.net.parameters(), lr=1e-3, momentum=self.momentum, nesterov=True)
         self._plan = None
+        # bumped whenever the weights change (train_step / restore): every plan handed out (and every CUDA graph that captured
+        # one: MCTS_tree, SelfPlay) re-folds its weight copies in place before its next search -- see InferencePlan.refresh
+        self.weights_version = 0
         self.train_restore()
 
     # -- inference -------------------------------------------------------------------------------
     def plan(self):
         if self._plan is None:
             self.net.eval()
-            self._plan = InferencePlan(self.net, self.precision)
+            self._plan = InferencePlan(self.net, self.precision, owner=self)
+        self._plan.refresh_if_stale()
         return self._plan
 
     def native_plan(self, max_batch, first_conv=None):
         """fp16 plan with the hand-written first-conv / head kernels (engine path); see NativePlan."""
         self.net.eval()
-        return NativePlan(self.net, max_batch, first_conv)
+        return NativePlan(self.net, max_batch, first_conv, owner=self)
 
     @property
     def nn_dtype(self):
@@ -358,31 +414,40 @@ class policy_value_network(object):
 
     # -- training (policy_value_network.py:76-126, 186-199) ---------------------------------------
     def train_step(self, positions, probs, winners, learning_rate):
-        self._plan = None
         x = torch.as_tensor(np.asarray(positions, dtype=np.float32)).reshape(-1, 9, 10, 14).to(self.device)
         pi = torch.as_tensor(np.asarray(probs, dtype=np.float32)).to(self.device)
         z = torch.as_tensor(np.asarray(winners, dtype=np.float32)).reshape(-1, 1).to(self.device)
         accuracy, loss = train_step_module(self.net, self.opt, x, pi, z, learning_rate, self.c_l2, self.global_norm)
+        self.net.eval()
+        self.weights_version += 1
         self.global_step += 1
         return accuracy, loss, self.global_step
 
     # -- checkpoints (policy_value_network.py:164-184) -------------------------------------------
     def save(self, in_global_step):
+        """Same call shape and file naming as tf.train.Saver in the reference (best_model.ckpt-<step> + a `checkpoint` index);
+        the payload is a torch state_dict -- the reference's TensorFlow checkpoints cannot be read (no TF in this stack, and no
+        reference weights ship with the repo).  Both files are written to a temporary name and renamed: a crash never leaves
+        the index pointing at a half-written checkpoint."""
         os.makedirs(self.save_dir, exist_ok=True)
         path = os.path.join(self.save_dir, "best_model.ckpt-%d" % int(in_global_step))
-        torch.save(dict(model=self.net.state_dict(), opt=self.opt.state_dict(), global_step=int(in_global_step)), path)
-        with open(os.path.join(self.save_dir, "checkpoint"), "w") as f:
+        tmp = path + ".tmp.%d" % os.getpid()
+        torch.save(dict(model=self.net.state_dict(), opt=self.opt.state_dict(), global_step=int(in_global_step)), tmp)
+        os.replace(tmp, path)
+        idx = os.path.join(self.save_dir, "checkpoint")
+        with open(idx + ".tmp", "w") as f:
             f.write(os.path.basename(path) + "\n")
+        os.replace(idx + ".tmp", idx)
         print("Model saved in file: {}".format(path))
         return path
 
     def restore(self, file):
         print("Restoring from {0}".format(file))
-        ck = torch.load(file, map_location=self.device)
+        ck = torch.load(file, map_location=self.device, weights_only=True)   # tensors / numbers only: no arbitrary unpickling
         self.net.load_state_dict(ck["model"])
         self.opt.load_state_dict(ck["opt"])
         self.global_step = ck.get("global_step", 0)
-        self._plan = None
+        self.weights_version += 1
 
     def train_restore(self):
         idx = os.path.join(self.save_dir, "checkpoint")
@@ -397,9 +462,11 @@ class policy_value_network(object):
 
 class policy_value_network_gpus(policy_value_network):
     """policy_value_network_gpus.py:9-379 replaced the batch split over in-graph towers; here every rank
-    owns one replica (one process per GPU), so the multi-GPU class is the single-GPU one per rank."""
+    owns one replica (one process per GPU), so the multi-GPU class is the single-GPU one per rank.
+    save_dir is './gpu_models' from the start (policy_value_network_gpus.py:14), so a resumed run restores from it."""
+
+    save_dir = "./gpu_models"
 
     def __init__(self, num_gpus=1, res_block_nums=7, **kw):
         super().__init__(res_block_nums, **kw)
         self.num_gpus = num_gpus
-        self.save_dir = "./gpu_models"

@@ -233,6 +233,7 @@ class SelfPlay:
             else:
                 self.nn_in = torch.zeros((n_games, 9, 10, 14), dtype=nn_dtype, device=dev)
             self.lanes = None
+        self.plan = plan
         self.forward = forward
         self.playouts = np.broadcast_to(np.asarray(playouts, dtype=np.int64), (n_games,)).copy()
         seeds = range(n_games) if seeds is None else seeds
@@ -357,6 +358,8 @@ class SelfPlay:
         if self.lanes is not None:
             return self._search_pipeline()
         e = self.engine
+        if self.plan is not None and hasattr(self.plan, "refresh_if_stale"):
+            self.plan.refresh_if_stale()       # weights trained / restored since the last search (the graph reads them in place)
         for p in np.unique(self.playouts[self.live]):
             e.begin_search(int(p), (self.live & (self.playouts == p)).astype(np.uint8))
         pmax = int(self.playouts[self.live].max()) if self.live.any() else 0
@@ -548,7 +551,9 @@ class cchess_main(object):
             new_probs, new_v = self.mcts.forward(state_batch)
             with np.errstate(all="ignore"):
                 kl_tmp = old_probs * (np.log((old_probs + 1e-10) / (new_probs + 1e-10)))
-            kl = np.mean([np.sum(line[np.isfinite(line)]) for line in kl_tmp])   # rows without nan/inf terms, main.py:1178-1182
+            # main.py:1178-1182 drops the terms whose str() is 'nan' or 'inf' -- and therefore KEEPS '-inf' (logits are used as
+            # probabilities, so negative old_probs are routine and a row sum can legitimately be -inf)
+            kl = np.mean([np.sum(line[~(np.isnan(line) | np.isposinf(line))]) for line in kl_tmp])
             if kl > self.kl_targ * 4:
                 break
         self.policy_value_netowrk.save(self.global_step)

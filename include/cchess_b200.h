@@ -170,7 +170,7 @@ int cz_engine_tree_signature(cz_engine *e, void *stream, int game, int64_t *out,
  *     (batch norm already folded in).  The one-hot [9][10][14] tensor of main.py:547-557 is never materialised.
  * cz_net_heads: x fp16 [B][90][128] -> logits f32 [B][2086] (raw, no softmax) and value f32 [B] (tanh).
  *     wh f32 [3][128] / bh [3]: 1x1 convs of the policy (2) and value (1) heads with BN folded; w1t f32 [90][256], b1 [256],
- *     w2 [256], b2: value MLP; wp fp16 [2112][192] / bp f32 [2112]: policy FC zero-padded; hp_scratch fp16 [B][192],
+ *     w2 [256], b2 [1] (device pointers, so that weights can be refreshed under a captured CUDA graph): value MLP; wp fp16 [2112][192] / bp f32 [2112]: policy FC zero-padded; hp_scratch fp16 [B][192],
  *     hv_scratch f32 [B][96]. */
 int cz_net_first_conv(const uint8_t *canon_boards, int B, const void *w1, const float *b1, void *out, void *stream);
 /* Same result on the tcgen05 tensor cores: the one-hot im2col matrix is built in shared memory, the accumulators live in
@@ -178,7 +178,7 @@ int cz_net_first_conv(const uint8_t *canon_boards, int B, const void *w1, const 
  * with k = tap*16 + piece code (code 0 rows are zero; row (centre tap, code 15) holds the bias, every other code-15 row is
  * zero); 36 864 bytes.  b1 is ignored (kept for signature symmetry with cz_net_first_conv). */
 int cz_net_first_conv_tc(const uint8_t *canon_boards, int B, const void *w_umma, const float *b1, void *out, void *stream);
-int cz_net_heads(const void *x, int B, const float *wh, const float *bh, const float *w1t, const float *b1, const float *w2, float b2,
+int cz_net_heads(const void *x, int B, const float *wh, const float *bh, const float *w1t, const float *b1, const float *w2, const float *b2,
                  const void *wp, const float *bp, void *hp_scratch, float *hv_scratch, float *logits, float *value, void *stream);
 
 #ifdef __cplusplus

@@ -31,7 +31,10 @@ import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
-REF_DIR = os.environ.get("CCHESS_REFERENCE_DIR", "/root/reference")
+import stage_reference as _stage  # noqa: E402
+
+# the live reference tree in the build container; on the GPU box the byte-identical copy staged by oracle/stage_reference.py
+REF_DIR = os.environ.get("CCHESS_REFERENCE_DIR") or _stage.staged_dir() or "/root/reference"
 
 _ref = None
 

@@ -83,8 +83,11 @@ def test_flip_helpers_and_record_packing():
     back = unpack_records(buf, k)
     for (s, pi, z), s0, p0, z0 in zip(back, g["states"], g["pis"], g["z"]):
         assert s == s0 and z == z0 and np.array_equal(pi, p0)
-    _, k2, left2 = pack_records([rec], 5)
-    assert k2 == 5 and len(left2) == len(g["states"]) - 5
+    _, k2, left2 = pack_records([rec, rec], len(g["states"]) + 3)      # a cap never splits or drops a game: the second one is handed back whole
+    assert k2 == len(g["states"]) and len(left2) == 1 and left2[0] is rec
+    from cchess_zero_b200.distributed import TupleBatch
+    tb = TupleBatch(buf[:k])
+    assert len(tb) == k and np.array_equal(tb.dense_pi(), np.stack(g["pis"])) and np.array_equal(tb.z, np.asarray(g["z"], dtype=np.float64))
     assert shard_seeds(4, 0) == [0, 1, 2, 3] and shard_seeds(4, 2, 10) == [18, 19, 20, 21]
 
 
@@ -127,13 +130,42 @@ def test_all_gather_tuples_world_size_2_gloo(tmp_path):
 
 
 def test_bench_reference_arm_prints_contract_line():
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--games", "8", "--steps", "1", "--warmup", "1"],
-                       capture_output=True, text=True, timeout=600)
+    """--impl reference times the UNMODIFIED reference (search_threads=16, one process per core) when it is present / staged."""
+    env = dict(os.environ, CCHESS_REF_SECONDS="8")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=900, env=env)
     assert r.returncode == 0, r.stderr[-2000:]
     import json
     line = json.loads(r.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["metric"] == "mcts_node_expansions_per_sec" and line["value"] > 0
-    assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import stage_reference as S
+    cb = line["cpu_baseline"]
+    if S.staged_dir() and S.verify():
+        assert cb["kind"] == "reference" and cb["search_threads"] == 16 and cb["cores"] >= 1 and cb["tree_only_value"] > cb["value"]
+        assert cb["port_value"]["kind"] == "port"
+    else:
+        assert cb["kind"] == "port"
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["steps"] == 2 and line["config"]["search_threads"] == 16
+
+
+def test_staged_reference_is_byte_identical_and_loads_from_the_staged_copy(tmp_path):
+    """oracle/stage_reference.py: the copy that travels to the GPU box hashes to the committed manifest and is importable
+    through the harness without /root/reference (CCHESS_REFERENCE_DIR points at the staged directory)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import stage_reference as S
+    if not os.path.isdir(S.DST):
+        if not os.path.isdir(S.SRC):
+            pytest.skip("neither the reference nor a staged copy is present")
+        S.stage()
+    assert S.verify(S.DST)
+    code = ("import os, sys; sys.path.insert(0, %r); import ref_harness as H; ref = H.load_reference(); "
+            "assert os.path.dirname(ref.__file__) == %r, ref.__file__; "
+            "t = H.make_mcts(H.FAKE_NETS['mod17'], 16); t.main(t.root.state, 'w', 0, 64); "
+            "print('STAGED_OK', sorted((a, c.N) for a, c in t.root.child.items() if c.N)[:2])") % (os.path.join(ROOT, "oracle"), S.DST)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=dict(os.environ, CCHESS_REFERENCE_DIR=S.DST))
+    assert r.returncode == 0 and "STAGED_OK" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
+    assert "('a0a1', 47), ('a0a2', 17)" in r.stdout          # SURVEY Appendix B: K=16, 64 playouts, mod17 net
 
 
 _DP = r'''
