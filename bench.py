@@ -63,7 +63,7 @@ def parse():
     ap.add_argument("--legs", default=os.environ.get("CCHESS_BENCH_LEGS", ALL_LEGS), help="comma list of extra legs (%s) or 'none'" % ALL_LEGS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=20.0)
-    ap.add_argument("--soak-plies", type=int, default=150)
+    ap.add_argument("--soak-plies", type=int, default=170)
     ap.add_argument("--profile-waves", type=int, default=200, help="waves timed individually for the roofline line")
     ap.add_argument("--arena-words", type=int, default=0)
     ap.add_argument("--kwave-capture", action="store_true", help="ncu helper: play --warmup plies (deep trees), then run --profile-waves eager waves and exit")
@@ -385,12 +385,14 @@ class Runner:
 
 
 def leg_precision(a, rank, world, local_rank, pv):
-    """The main workload in the other arithmetics, same weights: tf32 and fp32 (the reference's own arithmetic is fp32)."""
+    """The main workload in the other arithmetics, same weights: tf32 and fp32 (the reference's own arithmetic is fp32).
+    fp32 convolutions run ~57x slower than fp16 (no tensor cores), so that leg plays one ply of a 120-playout search: the rate per
+    wave is what is measured (the network is > 99 % of such a wave), the line says which playout count was used."""
     out = {}
-    for prec, steps in (("tf32", 2), ("fp32", 1)):
-        r = Runner(a, rank, world, local_rank, a.games, a.playouts, a.res_blocks, prec, pv=pv, arena_words=1 << 20)
-        m = r.plies(steps, 1)
-        out[prec] = dict(value=m["value"], e2e=m["e2e"], plies_timed=steps, ms_per_step=m["e2e_ms"] / steps,
+    for prec, steps, warm, playouts in (("tf32", 2, 1, a.playouts), ("fp32", 1, 0, min(a.playouts, 120))):
+        r = Runner(a, rank, world, local_rank, a.games, playouts, a.res_blocks, prec, pv=pv, arena_words=1 << 20)
+        m = r.plies(steps, warm)
+        out[prec] = dict(value=m["value"], e2e=m["e2e"], plies_timed=steps, playouts=playouts, ms_per_step=m["e2e_ms"] / steps,
                          nn_tflops=m["expansions"] * FLOPS_PER_EVAL.get(a.res_blocks, 0) / (m["dev_ms"] * 1e-3) / 1e12 / world)
         r.close()
     return out
@@ -520,7 +522,7 @@ def run_ours(a, rank, world, local_rank):
                                       pv=pv if a.res_blocks == 7 else None)
     if world == 1:
         if "precision" in legs:
-            extra["by_precision"] = dict(fp16=dict(value=m["value"], e2e=m["e2e"], plies_timed=a.steps, ms_per_step=m["e2e_ms"] / a.steps)) \
+            extra["by_precision"] = dict(fp16=dict(value=m["value"], e2e=m["e2e"], plies_timed=a.steps, playouts=a.playouts, ms_per_step=m["e2e_ms"] / a.steps)) \
                 if a.precision == "fp16" else {}
             extra["by_precision"].update(leg_precision(a, rank, world, local_rank, pv))
             pp = os.path.join(ROOT, "profiles", "r02_nn_precision_scaled.json")
