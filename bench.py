@@ -57,7 +57,6 @@ def parse():
     ap.add_argument("--precision", default=os.environ.get("CCHESS_NN_PRECISION", "fp16"))
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--first-conv", default=None, choices=["gather", "tc"], help="first-layer kernel: CUDA-core gather-add or tcgen05/TMEM")
-    ap.add_argument("--overlap-movegen", action="store_true", help="leaf move generation on a side stream under the network (measured: no gain)")
     ap.add_argument("--lanes", type=int, default=1, choices=[1, 2], help="2 = pipeline two half-batches (tree kernel under the other half's network)")
     ap.add_argument("--library-ends", action="store_true", help="use cuDNN/cuBLAS for the first conv and the heads instead of csrc/cz_net.cu")
     ap.add_argument("--legs", default=os.environ.get("CCHESS_BENCH_LEGS", ALL_LEGS), help="comma list of extra legs (%s) or 'none'" % ALL_LEGS)
@@ -254,7 +253,7 @@ class Runner:
         self.plan = factory(games // a.lanes)
         self.sp = SelfPlay(games, None, playouts, seeds=[rank * games + g for g in range(games)], device=local_rank,
                            auto_reset=True, keep_records=True, plan=self.plan if a.lanes == 1 else None, plan_factory=factory, lanes=a.lanes,
-                           overlap_movegen=a.overlap_movegen, arena_words=a.arena_words if arena_words is None else arena_words)
+                           arena_words=a.arena_words if arena_words is None else arena_words)
         if not a.no_graph:
             self.sp.capture_graph()
         self.search_ms = []
@@ -350,19 +349,12 @@ class Runner:
         k0 = e.counters()
         evs = []
         lanes = sp.lanes if sp.lanes is not None else [sp]       # a single-lane SelfPlay has the same attribute names
-        side = torch.cuda.Stream()
-        cur = torch.cuda.current_stream()
         for _ in range(n_waves):
             for ln in lanes:
                 x, y = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 x.record(); ln.engine.wave(ln.nn_in, ln.logits, ln.value); y.record()
                 evs.append((x, y))
-                if sp.lanes is None and sp.overlap_movegen and not a.no_graph:      # same schedule as the captured graph
-                    side.wait_stream(cur)
-                    with torch.cuda.stream(side):
-                        ln.engine.prepare_leaves()
                 ln.forward(ln.nn_in)
-                cur.wait_stream(side)
         torch.cuda.synchronize()
         sp.search = timed
         k1 = e.counters()
@@ -543,13 +535,13 @@ def run_ours(a, rank, world, local_rank):
     if rank == 0:
         B = a.games
         h2d = B * 4 + B          # chosen child indices + search mask
-        d2h = B * 4 + B * 128 * (2 + 4 + 4 + 4 + 4) + B * (1 + 1 + 4 + 4 + 1 + 90) + 4 * m["waves"] // max(1, a.steps) // max(1, a.playouts)
+        d2h = B * 4 + B * 128 * (2 + 4) + B * 112 + 4    # root n / moves / visits, packed status records, the unfinished count
         line = dict(metric=METRIC, value=m["value"], unit="expansions/s", n_gpus=world, steps=a.steps, warmup=a.warmup,
                     ms_per_step=m["e2e_ms"] / a.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
                     dtype=a.precision, data="synthetic (seed-0 xavier-initialised network, all games from the start position)",
                     config=dict(workload="%d concurrent self-play games x %d playouts per move, res_block_nums=%d, per GPU" % (B, a.playouts, a.res_blocks),
                                 games_per_gpu=B, playouts=a.playouts, res_block_nums=a.res_blocks, search_threads=1, exploration=True,
-                                cuda_graph=not a.no_graph, lanes=a.lanes, movegen_under_network=bool(a.overlap_movegen and not a.no_graph and a.lanes == 1),
+                                cuda_graph=not a.no_graph, lanes=a.lanes,
                                 fused_conv_epilogue=plan.fused,
                                 network_ends=("csrc/cz_net.cu (board-byte first conv [%s], fused heads)" % plan.first_conv) if plan.dtype == torch.uint8 else "library",
                                 l2_policy="working set (trees %.1f GB + activations) exceeds the 126 MB L2" % (c1["max_arena_words"] * 4 * B / 1e9)),

@@ -6,7 +6,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcchess_b200.so")
 
-NSQ, NLABEL, MAXCHILD, ENC_LEN = 90, 2086, 128, 1260
+NSQ, NLABEL, MAXCHILD, ENC_LEN, STATUS_BYTES = 90, 2086, 128, 1260, 112
 F32, BF16, F16, BOARD = 0, 1, 2, 3
 ERR_NAMES = {1: "NOMOVES", 2: "NOLABEL", 4: "DEPTH", 8: "ARENA", 16: "CHILDREN"}
 
@@ -41,8 +41,11 @@ def _sig(L):
     L.cz_engine_wave.argtypes = [vp, vp, vp, i32, vp, vp]
     L.cz_engine_select.argtypes = [vp, vp, vp, i32]
     L.cz_engine_expand_backup.argtypes = [vp, vp, vp, vp]
-    L.cz_engine_prepare_leaves.argtypes = [vp, vp]
-    L.cz_engine_use_prepared_leaves.argtypes = [vp, i32]
+    L.cz_engine_enable_hashing.argtypes = [vp, i32]
+    L.cz_engine_leaf_hashes.argtypes = [vp, vp]
+    L.cz_engine_root_keys.argtypes = [vp, vp, vp]
+    L.cz_engine_play_status.argtypes = [vp, vp, vp, vp]
+    L.cz_engine_status_packed.argtypes = [vp, vp, vp]
     L.cz_engine_unfinished.argtypes = [vp, vp, vp]
     L.cz_engine_unfinished_async.argtypes = [vp, vp, vp]
     L.cz_engine_root_children.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]

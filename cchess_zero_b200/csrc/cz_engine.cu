@@ -6,7 +6,12 @@
 // round-to-nearest IEEE intrinsic in the width numpy uses (f32 for P/W/Q, f64 for U and Q+U).
 //
 // HBM layout (SoA over games; B = n_games, A = arena words per half):
-//   root_board  u8  [B][96]     90-byte mailbox + pad, 24 coalesced u32 per game
+//   hdr         u32 [B][16]     ONE 64-byte line per game with every scalar of its search and game state (flags: active /
+//                               pending / side / arena half / terminal / winner; done, target, restrict_round, root N / count /
+//                               base, arena top, path length, ply, high-water marks, error flags, Zobrist key of the root).
+//                               A wave reads it with one coalesced load and writes it back with one coalesced store.
+//   root_board  u8  [B][96]     90-byte mailbox + pad, 24 coalesced u32 per game; the packed bitboards the move generator
+//                               works on (occupancy, red set, file-major occupancy) are derived from it by ballots (cz_rules.cuh)
 //   arena       u32 [B][2][A]   per-game bump arena of node blocks, two halves (ping-pong
 //                               compaction when the root moves, MCTS_tree.update_tree)
 //   node block  = 8-word header {n_children,...} followed by five arrays of stride
@@ -14,8 +19,15 @@
 //                 META = move | n_grandchildren << 16, CHILD = base of the child's block or NONE.
 //                 One node = one contiguous run, each array sector-aligned, so a warp reads
 //                 all PUCT inputs of a node with coalesced loads in a single round trip.
-//   path        uint2 [B][MAXD] (slot of P[idx], cs) of the edges of the current playout
+//   path        uint2 [B][MAXD] {slot of P[idx], cs | move << 8} of the edges of the current playout
 //   leaf_board  u8  [B][96]     board at the pending leaf (+ side in byte 90)
+//
+// Latency plan of a wave (the kernel is a chain of dependent loads, not a bandwidth problem): everything whose address is
+// known at entry -- header line, leaf board, root board, the first 32 path entries, the evaluated value -- is requested before
+// the first use (round trip 1); the W / N words of the path (back-up operands) are requested next and arrive under the move
+// generation (round trip 2); the root block of the next descent is requested before the logit gather of the expansion (round
+// trips 3 and 4 overlap); after that one round trip per tree level remains, which is the pointer chase itself.  Counters are
+// fire-and-forget reductions (RED), never read-modify-write chains.
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -33,7 +45,19 @@
 #define HDR 8
 #define WARPS_PER_BLOCK 4
 #define MAX_INKERNEL_PLAYOUTS 16
-#define MAX_WPB 10                 // warps per CTA of the wave kernels (10 * sizeof(WarpSmem) < 48 KB)
+#define MAX_WPB 10                 // warps per CTA of the wave kernels
+#define SPATH 32                   // path entries mirrored in shared memory / prefetched in registers
+
+// per-game header line
+enum { H_FLAGS = 0, H_DONE, H_TARGET, H_RR, H_ROOTN, H_ROOTCNT, H_ROOTBASE, H_ALLOC, H_PLEN, H_PLY, H_MAXALLOC, H_ERR, H_MAXDEPTH,
+       H_HASHLO, H_HASHHI, H_SPARE, HW = 16 };
+#define F_ACTIVE 1u
+#define F_PEND(f) (((f) >> 1) & 3u)                 // 0 none, 1 leaf evaluation pending, 2 root expansion pending
+#define F_SETPEND(f, p) (((f) & ~6u) | ((uint32_t)(p) << 1))
+#define F_SIDE 8u
+#define F_CUR 16u
+#define F_TERM(f) (((f) >> 8) & 3u)                 // 0 running, 1 king captured, 2 draw
+#define F_WIN(f) ((int)(((f) >> 10) & 3u) - 1)      // -1 none, 0 'w', 1 'b'
 
 namespace {
 
@@ -93,42 +117,31 @@ const Labels &labels() { static Labels L; return L; }
 struct Dev {
     int B;
     long long A;
-    uint8_t *root_board;
-    uint8_t *side;
-    int32_t *rr, *ply;
-    int32_t *root_N, *root_cnt;
-    uint32_t *root_base;
-    int32_t *done, *target;
-    uint8_t *pending, *active;
-    int32_t *path_len;
-    uint2 *path;
-    uint8_t *leaf_board;
-    uint16_t *leaf_moves, *leaf_li;   // [B][128]: move list and (flipped) label index of the pending leaf, filled by k_prepare_leaves
-    int32_t *leaf_n;                  // [B]: number of moves, -1 = not prepared
     int K;                            // leaves per game per wave (1 = the reference's search_threads=1 schedule)
+    int hash_on;                      // maintain Zobrist keys of the pending leaves (board hashing; off by default)
+    uint32_t *hdr;                    // [B][HW]
+    uint8_t *root_board;              // [B][96]
+    uint8_t *leaf_board;              // [B][96]
+    uint2 *path;                      // [B][MAXD]
     uint8_t *pendK;                   // [B][K] leaf-parallel mode: per-slot pending flag, path length, path, leaf board
     int32_t *plenK;
     uint2 *pathK;
     uint8_t *leafK;
-    int prepared;                     // 1: k_wave trusts leaf_moves / leaf_li / leaf_n (cz_engine_prepare_leaves ran after the previous wave)
     uint32_t *arena;
-    uint8_t *cur;
-    uint32_t *alloc, *max_alloc;
     unsigned long long *cnt_expand, *cnt_playout, *cnt_L, *cnt_c, *cnt_C;
-    uint32_t *err;
-    int32_t *max_depth;
-    uint8_t *terminal;
-    int8_t *winner;
+    unsigned long long *leaf_hash;    // [B*K] Zobrist key of the position in network row r (valid when hash_on)
+    const unsigned long long *zob;    // [16][96] piece-square keys; zob[95] = side-to-move key
     const int16_t *label_of;
     // staging
     int32_t *st_n, *st_visits, *st_choice;
     uint16_t *st_moves;
     float *st_w, *st_p, *st_q;
     int32_t *st_count;
+    uint8_t *st_status;               // [B][CZ_STATUS_BYTES]
 };
 
-__device__ __forceinline__ uint32_t *arena_of(const Dev &E, int g) {
-    return E.arena + ((size_t)g * 2 + E.cur[g]) * (size_t)E.A;
+__device__ __forceinline__ uint32_t *arena_half(const Dev &E, int g, int cur) {
+    return E.arena + ((size_t)g * 2 + cur) * (size_t)E.A;
 }
 
 struct WarpSmem {
@@ -136,6 +149,7 @@ struct WarpSmem {
     uint16_t moves[136];
     uint16_t li[128];
     float ps[128];
+    uint2 path[SPATH];
     cz::MoveScratch scratch;
 };
 
@@ -145,34 +159,33 @@ __device__ __forceinline__ unsigned long long dkey(double s) {
     return (unsigned long long)(b ^ ((b >> 63) | (long long)0x8000000000000000ULL));
 }
 
-// VL undo + back_up_value along the recorded path (main.py:426-435, 189-194).
+// a path entry names one edge: {word index of its P entry, stride cs (low byte) | move << 8}
+__device__ __forceinline__ uint2 path_entry(uint32_t slot, uint32_t cs, uint32_t move) { return make_uint2(slot, cs | (move << 8)); }
+#define PE_CS(pe) ((pe).y & 0xFFu)
+#define PE_MOVE(pe) ((pe).y >> 8)
+
+// VL undo + back_up_value of ONE edge (main.py:426-435, 189-194); (Wbits, Nbits) were loaded earlier.
 // val = value handed to the deepest edge; sign alternates going up.
 // `inflight`: leaf-parallel mode keeps a per-edge count of playouts currently holding a virtual loss on it (META bits 24-30).
+__device__ __forceinline__ void backup_edge(uint32_t *ar, uint2 pe, int d, int depth, float val, uint32_t Wbits, uint32_t Nbits, bool inflight) {
+    const uint32_t slot = pe.x, cs = PE_CS(pe);
+    const float v = ((depth - 1 - d) & 1) ? -val : val;
+    ar[slot + cs] = __float_as_uint(__fadd_rn(__fadd_rn(__uint_as_float(Wbits), 3.0f), v));
+    ar[slot + 2 * cs] = (uint32_t)((int)Nbits - 3 + 1);
+    if (inflight) ar[slot + 3 * cs] -= (1u << 24);
+}
+// whole path from memory (global or shared), any depth
 __device__ void warp_backup_path(const uint2 *path, uint32_t *ar, int depth, float val, int lane, bool inflight) {
     for (int d = lane; d < depth; d += 32) {
         const uint2 pe = path[d];
-        const uint32_t slot = pe.x, cs = pe.y;
-        float W = __uint_as_float(ar[slot + cs]);
-        int N = (int)ar[slot + 2 * cs];
-        const float v = ((depth - 1 - d) & 1) ? -val : val;
-        N = N - 3 + 1;
-        W = __fadd_rn(__fadd_rn(W, 3.0f), v);
-        ar[slot + cs] = __float_as_uint(W);
-        ar[slot + 2 * cs] = (uint32_t)N;
-        if (inflight) ar[slot + 3 * cs] -= (1u << 24);
+        backup_edge(ar, pe, d, depth, val, ar[pe.x + PE_CS(pe)], ar[pe.x + 2 * PE_CS(pe)], inflight);
     }
     __syncwarp();
 }
-__device__ __forceinline__ void warp_backup(const Dev &E, int g, uint32_t *ar, int depth, float val, int lane) {
-    warp_backup_path(E.path + (size_t)g * MAXD, ar, depth, val, lane, false);
-}
 
-// Move list of the pending leaf of game g in reference order + the label index of every move (with flip_policy,
-// main.py:1152-1155, folded into the index: rank y -> 9-y for black).  Leaves S.moves[i] / li in S.li[i]; returns n.
-__device__ int warp_leaf_moves_at(const Dev &E, const uint8_t *leaf_board, WarpSmem &S, uint32_t &errf, int lane) {
-    const uint32_t *lb = reinterpret_cast<const uint32_t *>(leaf_board);
-    if (lane < 24) reinterpret_cast<uint32_t *>(S.board)[lane] = lb[lane];
-    __syncwarp();
+// Move list of the leaf staged in S.board (+ side in byte 90), in reference order, and the label index of every move (with
+// flip_policy, main.py:1152-1155, folded into the index: rank y -> 9-y for black).  Leaves S.moves[i] / S.li[i]; returns n.
+__device__ int warp_leaf_moves(const Dev &E, WarpSmem &S, uint32_t &errf, int lane) {
     const int lside = S.board[90];
     int n = cz::warp_legal_moves(S.board, lside, S.moves, S.scratch, lane);
     if (n == 0) errf |= CZ_ERR_NOMOVES;
@@ -184,7 +197,7 @@ __device__ int warp_leaf_moves_at(const Dev &E, const uint8_t *leaf_board, WarpS
             src = (9 - src / 9) * 9 + src % 9;
             dst = (9 - dst / 9) * 9 + dst % 9;
         }
-        int li = E.label_of[src * CZ_NSQ + dst];
+        int li = __ldg(E.label_of + src * CZ_NSQ + dst);
         if (li < 0) { errf |= CZ_ERR_NOLABEL; li = 0; }
         S.li[i] = (uint16_t)li;
     }
@@ -192,37 +205,25 @@ __device__ int warp_leaf_moves_at(const Dev &E, const uint8_t *leaf_board, WarpS
     return n;
 }
 
-__device__ __forceinline__ int warp_leaf_moves(const Dev &E, int g, WarpSmem &S, uint32_t &errf, int lane) {
-    return warp_leaf_moves_at(E, E.leaf_board + (size_t)g * 96, S, errf, lane);
-}
-
-// leaf_node.expand (main.py:175-187) for a pending leaf of game g; returns false on error.
-// lg: that leaf's logits row; path/depth: its recorded path; leaf_board: its board (+ side in byte 90).
-__device__ bool warp_expand_at(const Dev &E, int g, uint32_t *ar, WarpSmem &S, const float *lg, int pend, const uint2 *path, int depth,
-                               const uint8_t *leaf_board, bool allow_prepared, int lane) {
-    uint32_t errf = 0;
-    int n;
-    if (allow_prepared && E.prepared && E.leaf_n[g] >= 0) {
-        // the move list was generated by k_prepare_leaves while the network was running
-        n = E.leaf_n[g];
-        for (int i = lane; i < n; i += 32) {
-            S.moves[i] = E.leaf_moves[(size_t)g * CZ_MAXCHILD + i];
-            S.ps[i] = __ldg(lg + E.leaf_li[(size_t)g * CZ_MAXCHILD + i]);
-        }
-        if (n == 0) errf |= CZ_ERR_NOMOVES;
-    } else {
-        n = warp_leaf_moves_at(E, leaf_board, S, errf, lane);
-        for (int i = lane; i < n; i += 32) S.ps[i] = __ldg(lg + S.li[i]);
-    }
+// leaf_node.expand (main.py:175-187) in three parts.
+// 1: move generation + arena reservation.  Returns n > 0, or 0 when the expansion cannot happen (no moves / arena full).
+__device__ int expand_reserve(const Dev &E, WarpSmem &S, uint32_t &alloc, uint32_t &base, uint32_t &errf, int lane) {
+    uint32_t ef = 0;
+    const int n = warp_leaf_moves(E, S, ef, lane);
     const uint32_t cs = (uint32_t)((n + 7) & ~7), size = HDR + 5 * cs;
-    const uint32_t base = E.alloc[g];
-    if ((long long)base + size > E.A) errf |= CZ_ERR_ARENA;
-    errf = __reduce_or_sync(CZ_FULL, errf);
+    base = alloc;
+    if ((long long)base + size > E.A) ef |= CZ_ERR_ARENA;
+    ef = __reduce_or_sync(CZ_FULL, ef);
+    errf |= ef;
+    if (ef & (CZ_ERR_ARENA | CZ_ERR_NOMOVES)) return 0;
+    alloc = base + size;
+    return n;
+}
+// 2: prior gather (lg = this leaf's logits row), serial float32 normalisation, block write
+__device__ void expand_write(uint32_t *ar, WarpSmem &S, const float *lg, int n, uint32_t base, int lane) {
+    for (int i = lane; i < n; i += 32) S.ps[i] = __ldg(lg + S.li[i]);
     __syncwarp();
-    if (errf) {
-        if (lane == 0) atomicOr(E.err + g, errf);
-        if (errf & (CZ_ERR_ARENA | CZ_ERR_NOMOVES)) return false;
-    }
+    const uint32_t cs = (uint32_t)((n + 7) & ~7);
     float tot = 1e-8f;  // tot_p = 1e-8 accumulated in float32, in move order (main.py:176, 184)
 #pragma unroll 8
     for (int i = 0; i < n; i++) tot = __fadd_rn(tot, S.ps[i]);   // strictly serial adds; unrolled so the LDS latency overlaps
@@ -236,26 +237,25 @@ __device__ bool warp_expand_at(const Dev &E, int g, uint32_t *ar, WarpSmem &S, c
         blk[HDR + 3 * cs + i] = live ? (uint32_t)S.moves[i] : 0u;              // META: move, no grandchildren yet
         blk[HDR + 4 * cs + i] = NONE;
     }
-    if (lane == 0) {
-        E.alloc[g] = base + size;
-        if (base + size > E.max_alloc[g]) E.max_alloc[g] = base + size;
-        if (pend == 2) {
-            E.root_base[g] = base;
-            E.root_cnt[g] = n;
-        } else {
-            // META: move (0-15) | n_children (16-23) | in-flight count (24-30, leaf-parallel mode) | claimed (31)
-            const uint2 pe = path[depth - 1];
-            ar[pe.x + 3 * pe.y] = (ar[pe.x + 3 * pe.y] & 0x7F00FFFFu) | ((uint32_t)n << 16);   // links the child, clears `claimed`
-            ar[pe.x + 4 * pe.y] = base;
-        }
-        E.cnt_expand[g] += 1;
-        E.cnt_C[g] += (unsigned)n;
-    }
     __syncwarp();
-    return true;
 }
-__device__ __forceinline__ bool warp_expand(const Dev &E, int g, uint32_t *ar, WarpSmem &S, const float *logits, int pend, int depth, int lane) {
-    return warp_expand_at(E, g, ar, S, logits + (size_t)g * CZ_NLABEL, pend, E.path + (size_t)g * MAXD, depth, E.leaf_board + (size_t)g * 96, true, lane);
+// 3: link the new block under the edge it was reached by (plain stores: the move travels in the path entry).
+// META: move (0-15) | n_children (16-23) | in-flight count (24-30, leaf-parallel mode) | claimed (31, cleared here)
+__device__ __forceinline__ void expand_link(uint32_t *ar, uint2 pe, int n, uint32_t base, uint32_t inflight) {
+    ar[pe.x + 3 * PE_CS(pe)] = PE_MOVE(pe) | ((uint32_t)n << 16) | (inflight << 24);
+    ar[pe.x + 4 * PE_CS(pe)] = base;
+}
+
+// Zobrist key delta of one move on the mailbox board (piece p moves src -> dst, capturing q): board hashing of north_star
+__device__ __forceinline__ unsigned long long zob_move(const unsigned long long *z, int p, int q, int src, int dst) {
+    unsigned long long h = __ldg(z + p * 96 + src) ^ __ldg(z + p * 96 + dst) ^ __ldg(z + 95);   // mover leaves / arrives, side flips
+    if (q) h ^= __ldg(z + q * 96 + dst);
+    return h;
+}
+__device__ unsigned long long zob_board(const unsigned long long *z, const uint8_t *b, int side) {
+    unsigned long long h = side ? z[95] : 0ull;
+    for (int s = 0; s < 90; s++) if (b[s]) h ^= z[b[s] * 96 + s];
+    return h;
 }
 
 // row: index of this leaf's row in the network batch (g in one-leaf mode, g*K+slot in leaf-parallel mode)
@@ -281,11 +281,64 @@ __device__ void store_leaf_at(uint8_t *leaf_board, WarpSmem &S, int side, T *nn_
         cz::warp_encode<T>(S.board, side, nn_in + row * CZ_ENC_LEN, lane);
     }
 }
-template <typename T>
-__device__ __forceinline__ void store_leaf(const Dev &E, int g, WarpSmem &S, int side, T *nn_in, int lane) {
-    if (lane == 0) E.leaf_n[g] = -1;          // no prepared move list for this leaf yet
-    store_leaf_at<T>(E.leaf_board + (size_t)g * 96, S, side, nn_in, (size_t)g, lane);
+
+// The PUCT inputs of one node block in registers: lane l holds children l, l+32, l+64, l+96.
+struct BlockRegs {
+    uint32_t P[4], W[4], N[4], meta[4], child[4];
+};
+__device__ __forceinline__ void load_block(const uint32_t *ar, uint32_t base, int cnt, int lane, BlockRegs &R) {
+    const uint32_t cs = (uint32_t)((cnt + 7) & ~7);
+    const uint32_t *blk = ar + base + HDR;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int i = lane + 32 * k;
+        if (i < cnt) {
+            R.P[k] = blk[i]; R.W[k] = blk[cs + i]; R.N[k] = blk[2 * cs + i]; R.meta[k] = blk[3 * cs + i]; R.child[k] = blk[4 * cs + i];
+        }
+    }
 }
+__device__ __forceinline__ uint32_t pick(const uint32_t (&a)[4], int k) { return k == 0 ? a[0] : k == 1 ? a[1] : k == 2 ? a[2] : a[3]; }
+
+// select_new (main.py:158-159) over get_Q_plus_U_new (108-116) on a block held in registers: index of the FIRST maximum.
+// MULTI: Q is taken from the loss-free statistics (in-flight count in META bits 24-30), see k_wave_multi.
+template <bool MULTI>
+__device__ __forceinline__ uint32_t select_child(const BlockRegs &R, int cnt, int parentN, int lane) {
+    const double sq = __dsqrt_rn((double)parentN);
+    double bs = 0.0;
+    uint32_t bi = NONE;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int i = lane + 32 * k;
+        if (i < cnt) {
+            const float P = __uint_as_float(R.P[k]);
+            float W = __uint_as_float(R.W[k]);
+            const int N = (int)R.N[k];
+            int Nr = N;
+            if (MULTI) {
+                const int c = (int)((R.meta[k] >> 24) & 0x7Fu);                       // playouts holding a virtual loss here
+                Nr = N - 3 * c;
+                if (c) W = __fadd_rn(W, (float)(3 * c));
+            }
+            const float Q = Nr > 0 ? __fdiv_rn(W, (float)Nr) : 0.0f;                  // Q = W / N in float32 (of the last real backup)
+            const float p5 = __fmul_rn(5.0f, P);                                      // c_puct * P in float32
+            const double U = __ddiv_rn(__dmul_rn((double)p5, sq), (double)(1 + N));
+            double s = __dadd_rn((double)Q, U);
+            if (i > 0 && s != s) s = -INFINITY;   // a NaN score never displaces an earlier candidate
+            if (k == 0 || s > bs) { bs = s; bi = (uint32_t)i; }
+        }
+    }
+    // warp arg-max, first maximum wins (python max(): strict >)
+    const bool nan0 = __shfl_sync(CZ_FULL, (int)(bs != bs), 0) != 0;   // only lane 0 (i == 0) can hold a NaN
+    if (nan0) return 0;
+    const unsigned long long key = bi == NONE ? 0ull : dkey(__dadd_rn(bs, 0.0));
+    const uint32_t hi = (uint32_t)(key >> 32), lo = (uint32_t)key;
+    const uint32_t mhi = __reduce_max_sync(CZ_FULL, hi);
+    const uint32_t mlo = __reduce_max_sync(CZ_FULL, hi == mhi ? lo : 0u);
+    return __reduce_min_sync(CZ_FULL, (bi != NONE && hi == mhi && lo == mlo) ? bi : NONE);
+}
+
+#define HGET(f) __shfl_sync(CZ_FULL, h, (f))
+#define HSET(f, v) do { if (lane == (f)) h = (uint32_t)(v); } while (0)
 
 // One wave for one game (one warp).  DO_EXPAND: consume the previous evaluation; DO_SELECT: run playouts
 // until the next leaf.
@@ -298,144 +351,189 @@ __global__ void __launch_bounds__(32 * MAX_WPB, 1) k_wave(Dev E, T *nn_in, const
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int g = blockIdx.x * (blockDim.x >> 5) + w;
     if (g >= E.B) return;
-    if (!E.active[g]) return;
     WarpSmem &S = smem[w];
-    uint32_t *ar = arena_of(E, g);
-    int pend = E.pending[g];
-    int done = E.done[g];
+    // ---- round trip 1: everything addressed by g alone ----
+    uint32_t *hp = E.hdr + (size_t)g * HW;
+    uint32_t h = lane < HW ? hp[lane] : 0u;
+    uint32_t lbw = 0, rbw = 0;
+    if (lane < 24) {
+        if (DO_EXPAND) lbw = reinterpret_cast<const uint32_t *>(E.leaf_board + (size_t)g * 96)[lane];
+        if (DO_SELECT) rbw = reinterpret_cast<const uint32_t *>(E.root_board + (size_t)g * 96)[lane];
+    }
+    uint2 pth = make_uint2(0, 0);
+    float val = 0.f;
+    if (DO_EXPAND) { pth = E.path[(size_t)g * MAXD + lane]; val = value[g]; }
+    uint32_t flags = HGET(H_FLAGS);
+    if (!(flags & F_ACTIVE)) return;
+    uint32_t *ar = arena_half(E, g, (flags & F_CUR) ? 1 : 0);
+    int pend = (int)F_PEND(flags);
+    int done = (int)HGET(H_DONE);
+    const int target = (int)HGET(H_TARGET);
+    uint32_t alloc = HGET(H_ALLOC), errf = 0;
+    uint32_t root_base = HGET(H_ROOTBASE);
+    int root_cnt = (int)HGET(H_ROOTCNT);
+    const int root_N = (int)HGET(H_ROOTN);
+    int plen = (int)HGET(H_PLEN);
+    BlockRegs R;
+    bool have_root = false;
 
     if (DO_EXPAND && pend) {
-        const int depth = E.path_len[g];
-        const bool ok = warp_expand(E, g, ar, S, logits, pend, depth, lane);
+        const int depth = pend == 1 ? plen : 0;
+        // ---- round trip 2: the W / N words of the path (back-up operands) fly under the move generation ----
+        uint32_t bW = 0, bN = 0;
+        if (lane < depth && lane < SPATH) { bW = ar[pth.x + PE_CS(pth)]; bN = ar[pth.x + 2 * PE_CS(pth)]; }
+        if (lane < 24) reinterpret_cast<uint32_t *>(S.board)[lane] = lbw;
+        __syncwarp();
+        uint32_t base;
+        const int n = expand_reserve(E, S, alloc, base, errf, lane);
+        const bool ok = n > 0;
         if (pend == 1) {
             // leaf returns -v (main.py:384); on an engine error the playout is closed with 0
-            const float v = ok ? -value[g] : 0.0f;
-            warp_backup(E, g, ar, depth, v, lane);
-            done++;
-            if (lane == 0) E.cnt_playout[g] += 1;
-        }
-        if (!ok && pend == 2) { if (lane == 0) { E.active[g] = 0; E.pending[g] = 0; } return; }
-        pend = 0;
-        if (lane == 0) { E.pending[g] = 0; E.done[g] = done; }
-    }
-    if (!DO_SELECT || pend) return;
-
-    const int target = E.target[g];
-    const int side0 = E.side[g], rr0 = E.rr[g];
-    const uint32_t *rb = reinterpret_cast<const uint32_t *>(E.root_board + (size_t)g * 96);
-
-    if (E.root_cnt[g] < 0) {
-        // MCTS_tree.main: expand the root first (main.py:475-487); not a playout
-        if (lane < 24) reinterpret_cast<uint32_t *>(S.board)[lane] = rb[lane];
-        __syncwarp();
-        store_leaf<T>(E, g, S, side0, nn_in, lane);
-        if (lane == 0) { E.pending[g] = 2; E.path_len[g] = 0; }
-        return;
-    }
-    unsigned long long accL = 0, accC = 0;
-    int maxdep = 0;
-    // Terminal playouts are resolved here without the network.  A position with a king capture at the root sends
-    // nearly all of its playouts down that edge; bounding the number resolved per launch keeps one such game from
-    // stretching the wave for the other games (it simply continues in the next wave; per-game order is unchanged).
-    int budget = MAX_INKERNEL_PLAYOUTS;
-    while (done < target && budget-- > 0) {
-        // ---- one playout of start_tree_search (main.py:350-440) ----
-        if (lane < 24) reinterpret_cast<uint32_t *>(S.board)[lane] = rb[lane];
-        __syncwarp();
-        int side = side0, rr = rr0, depth = 0;
-        uint32_t base = E.root_base[g];
-        int cnt = E.root_cnt[g];
-        int parentN = E.root_N[g];
-        bool leaf = false, fault = false;
-        float tval = 0.0f;
-        for (;;) {
-            if (cnt <= 0 || depth >= MAXD) {
-                if (lane == 0) atomicOr(E.err + g, cnt <= 0 ? CZ_ERR_NOMOVES : CZ_ERR_DEPTH);
-                fault = true;
-                break;
+            const float v = ok ? -val : 0.0f;
+            if (lane < depth && lane < SPATH) backup_edge(ar, pth, lane, depth, v, bW, bN, false);
+            for (int d = SPATH + lane; d < depth; d += 32) {          // (paths longer than the prefetch window)
+                const uint2 pe = E.path[(size_t)g * MAXD + d];
+                backup_edge(ar, pe, d, depth, v, ar[pe.x + PE_CS(pe)], ar[pe.x + 2 * PE_CS(pe)], false);
             }
-            const uint32_t cs = (uint32_t)((cnt + 7) & ~7);
-            const uint32_t *blk = ar + base + HDR;
-            // select_new (main.py:158-159) over get_Q_plus_U_new (108-116)
-            const double sq = __dsqrt_rn((double)parentN);
-            double bs = 0.0;
-            uint32_t bi = NONE, bmeta = 0, bchild = NONE;
-            float bW = 0.f;
-            int bN = 0;
+            done++;
+            if (lane == 0) atomicAdd(E.cnt_playout + g, 1ull);
+        }
+        __syncwarp();
+        if (!ok && pend == 2) {      // the root could not be expanded: the game leaves the search
+            HSET(H_FLAGS, F_SETPEND(flags & ~F_ACTIVE, 0));
+            if (lane == H_ERR) h |= errf;
+            if (lane < HW) hp[lane] = h;
+            return;
+        }
+        // ---- round trip 3 (root block of the next descent) is requested BEFORE the logit gather (round trip 4) ----
+        if (DO_SELECT && pend == 1 && done < target) { load_block(ar, root_base, root_cnt, lane, R); have_root = true; }
+        if (ok) {
+            expand_write(ar, S, logits + (size_t)g * CZ_NLABEL, n, base, lane);
+            if (pend == 2) { root_base = base; root_cnt = n; }
+            else {
+                uint2 last;
+                if (depth - 1 < SPATH) { last.x = __shfl_sync(CZ_FULL, pth.x, depth - 1); last.y = __shfl_sync(CZ_FULL, pth.y, depth - 1); }
+                else last = E.path[(size_t)g * MAXD + depth - 1];
+                if (lane == 0) expand_link(ar, last, n, base, 0);
+                if (have_root && depth == 1) {        // the new node hangs under the root: patch the prefetched copy of that edge
+                    const uint32_t e = last.x - (root_base + HDR);
+                    if (lane == (int)(e & 31)) {
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const int i = lane + 32 * k;
-                if (i < cnt) {
-                    const float P = __uint_as_float(blk[i]);
-                    const float W = __uint_as_float(blk[cs + i]);
-                    const int N = (int)blk[2 * cs + i];
-                    const uint32_t meta = blk[3 * cs + i], child = blk[4 * cs + i];
-                    const float Q = N > 0 ? __fdiv_rn(W, (float)N) : 0.0f;           // Q = W / N in float32
-                    const float p5 = __fmul_rn(5.0f, P);                              // c_puct * P in float32
-                    const double U = __ddiv_rn(__dmul_rn((double)p5, sq), (double)(1 + N));
-                    double s = __dadd_rn((double)Q, U);
-                    if (i > 0 && s != s) s = -INFINITY;   // a NaN score never displaces an earlier candidate
-                    if (k == 0 || s > bs) { bs = s; bi = (uint32_t)i; bmeta = meta; bchild = child; bW = W; bN = N; }
+                        for (int k = 0; k < 4; k++)
+                            if (k == (int)(e >> 5)) { R.meta[k] = PE_MOVE(last) | ((uint32_t)n << 16); R.child[k] = base; }
+                    }
                 }
             }
-            // warp arg-max, first maximum wins (python max(): strict >)
-            const bool nan0 = __shfl_sync(CZ_FULL, (int)(bs != bs), 0) != 0;   // only lane 0 (i == 0) can hold a NaN
-            uint32_t e;
-            if (nan0) e = 0;
-            else {
-                const unsigned long long key = bi == NONE ? 0ull : dkey(__dadd_rn(bs, 0.0));
-                const uint32_t hi = (uint32_t)(key >> 32), lo = (uint32_t)key;
-                const uint32_t mhi = __reduce_max_sync(CZ_FULL, hi);
-                const uint32_t mlo = __reduce_max_sync(CZ_FULL, hi == mhi ? lo : 0u);
-                e = __reduce_min_sync(CZ_FULL, (bi != NONE && hi == mhi && lo == mlo) ? bi : NONE);
-            }
-            const int owner = e & 31;
-            const uint32_t meta = __shfl_sync(CZ_FULL, bmeta, owner);
-            const uint32_t child = __shfl_sync(CZ_FULL, bchild, owner);
-            const int eN = __shfl_sync(CZ_FULL, bN, owner);
-            if (lane == owner) {  // virtual loss (main.py:403-404)
-                const_cast<uint32_t *>(blk)[cs + e] = __float_as_uint(__fadd_rn(bW, -3.0f));
-                const_cast<uint32_t *>(blk)[2 * cs + e] = (uint32_t)(bN + 3);
-            }
-            if (lane == 0) E.path[(size_t)g * MAXD + depth] = make_uint2(base + HDR + e, cs);
-            depth++;
-            accL += 1; accC += (unsigned)cnt;
-            const int src = meta & 127, dst = (meta >> 7) & 127;
-            const int cap = S.board[dst];
-            __syncwarp();
-            if (lane == 0) { S.board[dst] = S.board[src]; S.board[src] = 0; }
-            __syncwarp();
-            side ^= 1;                                   // main.py:392
-            rr = cap == 0 ? rr + 1 : 0;                  // is_kill_move, main.py:393-396
-            if (cap == 1 || cap == 8) {                  // king captured: main.py:409-414
-                float v = cap == 1 ? (side == 1 ? 1.0f : -1.0f) : (side == 1 ? -1.0f : 1.0f);
-                tval = -v;
-                break;
-            }
-            if (rr >= 60) { tval = 0.0f; break; }        // main.py:415-416
-            if (child == NONE) { leaf = true; break; }   // main.py:357: not expanded -> evaluate
-            base = child;
-            cnt = (int)((meta >> 16) & 0xFFu);
-            parentN = eN + 3;                            // the child's N carries the virtual loss just added
+            if (lane == 0) { atomicAdd(E.cnt_expand + g, 1ull); atomicAdd(E.cnt_C + g, (unsigned long long)n); }
         }
-        if (depth > maxdep) maxdep = depth;
-        if (leaf) {
-            store_leaf<T>(E, g, S, side, nn_in, lane);
-            if (lane == 0) { E.pending[g] = 1; E.path_len[g] = depth; }
-            break;
-        }
+        pend = 0;
         __syncwarp();
-        warp_backup(E, g, ar, depth, tval, lane);       // also unwinds the VL of a faulted path
-        done++;
-        if (lane == 0) E.cnt_playout[g] += 1;
-        if (fault) break;
     }
-    if (lane == 0) {
-        E.done[g] = done;
-        E.cnt_L[g] += accL;
-        E.cnt_c[g] += accC;
-        if (maxdep > E.max_depth[g]) E.max_depth[g] = maxdep;
+
+    uint32_t maxdep = HGET(H_MAXDEPTH);
+    if (DO_SELECT && !pend) {
+        const int side0 = (flags & F_SIDE) ? 1 : 0, rr0 = (int)HGET(H_RR);
+        unsigned long long rhash = 0;
+        if (E.hash_on) rhash = (unsigned long long)HGET(H_HASHLO) | ((unsigned long long)HGET(H_HASHHI) << 32);
+        if (root_cnt < 0) {
+            // MCTS_tree.main: expand the root first (main.py:475-487); not a playout
+            if (lane < 24) reinterpret_cast<uint32_t *>(S.board)[lane] = rbw;
+            __syncwarp();
+            store_leaf_at<T>(E.leaf_board + (size_t)g * 96, S, side0, nn_in, (size_t)g, lane);
+            if (E.hash_on && lane == 0) E.leaf_hash[g] = rhash;
+            pend = 2; plen = 0;
+        } else {
+            unsigned long long accL = 0, accC = 0;
+            // Terminal playouts are resolved here without the network.  A position with a king capture at the root sends
+            // nearly all of its playouts down that edge; bounding the number resolved per launch keeps one such game from
+            // stretching the wave for the other games (it simply continues in the next wave; per-game order is unchanged).
+            int budget = MAX_INKERNEL_PLAYOUTS;
+            while (done < target && budget-- > 0) {
+                // ---- one playout of start_tree_search (main.py:350-440) ----
+                if (lane < 24) reinterpret_cast<uint32_t *>(S.board)[lane] = rbw;
+                __syncwarp();
+                int side = side0, rr = rr0, depth = 0;
+                uint32_t base = root_base;
+                int cnt = root_cnt;
+                int parentN = root_N;
+                unsigned long long hash = rhash;
+                bool leaf = false, fault = false;
+                float tval = 0.0f;
+                if (!have_root) load_block(ar, base, cnt, lane, R);
+                have_root = false;
+                for (;;) {
+                    if (cnt <= 0 || depth >= MAXD) {
+                        errf |= cnt <= 0 ? CZ_ERR_NOMOVES : CZ_ERR_DEPTH;
+                        fault = true;
+                        break;
+                    }
+                    const uint32_t cs = (uint32_t)((cnt + 7) & ~7);
+                    uint32_t *blk = ar + base + HDR;
+                    const uint32_t e = select_child<false>(R, cnt, parentN, lane);
+                    const int owner = e & 31, ke = (int)(e >> 5);
+                    const uint32_t meta = __shfl_sync(CZ_FULL, pick(R.meta, ke), owner);
+                    const uint32_t child = __shfl_sync(CZ_FULL, pick(R.child, ke), owner);
+                    const int eN = (int)__shfl_sync(CZ_FULL, pick(R.N, ke), owner);
+                    if (lane == owner) {  // virtual loss (main.py:403-404)
+                        blk[cs + e] = __float_as_uint(__fadd_rn(__uint_as_float(pick(R.W, ke)), -3.0f));
+                        blk[2 * cs + e] = (uint32_t)(eN + 3);
+                    }
+                    if (lane == 0) {
+                        const uint2 pe = path_entry(base + HDR + e, cs, meta & 0xFFFFu);
+                        E.path[(size_t)g * MAXD + depth] = pe;
+                        if (depth < SPATH) S.path[depth] = pe;
+                    }
+                    depth++;
+                    accL += 1; accC += (unsigned)cnt;
+                    const int src = meta & 127, dst = (meta >> 7) & 127;
+                    const int cap = S.board[dst], mover = S.board[src];
+                    __syncwarp();
+                    if (lane == 0) { S.board[dst] = (uint8_t)mover; S.board[src] = 0; }
+                    __syncwarp();
+                    if (E.hash_on) hash ^= zob_move(E.zob, mover, cap, src, dst);
+                    side ^= 1;                                   // main.py:392
+                    rr = cap == 0 ? rr + 1 : 0;                  // is_kill_move, main.py:393-396
+                    if (cap == 1 || cap == 8) {                  // king captured: main.py:409-414
+                        const float v = cap == 1 ? (side == 1 ? 1.0f : -1.0f) : (side == 1 ? -1.0f : 1.0f);
+                        tval = -v;
+                        break;
+                    }
+                    if (rr >= 60) { tval = 0.0f; break; }        // main.py:415-416
+                    if (child == NONE) { leaf = true; break; }   // main.py:357: not expanded -> evaluate
+                    base = child;
+                    cnt = (int)((meta >> 16) & 0xFFu);
+                    parentN = eN + 3;                            // the child's N carries the virtual loss just added
+                    load_block(ar, base, cnt, lane, R);          // one round trip per level: the pointer chase itself
+                }
+                if ((uint32_t)depth > maxdep) maxdep = (uint32_t)depth;
+                if (leaf) {
+                    store_leaf_at<T>(E.leaf_board + (size_t)g * 96, S, side, nn_in, (size_t)g, lane);
+                    if (E.hash_on && lane == 0) E.leaf_hash[g] = hash;
+                    pend = 1; plen = depth;
+                    break;
+                }
+                __syncwarp();
+                // terminal (or faulted) playout: VL undo + backup, also from the shared-memory mirror of the path
+                warp_backup_path(depth <= SPATH ? S.path : E.path + (size_t)g * MAXD, ar, depth, tval, lane, false);
+                done++;
+                if (lane == 0) atomicAdd(E.cnt_playout + g, 1ull);
+                if (fault) break;
+            }
+            if (lane == 0 && accL) { atomicAdd(E.cnt_L + g, accL); atomicAdd(E.cnt_c + g, accC); }
+        }
     }
+    if (DO_SELECT && E.hash_on && pend == 0 && lane == 0) E.leaf_hash[g] = 0ull;    // no leaf of this game in the batch
+    // ---- the header line goes back with one coalesced store ----
+    HSET(H_FLAGS, F_SETPEND(flags, pend));
+    HSET(H_DONE, done);
+    HSET(H_ALLOC, alloc);
+    HSET(H_PLEN, plen);
+    HSET(H_ROOTBASE, root_base);
+    HSET(H_ROOTCNT, root_cnt);
+    HSET(H_MAXDEPTH, maxdep);
+    if (lane == H_MAXALLOC && alloc > h) h = alloc;
+    if (lane == H_ERR) h |= errf;
+    if (lane < HW) hp[lane] = h;
 }
 
 __constant__ uint8_t c_start[96];   // start position, uploaded by cz_engine_create
@@ -454,185 +552,160 @@ __global__ void __launch_bounds__(32 * MAX_WPB, 1) k_wave_multi(Dev E, T *nn_in,
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int g = blockIdx.x * (blockDim.x >> 5) + w;
     if (g >= E.B) return;
-    if (!E.active[g]) return;
     WarpSmem &S = smem[w];
-    uint32_t *ar = arena_of(E, g);
+    uint32_t *hp = E.hdr + (size_t)g * HW;
+    uint32_t h = lane < HW ? hp[lane] : 0u;
+    uint32_t rbw = lane < 24 ? reinterpret_cast<const uint32_t *>(E.root_board + (size_t)g * 96)[lane] : 0u;
+    uint32_t flags = HGET(H_FLAGS);
+    if (!(flags & F_ACTIVE)) return;
+    uint32_t *ar = arena_half(E, g, (flags & F_CUR) ? 1 : 0);
     const int K = E.K;
-    int done = E.done[g];
+    int done = (int)HGET(H_DONE);
+    const int target = (int)HGET(H_TARGET);
+    uint32_t alloc = HGET(H_ALLOC), errf = 0, maxdep = HGET(H_MAXDEPTH);
+    uint32_t root_base = HGET(H_ROOTBASE);
+    int root_cnt = (int)HGET(H_ROOTCNT);
+    const int root_N = (int)HGET(H_ROOTN);
+    const int side0 = (flags & F_SIDE) ? 1 : 0, rr0 = (int)HGET(H_RR);
+    unsigned long long rhash = 0;
+    if (E.hash_on) rhash = (unsigned long long)HGET(H_HASHLO) | ((unsigned long long)HGET(H_HASHHI) << 32);
+    bool dead = false;
 
     // ---- phase 1: consume the evaluations of the previous wave, slot by slot ----
-    for (int s = 0; s < K; s++) {
+    for (int s = 0; s < K && !dead; s++) {
         const size_t idx = (size_t)g * K + s;
         const int pend = E.pendK[idx];
         if (!pend) continue;
         const int depth = E.plenK[idx];
         const uint2 *path = E.pathK + idx * MAXD;
-        const bool ok = warp_expand_at(E, g, ar, S, logits + idx * CZ_NLABEL, pend, path, depth, E.leafK + idx * 96, false, lane);
+        if (lane < 24) reinterpret_cast<uint32_t *>(S.board)[lane] = reinterpret_cast<const uint32_t *>(E.leafK + idx * 96)[lane];
+        __syncwarp();
+        uint32_t base;
+        const int n = expand_reserve(E, S, alloc, base, errf, lane);
+        const bool ok = n > 0;
+        if (ok) {
+            expand_write(ar, S, logits + idx * CZ_NLABEL, n, base, lane);
+            if (pend == 2) { root_base = base; root_cnt = n; }
+            else if (lane == 0) expand_link(ar, path[depth - 1], n, base, 1u);    // exactly one playout (ours) holds a loss on a claimed edge
+            if (lane == 0) { atomicAdd(E.cnt_expand + g, 1ull); atomicAdd(E.cnt_C + g, (unsigned long long)n); }
+        }
+        __syncwarp();
         if (pend == 1) {
             warp_backup_path(path, ar, depth, ok ? -value[idx] : 0.0f, lane, true);
             done++;
-            if (lane == 0) E.cnt_playout[g] += 1;
+            if (lane == 0) atomicAdd(E.cnt_playout + g, 1ull);
         }
         if (lane == 0) E.pendK[idx] = 0;
-        if (!ok && pend == 2) { if (lane == 0) E.active[g] = 0; return; }
+        if (!ok && pend == 2) { flags &= ~F_ACTIVE; dead = true; }
         __syncwarp();
     }
-    if (lane == 0) E.done[g] = done;
 
-    const int target = E.target[g];
-    const int side0 = E.side[g], rr0 = E.rr[g];
-    const uint32_t *rb = reinterpret_cast<const uint32_t *>(E.root_board + (size_t)g * 96);
-    if (E.root_cnt[g] < 0) {   // root expansion first (main.py:475-487), one slot
-        if (lane < 24) reinterpret_cast<uint32_t *>(S.board)[lane] = rb[lane];
+    if (!dead && root_cnt < 0) {   // root expansion first (main.py:475-487), one slot
+        if (lane < 24) reinterpret_cast<uint32_t *>(S.board)[lane] = rbw;
         __syncwarp();
         store_leaf_at<T>(E.leafK + (size_t)g * K * 96, S, side0, nn_in, (size_t)g * K, lane);
-        if (lane == 0) { E.pendK[(size_t)g * K] = 2; E.plenK[(size_t)g * K] = 0; }
-        return;
-    }
-
-    // ---- phase 2: up to K descents with virtual loss ----
-    unsigned long long accL = 0, accC = 0;
-    int maxdep = 0, inflight = 0, budget = MAX_INKERNEL_PLAYOUTS + K;
-    bool stop = false;
-    for (int s = 0; s < K && !stop; s++) {
-        const size_t idx = (size_t)g * K + s;
-        uint2 *path = E.pathK + idx * MAXD;
-        while (done + inflight < target && budget-- > 0) {
-            if (lane < 24) reinterpret_cast<uint32_t *>(S.board)[lane] = rb[lane];
-            __syncwarp();
-            int side = side0, rr = rr0, depth = 0;
-            uint32_t base = E.root_base[g];
-            int cnt = E.root_cnt[g];
-            int parentN = E.root_N[g];
-            int outcome = 0;   // 1 leaf, 2 terminal, 3 collision, 4 fault
-            float tval = 0.0f;
-            for (;;) {
-                if (cnt <= 0 || depth >= MAXD) {
-                    if (lane == 0) atomicOr(E.err + g, cnt <= 0 ? CZ_ERR_NOMOVES : CZ_ERR_DEPTH);
-                    outcome = 4;
-                    break;
-                }
-                const uint32_t cs = (uint32_t)((cnt + 7) & ~7);
-                uint32_t *blk = ar + base + HDR;
-                const double sq = __dsqrt_rn((double)parentN);
-                double bs = 0.0;
-                uint32_t bi = NONE, bmeta = 0, bchild = NONE;
-                float bW = 0.f;
-                int bN = 0;
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const int i = lane + 32 * k;
-                    if (i < cnt) {
-                        const float P = __uint_as_float(blk[i]);
-                        const float W = __uint_as_float(blk[cs + i]);
-                        const int N = (int)blk[2 * cs + i];
-                        const uint32_t meta = blk[3 * cs + i], child = blk[4 * cs + i];
-                        const int c = (int)((meta >> 24) & 0x7Fu);                       // playouts holding a virtual loss here
-                        const int Nr = N - 3 * c;
-                        const float Wr = c ? __fadd_rn(W, (float)(3 * c)) : W;
-                        const float Q = Nr > 0 ? __fdiv_rn(Wr, (float)Nr) : 0.0f;          // Q of the last real backup
-                        const float p5 = __fmul_rn(5.0f, P);
-                        const double U = __ddiv_rn(__dmul_rn((double)p5, sq), (double)(1 + N));
-                        double sc = __dadd_rn((double)Q, U);
-                        if (i > 0 && sc != sc) sc = -INFINITY;
-                        if (k == 0 || sc > bs) { bs = sc; bi = (uint32_t)i; bmeta = meta; bchild = child; bW = W; bN = N; }
+        if (lane == 0) { E.pendK[(size_t)g * K] = 2; E.plenK[(size_t)g * K] = 0; if (E.hash_on) E.leaf_hash[(size_t)g * K] = rhash; }
+    } else if (!dead) {
+        // ---- phase 2: up to K descents with virtual loss ----
+        unsigned long long accL = 0, accC = 0;
+        int inflight = 0, budget = MAX_INKERNEL_PLAYOUTS + K;
+        bool stop = false;
+        BlockRegs R;
+        for (int s = 0; s < K && !stop; s++) {
+            const size_t idx = (size_t)g * K + s;
+            uint2 *path = E.pathK + idx * MAXD;
+            while (done + inflight < target && budget-- > 0) {
+                if (lane < 24) reinterpret_cast<uint32_t *>(S.board)[lane] = rbw;
+                __syncwarp();
+                int side = side0, rr = rr0, depth = 0;
+                uint32_t base = root_base;
+                int cnt = root_cnt;
+                int parentN = root_N;
+                unsigned long long hash = rhash;
+                int outcome = 0;   // 1 leaf, 2 terminal, 3 collision, 4 fault
+                float tval = 0.0f;
+                for (;;) {
+                    if (cnt <= 0 || depth >= MAXD) {
+                        errf |= cnt <= 0 ? CZ_ERR_NOMOVES : CZ_ERR_DEPTH;
+                        outcome = 4;
+                        break;
                     }
+                    const uint32_t cs = (uint32_t)((cnt + 7) & ~7);
+                    uint32_t *blk = ar + base + HDR;
+                    load_block(ar, base, cnt, lane, R);
+                    const uint32_t e = select_child<true>(R, cnt, parentN, lane);
+                    const int owner = e & 31, ke = (int)(e >> 5);
+                    const uint32_t meta = __shfl_sync(CZ_FULL, pick(R.meta, ke), owner);
+                    const uint32_t child = __shfl_sync(CZ_FULL, pick(R.child, ke), owner);
+                    const int eN = (int)__shfl_sync(CZ_FULL, pick(R.N, ke), owner);
+                    const bool claimed = (meta & 0x80000000u) != 0;
+                    const int src = meta & 127, dst = (meta >> 7) & 127;
+                    const int cap = S.board[dst], mover = S.board[src];
+                    const bool term = cap == 1 || cap == 8 || (cap == 0 ? rr + 1 : 0) >= 60;
+                    if (child == NONE && claimed && !term) { outcome = 3; break; }     // someone else is evaluating this leaf
+                    if (lane == owner) {  // virtual loss + in-flight count (+ claim when this becomes our leaf)
+                        blk[cs + e] = __float_as_uint(__fadd_rn(__uint_as_float(pick(R.W, ke)), -3.0f));
+                        blk[2 * cs + e] = (uint32_t)(eN + 3);
+                        blk[3 * cs + e] = (meta + (1u << 24)) | ((child == NONE && !term) ? 0x80000000u : 0u);
+                    }
+                    if (lane == 0) path[depth] = path_entry(base + HDR + e, cs, meta & 0xFFFFu);
+                    depth++;
+                    accL += 1; accC += (unsigned)cnt;
+                    __syncwarp();
+                    if (lane == 0) { S.board[dst] = (uint8_t)mover; S.board[src] = 0; }
+                    __syncwarp();
+                    if (E.hash_on) hash ^= zob_move(E.zob, mover, cap, src, dst);
+                    side ^= 1;
+                    rr = cap == 0 ? rr + 1 : 0;
+                    if (cap == 1 || cap == 8) {
+                        const float v = cap == 1 ? (side == 1 ? 1.0f : -1.0f) : (side == 1 ? -1.0f : 1.0f);
+                        tval = -v; outcome = 2;
+                        break;
+                    }
+                    if (rr >= 60) { tval = 0.0f; outcome = 2; break; }
+                    if (child == NONE) { outcome = 1; break; }
+                    base = child;
+                    cnt = (int)((meta >> 16) & 0xFFu);
+                    parentN = eN + 3;
                 }
-                const bool nan0 = __shfl_sync(CZ_FULL, (int)(bs != bs), 0) != 0;
-                uint32_t e;
-                if (nan0) e = 0;
-                else {
-                    const unsigned long long key = bi == NONE ? 0ull : dkey(__dadd_rn(bs, 0.0));
-                    const uint32_t hi = (uint32_t)(key >> 32), lo = (uint32_t)key;
-                    const uint32_t mhi = __reduce_max_sync(CZ_FULL, hi);
-                    const uint32_t mlo = __reduce_max_sync(CZ_FULL, hi == mhi ? lo : 0u);
-                    e = __reduce_min_sync(CZ_FULL, (bi != NONE && hi == mhi && lo == mlo) ? bi : NONE);
-                }
-                const int owner = e & 31;
-                const uint32_t meta = __shfl_sync(CZ_FULL, bmeta, owner);
-                const uint32_t child = __shfl_sync(CZ_FULL, bchild, owner);
-                const int eN = __shfl_sync(CZ_FULL, bN, owner);
-                const bool claimed = (meta & 0x80000000u) != 0;
-                const int src = meta & 127, dst = (meta >> 7) & 127;
-                const int cap = S.board[dst];
-                const bool term = cap == 1 || cap == 8 || (cap == 0 ? rr + 1 : 0) >= 60;
-                if (child == NONE && claimed && !term) { outcome = 3; break; }     // someone else is evaluating this leaf
-                if (lane == owner) {  // virtual loss + in-flight count (+ claim when this becomes our leaf)
-                    blk[cs + e] = __float_as_uint(__fadd_rn(bW, -3.0f));
-                    blk[2 * cs + e] = (uint32_t)(bN + 3);
-                    blk[3 * cs + e] = (bmeta + (1u << 24)) | ((child == NONE && !term) ? 0x80000000u : 0u);
-                }
-                if (lane == 0) path[depth] = make_uint2(base + HDR + e, cs);
-                depth++;
-                accL += 1; accC += (unsigned)cnt;
+                if ((uint32_t)depth > maxdep) maxdep = (uint32_t)depth;
                 __syncwarp();
-                if (lane == 0) { S.board[dst] = S.board[src]; S.board[src] = 0; }
-                __syncwarp();
-                side ^= 1;
-                rr = cap == 0 ? rr + 1 : 0;
-                if (cap == 1 || cap == 8) {
-                    const float v = cap == 1 ? (side == 1 ? 1.0f : -1.0f) : (side == 1 ? -1.0f : 1.0f);
-                    tval = -v; outcome = 2;
+                if (outcome == 1) {
+                    store_leaf_at<T>(E.leafK + idx * 96, S, side, nn_in, idx, lane);
+                    if (lane == 0) { E.pendK[idx] = 1; E.plenK[idx] = depth; if (E.hash_on) E.leaf_hash[idx] = hash; }
+                    inflight++;
+                    break;                                   // next slot
+                }
+                if (outcome == 3) {                          // back off: take the virtual losses of this partial path back
+                    for (int d = lane; d < depth; d += 32) {
+                        const uint2 pe = path[d];
+                        const uint32_t cs = PE_CS(pe);
+                        ar[pe.x + cs] = __float_as_uint(__fadd_rn(__uint_as_float(ar[pe.x + cs]), 3.0f));
+                        ar[pe.x + 2 * cs] -= 3u;
+                        ar[pe.x + 3 * cs] -= (1u << 24);
+                    }
+                    __syncwarp();
+                    stop = true;
                     break;
                 }
-                if (rr >= 60) { tval = 0.0f; outcome = 2; break; }
-                if (child == NONE) { outcome = 1; break; }
-                base = child;
-                cnt = (int)((meta >> 16) & 0xFFu);
-                parentN = eN + 3;
+                warp_backup_path(path, ar, depth, tval, lane, true);   // terminal (or faulted) playout
+                done++;
+                if (lane == 0) atomicAdd(E.cnt_playout + g, 1ull);
+                if (outcome == 4) { stop = true; break; }
             }
-            if (depth > maxdep) maxdep = depth;
-            __syncwarp();
-            if (outcome == 1) {
-                store_leaf_at<T>(E.leafK + idx * 96, S, side, nn_in, idx, lane);
-                if (lane == 0) { E.pendK[idx] = 1; E.plenK[idx] = depth; }
-                inflight++;
-                break;                                   // next slot
-            }
-            if (outcome == 3) {                          // back off: take the virtual losses of this partial path back
-                for (int d = lane; d < depth; d += 32) {
-                    const uint2 pe = path[d];
-                    ar[pe.x + pe.y] = __float_as_uint(__fadd_rn(__uint_as_float(ar[pe.x + pe.y]), 3.0f));
-                    ar[pe.x + 2 * pe.y] -= 3u;
-                    ar[pe.x + 3 * pe.y] -= (1u << 24);
-                }
-                __syncwarp();
-                stop = true;
-                break;
-            }
-            warp_backup_path(path, ar, depth, tval, lane, true);   // terminal (or faulted) playout
-            done++;
-            if (lane == 0) E.cnt_playout[g] += 1;
-            if (outcome == 4) { stop = true; break; }
+            if (!(done + inflight < target)) break;
         }
-        if (!(done + inflight < target)) break;
+        if (lane == 0 && accL) { atomicAdd(E.cnt_L + g, accL); atomicAdd(E.cnt_c + g, accC); }
     }
-    if (lane == 0) {
-        E.done[g] = done;
-        E.cnt_L[g] += accL;
-        E.cnt_c[g] += accC;
-        if (maxdep > E.max_depth[g]) E.max_depth[g] = maxdep;
-    }
-}
-
-// ---- move generation of the pending leaves, off the critical path -------------------------------------------
-// Runs on a side stream underneath the network evaluation of the same leaves: the next k_wave then only gathers
-// the logits.  Same device functions as the in-wave path, so the result is identical by construction.
-__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_prepare_leaves(Dev E) {
-    __shared__ WarpSmem smem[WARPS_PER_BLOCK];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = blockIdx.x * WARPS_PER_BLOCK + w;
-    if (g >= E.B || !E.active[g] || !E.pending[g] || E.leaf_n[g] >= 0) return;
-    WarpSmem &S = smem[w];
-    uint32_t errf = 0;
-    const int n = warp_leaf_moves(E, g, S, errf, lane);
-    errf = __reduce_or_sync(CZ_FULL, errf);
-    if (errf && lane == 0) atomicOr(E.err + g, errf);
-    for (int i = lane; i < n; i += 32) {
-        E.leaf_moves[(size_t)g * CZ_MAXCHILD + i] = S.moves[i];
-        E.leaf_li[(size_t)g * CZ_MAXCHILD + i] = S.li[i];
-    }
-    __syncwarp();
-    if (lane == 0) E.leaf_n[g] = n;
+    HSET(H_FLAGS, flags);
+    HSET(H_DONE, done);
+    HSET(H_ALLOC, alloc);
+    HSET(H_ROOTBASE, root_base);
+    HSET(H_ROOTCNT, root_cnt);
+    HSET(H_MAXDEPTH, maxdep);
+    if (lane == H_MAXALLOC && alloc > h) h = alloc;
+    if (lane == H_ERR) h |= errf;
+    if (lane < HW) hp[lane] = h;
 }
 
 // ---- GameBoard.reload + MCTS_tree.reload -------------------------------------------------
@@ -642,46 +715,53 @@ __global__ void k_reset(Dev E, const uint8_t *mask, const uint8_t *boards, const
     uint8_t *b = E.root_board + (size_t)g * 96;
     for (int i = 0; i < 90; i++) b[i] = boards ? boards[(size_t)g * 90 + i] : c_start[i];
     for (int i = 90; i < 96; i++) b[i] = 0;
-    E.side[g] = sides ? sides[g] : 0;
-    E.rr[g] = rr ? rr[g] : 0;
-    E.ply[g] = 0;
-    E.root_N[g] = 0;
-    E.root_cnt[g] = -1;
-    E.root_base[g] = 0;
-    E.done[g] = 0;
-    E.target[g] = 0;
-    E.pending[g] = 0;
-    E.active[g] = 0;
-    E.path_len[g] = 0;
+    const int side = sides ? (sides[g] ? 1 : 0) : 0;
+    uint32_t *h = E.hdr + (size_t)g * HW;
+    const unsigned long long z = zob_board(E.zob, b, side);
+    const uint32_t keep_err = h[H_ERR], keep_ma = h[H_MAXALLOC], keep_md = h[H_MAXDEPTH];
+    for (int i = 0; i < HW; i++) h[i] = 0;
+    h[H_FLAGS] = side ? F_SIDE : 0u;
+    h[H_RR] = (uint32_t)(rr ? rr[g] : 0);
+    h[H_ROOTCNT] = (uint32_t)-1;
+    h[H_HASHLO] = (uint32_t)z; h[H_HASHHI] = (uint32_t)(z >> 32);
+    h[H_ERR] = keep_err; h[H_MAXALLOC] = keep_ma; h[H_MAXDEPTH] = keep_md;      // diagnostics live for the engine's lifetime
     if (E.pendK) for (int s = 0; s < E.K; s++) E.pendK[(size_t)g * E.K + s] = 0;
-    E.leaf_n[g] = -1;
-    E.alloc[g] = 0;
-    E.terminal[g] = 0;
-    E.winner[g] = -1;
 }
 
 __global__ void k_set_meta(Dev E, const uint8_t *mask, const uint8_t *sides, const int32_t *rr) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= E.B || (mask && !mask[g])) return;
-    if (sides) E.side[g] = sides[g];
-    if (rr) E.rr[g] = rr[g];
+    uint32_t *h = E.hdr + (size_t)g * HW;
+    if (sides) {
+        const int side = sides[g] ? 1 : 0;
+        h[H_FLAGS] = (h[H_FLAGS] & ~F_SIDE) | (side ? F_SIDE : 0u);
+        const unsigned long long z = zob_board(E.zob, E.root_board + (size_t)g * 96, side);
+        h[H_HASHLO] = (uint32_t)z; h[H_HASHHI] = (uint32_t)(z >> 32);
+    }
+    if (rr) h[H_RR] = (uint32_t)rr[g];
 }
 
 __global__ void k_begin(Dev E, const uint8_t *mask, int playouts) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= E.B) return;
-    if (mask ? !mask[g] : E.terminal[g] != 0) return;
-    E.done[g] = 0;
-    E.target[g] = playouts;
-    E.active[g] = 1;
+    uint32_t *h = E.hdr + (size_t)g * HW;
+    const uint32_t f = h[H_FLAGS];
+    if (mask ? !mask[g] : F_TERM(f) != 0) return;
+    h[H_DONE] = 0;
+    h[H_TARGET] = (uint32_t)playouts;
+    h[H_FLAGS] = f | F_ACTIVE;
 }
 
 __global__ void k_unfinished(Dev E, int32_t *out) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     int u = 0;
-    if (g < E.B && E.active[g]) {
-        u = (E.pending[g] || E.root_cnt[g] < 0 || E.done[g] < E.target[g]) ? 1 : 0;
-        if (E.pendK) for (int s = 0; s < E.K; s++) u |= E.pendK[(size_t)g * E.K + s] ? 1 : 0;
+    if (g < E.B) {
+        const uint32_t *h = E.hdr + (size_t)g * HW;
+        const uint32_t f = h[H_FLAGS];
+        if (f & F_ACTIVE) {
+            u = (F_PEND(f) || (int)h[H_ROOTCNT] < 0 || (int)h[H_DONE] < (int)h[H_TARGET]) ? 1 : 0;
+            if (E.pendK) for (int s = 0; s < E.K; s++) u |= E.pendK[(size_t)g * E.K + s] ? 1 : 0;
+        }
     }
     u = __reduce_add_sync(CZ_FULL, u);
     if ((threadIdx.x & 31) == 0 && u) atomicAdd(out, u);
@@ -691,11 +771,12 @@ __global__ void k_unfinished(Dev E, int32_t *out) {
 __global__ void k_root_children(Dev E) {
     const int lane = threadIdx.x & 31, g = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
     if (g >= E.B) return;
-    const int cnt = E.root_cnt[g];
+    const uint32_t *h = E.hdr + (size_t)g * HW;
+    const int cnt = (int)h[H_ROOTCNT];
     if (lane == 0) E.st_n[g] = cnt;
     if (cnt <= 0) return;
     const uint32_t cs = (uint32_t)((cnt + 7) & ~7);
-    const uint32_t *blk = arena_of(E, g) + E.root_base[g] + HDR;
+    const uint32_t *blk = arena_half(E, g, (h[H_FLAGS] & F_CUR) ? 1 : 0) + h[H_ROOTBASE] + HDR;
     for (int i = lane; i < cnt; i += 32) {
         const float W = __uint_as_float(blk[cs + i]);
         const int N = (int)blk[2 * cs + i];
@@ -708,24 +789,56 @@ __global__ void k_root_children(Dev E) {
     }
 }
 
+// packed game status record (cchess_main.check_end + GameBoard fields), CZ_STATUS_BYTES per game:
+//   [0,90) board | 90 side | 91 terminal | 92 winner (int8) | 96 ply i32 | 100 restrict_round i32 | 104 q f32 | 108 root N i32
+__device__ __forceinline__ void write_status(const Dev &E, int g, const uint32_t *h, const uint8_t *b, float q, int lane) {
+    uint8_t *o = E.st_status + (size_t)g * CZ_STATUS_BYTES;
+    for (int i = lane; i < 90; i += 32) o[i] = b[i];
+    if (lane == 0) {
+        const uint32_t f = h[H_FLAGS];
+        o[90] = (f & F_SIDE) ? 1 : 0;
+        o[91] = (uint8_t)F_TERM(f);
+        o[92] = (uint8_t)(int8_t)F_WIN(f);
+        o[93] = o[94] = o[95] = 0;
+        int32_t *w = reinterpret_cast<int32_t *>(o + 96);
+        w[0] = (int32_t)h[H_PLY];
+        w[1] = (int32_t)h[H_RR];
+        w[2] = __float_as_int(q);
+        w[3] = (int32_t)h[H_ROOTN];
+    }
+}
+__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_status(Dev E) {
+    const int lane = threadIdx.x & 31, g = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    if (g >= E.B) return;
+    write_status(E, g, E.hdr + (size_t)g * HW, E.root_board + (size_t)g * 96, 0.0f, lane);
+}
+
 // ---- play a move: board update + MCTS_tree.update_tree with subtree compaction ------------
-// Cheney-style breadth-first copy of the chosen child's subtree into the other arena half.
+// Cheney-style breadth-first copy of the chosen child's subtree into the other arena half.  Also leaves the game's
+// packed status record (with Q of the move played = mcts.Q(act), main.py:1350) in st_status.
 __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_play(Dev E) {
     const int lane = threadIdx.x & 31, g = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
     if (g >= E.B) return;
+    uint32_t *h = E.hdr + (size_t)g * HW;
+    uint8_t *b = E.root_board + (size_t)g * 96;
     const int choice = E.st_choice[g];
-    if (choice < 0) return;
-    const int rcnt = E.root_cnt[g];
-    if (rcnt <= 0 || choice >= rcnt) { if (lane == 0) atomicOr(E.err + g, CZ_ERR_NOMOVES); return; }
-    const uint32_t *old = arena_of(E, g);
-    uint32_t *neu = E.arena + ((size_t)g * 2 + (E.cur[g] ^ 1)) * (size_t)E.A;
+    if (choice < 0) { write_status(E, g, h, b, 0.0f, lane); return; }
+    const int rcnt = (int)h[H_ROOTCNT];
+    if (rcnt <= 0 || choice >= rcnt) { if (lane == 0) atomicOr(h + H_ERR, CZ_ERR_NOMOVES); write_status(E, g, h, b, 0.0f, lane); return; }
+    const uint32_t flags = h[H_FLAGS];
+    const int cur = (flags & F_CUR) ? 1 : 0;
+    const uint32_t *old = arena_half(E, g, cur);
+    uint32_t *neu = arena_half(E, g, cur ^ 1);
     const uint32_t rcs = (uint32_t)((rcnt + 7) & ~7);
-    const uint32_t *rblk = old + E.root_base[g] + HDR;
+    const uint32_t *rblk = old + h[H_ROOTBASE] + HDR;
     const uint32_t meta = rblk[3 * rcs + choice], child = rblk[4 * rcs + choice];
     const int N = (int)rblk[2 * rcs + choice];
-    uint8_t *b = E.root_board + (size_t)g * 96;
+    const float Wc = __uint_as_float(rblk[rcs + choice]);
+    const float q = N > 0 ? __fdiv_rn(Wc, (float)N) : 0.0f;
     const int src = meta & 127, dst = (meta >> 7) & 127;
-    const int cap = b[dst];
+    const int cap = b[dst], mover = b[src];
+    const int rr_old = (int)h[H_RR], ply_old = (int)h[H_PLY];
+    const unsigned long long z_old = (unsigned long long)h[H_HASHLO] | ((unsigned long long)h[H_HASHHI] << 32);
     __syncwarp();
     uint32_t alloc = 0;
     int ncnt = -1;
@@ -763,28 +876,33 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_play(Dev E) {
             scan += HDR + 5 * cs;
         }
     }
+    __syncwarp();
     if (lane == 0) {
-        b[dst] = b[src];
+        b[dst] = (uint8_t)mover;
         b[src] = 0;
-        const int side = E.side[g] ^ 1;
-        const int rr = cap == 0 ? E.rr[g] + 1 : 0;
-        E.side[g] = (uint8_t)side;
-        E.rr[g] = rr;
-        E.ply[g] += 1;
-        E.root_N[g] = N;
-        E.root_cnt[g] = ncnt;
-        E.root_base[g] = 0;
-        E.cur[g] ^= 1;
-        E.alloc[g] = alloc;
-        E.done[g] = 0;
-        E.target[g] = 0;
-        E.pending[g] = 0;
-        E.active[g] = 0;
+        const int side = (flags & F_SIDE) ? 0 : 1;
+        const int rr = cap == 0 ? rr_old + 1 : 0;
+        uint32_t f = (flags & ~(F_ACTIVE | 6u | F_SIDE | F_CUR)) | (side ? F_SIDE : 0u) | (cur ? 0u : F_CUR);
         // main.py:1532-1545: king missing -> winner, else restrict_round >= 60 -> tie
-        if (cap == 1) { E.terminal[g] = 1; E.winner[g] = 1; }
-        else if (cap == 8) { E.terminal[g] = 1; E.winner[g] = 0; }
-        else if (rr >= 60) { E.terminal[g] = 2; E.winner[g] = -1; }
+        if (cap == 1) f = (f & ~0xF00u) | (1u << 8) | (2u << 10);          // 'K' captured: black wins
+        else if (cap == 8) f = (f & ~0xF00u) | (1u << 8) | (1u << 10);     // 'k' captured: red wins
+        else if (rr >= 60) f = (f & ~0xF00u) | (2u << 8);
+        const unsigned long long z = z_old ^ E.zob[mover * 96 + src] ^ E.zob[mover * 96 + dst] ^ E.zob[95] ^ (cap ? E.zob[cap * 96 + dst] : 0ull);
+        h[H_FLAGS] = f;
+        h[H_RR] = (uint32_t)rr;
+        h[H_PLY] = (uint32_t)(ply_old + 1);
+        h[H_ROOTN] = (uint32_t)N;
+        h[H_ROOTCNT] = (uint32_t)ncnt;
+        h[H_ROOTBASE] = 0;
+        h[H_ALLOC] = alloc;
+        h[H_DONE] = 0;
+        h[H_TARGET] = 0;
+        h[H_PLEN] = 0;
+        h[H_HASHLO] = (uint32_t)z; h[H_HASHHI] = (uint32_t)(z >> 32);
+        if (alloc > h[H_MAXALLOC]) h[H_MAXALLOC] = alloc;
     }
+    __syncwarp();
+    write_status(E, g, h, b, q, lane);
 }
 
 // ---- stateless batched rules ------------------------------------------------------------
@@ -834,6 +952,28 @@ const int16_t *device_label_table(int device) {
     return tab[device];
 }
 
+// Zobrist keys: 16 piece codes x 96 squares of splitmix64 output (fixed seed), entry [0][95] = side to move.
+const unsigned long long *device_zobrist_table(int device) {
+    static const unsigned long long *tab[64] = {nullptr};
+    if (device < 0 || device >= 64) return nullptr;
+    if (!tab[device]) {
+        std::vector<unsigned long long> z(16 * 96);
+        unsigned long long x = 0x9E3779B97F4A7C15ull;
+        for (auto &v : z) {
+            x += 0x9E3779B97F4A7C15ull;
+            unsigned long long t = x;
+            t = (t ^ (t >> 30)) * 0xBF58476D1CE4E5B9ull;
+            t = (t ^ (t >> 27)) * 0x94D049BB133111EBull;
+            v = t ^ (t >> 31);
+        }
+        unsigned long long *p = nullptr;
+        if (cudaMalloc(&p, z.size() * 8) != cudaSuccess) return nullptr;
+        if (cudaMemcpy(p, z.data(), z.size() * 8, cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
+        tab[device] = p;
+    }
+    return tab[device];
+}
+
 inline int nblk(int n, int per) { return (n + per - 1) / per; }
 
 }  // namespace
@@ -847,7 +987,8 @@ struct cz_engine {
     int32_t *h_n = nullptr, *h_visits = nullptr, *h_choice = nullptr, *h_i32 = nullptr;
     uint16_t *h_moves = nullptr;
     float *h_f = nullptr;
-    uint8_t *h_u8 = nullptr;
+    uint8_t *h_status = nullptr;
+    uint32_t *h_hdr = nullptr;
     uint8_t *d_mask = nullptr, *d_boards = nullptr, *d_sides = nullptr;
     int32_t *d_rr = nullptr;
 };
@@ -855,7 +996,7 @@ struct cz_engine {
 extern "C" {
 
 const char *cz_last_error(void) { return g_err.c_str(); }
-int cz_version(void) { return 1; }
+int cz_version(void) { return 2; }
 
 int cz_labels(char *out) {
     if (!out) return fail(CZ_EINVAL, "cz_labels: null");
@@ -1019,6 +1160,14 @@ static int dalloc(cz_engine *e, T **p, size_t count, bool zero = true) {
     *p = (T *)q;
     return CZ_OK;
 }
+// every exit of cz_engine_create_ex after `new` goes through here: nothing (arena, pinned staging) leaks on failure
+static int create_failed(cz_engine *e, int code, const char *what, cudaError_t ce = cudaSuccess) {
+    const int rc = fail(code, what, ce);
+    const std::string keep = g_err;
+    cz_engine_destroy(e);
+    g_err = keep;
+    return rc;
+}
 }  // extern "C++"
 
 int cz_engine_create(int n_games, int64_t arena_words, int device, cz_engine **out) {
@@ -1032,16 +1181,16 @@ int cz_engine_create_ex(int n_games, int64_t arena_words, int device, int leaves
     const bool multi = leaves != 1;            // leaves == -1: the leaf-parallel kernel with one slot (test hook)
     const int K = leaves < 0 ? -leaves : leaves;
     if (K < 1 || K > 64) return fail(CZ_EINVAL, "cz_engine_create_ex: leaves must be 1..64");
-    if (arena_words <= 0) arena_words = 2ll << 20;
+    if (arena_words <= 0) arena_words = 2ll << 20;     // 8 MiB per half: 2.7x the high-water mark of a 1200-playout self-play soak (0.74 Mi words)
     if (arena_words < 4096 || arena_words >= (1ll << 31)) return fail(CZ_EINVAL, "cz_engine_create: arena_words out of range");
     arena_words = (arena_words + 31) & ~31ll;
     CUDA_TRY(cudaSetDevice(device));
     cz_engine *e = new cz_engine();
     e->device = device;
     Dev &d = e->d;
+    memset(&d, 0, sizeof(d));
     d.B = n_games;
     d.A = arena_words;
-    d.prepared = 0;
     d.K = K;
     {
         int sms = 148;
@@ -1049,38 +1198,35 @@ int cz_engine_create_ex(int n_games, int64_t arena_words, int device, int leaves
         int w = (n_games + sms - 1) / sms;
         e->wpb = w < 1 ? 1 : (w > MAX_WPB ? MAX_WPB : w);
     }
-    d.pendK = nullptr; d.plenK = nullptr; d.pathK = nullptr; d.leafK = nullptr;
     const size_t B = (size_t)n_games;
     int rc = 0;
 #define AL(ptr, cnt) if (!rc) rc = dalloc(e, &ptr, cnt)
-    AL(d.root_board, B * 96); AL(d.side, B); AL(d.rr, B); AL(d.ply, B); AL(d.root_N, B); AL(d.root_cnt, B);
-    AL(d.root_base, B); AL(d.done, B); AL(d.target, B); AL(d.pending, B); AL(d.active, B); AL(d.path_len, B);
-    AL(d.path, B * MAXD); AL(d.leaf_board, B * 96); AL(d.leaf_moves, B * CZ_MAXCHILD); AL(d.leaf_li, B * CZ_MAXCHILD); AL(d.leaf_n, B); AL(d.cur, B); AL(d.alloc, B); AL(d.max_alloc, B);
-    AL(d.cnt_expand, B); AL(d.cnt_playout, B); AL(d.cnt_L, B); AL(d.cnt_c, B); AL(d.cnt_C, B); AL(d.err, B); AL(d.max_depth, B);
-    AL(d.terminal, B); AL(d.winner, B);
+    AL(d.hdr, B * HW); AL(d.root_board, B * 96); AL(d.leaf_board, B * 96); AL(d.path, B * MAXD);
+    AL(d.cnt_expand, B); AL(d.cnt_playout, B); AL(d.cnt_L, B); AL(d.cnt_c, B); AL(d.cnt_C, B); AL(d.leaf_hash, B * K);
     AL(d.st_n, B); AL(d.st_visits, B * CZ_MAXCHILD); AL(d.st_choice, B); AL(d.st_moves, B * CZ_MAXCHILD);
-    AL(d.st_w, B * CZ_MAXCHILD); AL(d.st_p, B * CZ_MAXCHILD); AL(d.st_q, B * CZ_MAXCHILD); AL(d.st_count, 8);
+    AL(d.st_w, B * CZ_MAXCHILD); AL(d.st_p, B * CZ_MAXCHILD); AL(d.st_q, B * CZ_MAXCHILD); AL(d.st_count, 8); AL(d.st_status, B * CZ_STATUS_BYTES);
     AL(e->d_mask, B); AL(e->d_boards, B * 90); AL(e->d_sides, B); AL(e->d_rr, B);
     if (multi) { AL(d.pendK, B * K); AL(d.plenK, B * K); AL(d.pathK, B * K * MAXD); AL(d.leafK, B * K * 96); }
     if (!rc) { uint32_t *a = nullptr; rc = dalloc(e, &a, B * 2 * (size_t)arena_words, false); d.arena = a; }
 #undef AL
-    if (rc) { cz_engine_destroy(e); return rc; }
+    if (rc) { const std::string keep = g_err; cz_engine_destroy(e); g_err = keep; return rc; }
     d.label_of = device_label_table(device);
-    if (!d.label_of) { cz_engine_destroy(e); return fail(CZ_ECUDA, "label table upload"); }
+    d.zob = device_zobrist_table(device);
+    if (!d.label_of || !d.zob) return create_failed(e, CZ_ECUDA, "label / zobrist table upload");
     const size_t hb = B * CZ_MAXCHILD;
     if (cudaMallocHost(&e->h_n, B * 4) || cudaMallocHost(&e->h_visits, hb * 4) || cudaMallocHost(&e->h_choice, B * 4) ||
-        cudaMallocHost(&e->h_moves, hb * 2) || cudaMallocHost(&e->h_f, hb * 4 * 3) || cudaMallocHost(&e->h_u8, B * 96 + 64) ||
-        cudaMallocHost(&e->h_i32, B * 4 * 4 + 64)) {
-        cz_engine_destroy(e);
-        return fail(CZ_ENOMEM, "cudaMallocHost");
-    }
+        cudaMallocHost(&e->h_moves, hb * 2) || cudaMallocHost(&e->h_f, hb * 4 * 3) || cudaMallocHost(&e->h_status, B * CZ_STATUS_BYTES) ||
+        cudaMallocHost(&e->h_i32, 64) || cudaMallocHost(&e->h_hdr, B * HW * 4))
+        return create_failed(e, CZ_ENOMEM, "cudaMallocHost");
     {
         uint8_t sb[96] = {0};
-        if (cz_from_state("RNBAKABNR/9/1C5C1/P1P1P1P1P/9/9/p1p1p1p1p/1c5c1/9/rnbakabnr", sb) != CZ_OK) { cz_engine_destroy(e); return CZ_EINVAL; }
-        CUDA_TRY(cudaMemcpyToSymbol(c_start, sb, 96));   // GameBoard.__init__ state, main.py:585
+        if (cz_from_state("RNBAKABNR/9/1C5C1/P1P1P1P1P/9/9/p1p1p1p1p/1c5c1/9/rnbakabnr", sb) != CZ_OK) return create_failed(e, CZ_EINVAL, "start position");
+        cudaError_t ce = cudaMemcpyToSymbol(c_start, sb, 96);   // GameBoard.__init__ state, main.py:585
+        if (ce != cudaSuccess) return create_failed(e, CZ_ECUDA, "cudaMemcpyToSymbol(c_start)", ce);
     }
     k_reset<<<nblk(n_games, 128), 128>>>(d, nullptr, nullptr, nullptr, nullptr);
-    CUDA_TRY(cudaDeviceSynchronize());
+    cudaError_t ce = cudaDeviceSynchronize();
+    if (ce != cudaSuccess) return create_failed(e, CZ_ECUDA, "k_reset", ce);
     *out = e;
     return CZ_OK;
 }
@@ -1091,7 +1237,7 @@ int cz_engine_destroy(cz_engine *e) {
     cudaDeviceSynchronize();
     for (void *p : e->allocs) cudaFree(p);
     cudaFreeHost(e->h_n); cudaFreeHost(e->h_visits); cudaFreeHost(e->h_choice); cudaFreeHost(e->h_moves);
-    cudaFreeHost(e->h_f); cudaFreeHost(e->h_u8); cudaFreeHost(e->h_i32);
+    cudaFreeHost(e->h_f); cudaFreeHost(e->h_status); cudaFreeHost(e->h_i32); cudaFreeHost(e->h_hdr);
     delete e;
     return CZ_OK;
 }
@@ -1182,16 +1328,14 @@ int cz_engine_expand_backup(cz_engine *e, void *stream, const float *logits, con
     return launch_wave<true, false>(e, stream, (void *)logits, CZ_F32, logits, value);
 }
 
-int cz_engine_use_prepared_leaves(cz_engine *e, int on) {
+int cz_engine_enable_hashing(cz_engine *e, int on) {
     if (!e) return fail(CZ_EINVAL, "null engine");
-    e->d.prepared = on ? 1 : 0;   // read by every wave launched (or captured) afterwards
+    e->d.hash_on = on ? 1 : 0;   // read by every wave launched (or captured) afterwards
     return CZ_OK;
 }
-
-int cz_engine_prepare_leaves(cz_engine *e, void *stream) {
-    if (!e) return fail(CZ_EINVAL, "null engine");
-    k_prepare_leaves<<<nblk(e->d.B, WARPS_PER_BLOCK), 32 * WARPS_PER_BLOCK, 0, (cudaStream_t)stream>>>(e->d);
-    CUDA_TRY(cudaGetLastError());
+int cz_engine_leaf_hashes(cz_engine *e, uint64_t **dev_keys) {
+    if (!e || !dev_keys) return fail(CZ_EINVAL, "cz_engine_leaf_hashes: null");
+    *dev_keys = (uint64_t *)e->d.leaf_hash;
     return CZ_OK;
 }
 
@@ -1239,73 +1383,106 @@ int cz_engine_root_children(cz_engine *e, void *stream, int32_t *n_children, uin
     return CZ_OK;
 }
 
-int cz_engine_play(cz_engine *e, void *stream, const int32_t *child_index) {
+int cz_engine_play_status(cz_engine *e, void *stream, const int32_t *child_index, uint8_t *status) {
     if (!e || !child_index) return fail(CZ_EINVAL, "cz_engine_play: null");
     cudaStream_t st = (cudaStream_t)stream;
+    const size_t B = (size_t)e->d.B;
     CUDA_TRY(cudaSetDevice(e->device));
-    memcpy(e->h_choice, child_index, (size_t)e->d.B * 4);
-    CUDA_TRY(cudaMemcpyAsync(e->d.st_choice, e->h_choice, (size_t)e->d.B * 4, cudaMemcpyHostToDevice, st));
+    memcpy(e->h_choice, child_index, B * 4);
+    CUDA_TRY(cudaMemcpyAsync(e->d.st_choice, e->h_choice, B * 4, cudaMemcpyHostToDevice, st));
     k_play<<<nblk(e->d.B, WARPS_PER_BLOCK), 32 * WARPS_PER_BLOCK, 0, st>>>(e->d);
     CUDA_TRY(cudaGetLastError());
+    if (status) CUDA_TRY(cudaMemcpyAsync(e->h_status, e->d.st_status, B * CZ_STATUS_BYTES, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));   // h_choice is reused by the next call
+    if (status) memcpy(status, e->h_status, B * CZ_STATUS_BYTES);
+    return CZ_OK;
+}
+
+int cz_engine_play(cz_engine *e, void *stream, const int32_t *child_index) { return cz_engine_play_status(e, stream, child_index, nullptr); }
+
+int cz_engine_status_packed(cz_engine *e, void *stream, uint8_t *status) {
+    if (!e || !status) return fail(CZ_EINVAL, "cz_engine_status_packed: null");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t B = (size_t)e->d.B;
+    CUDA_TRY(cudaSetDevice(e->device));
+    k_status<<<nblk(e->d.B, WARPS_PER_BLOCK), 32 * WARPS_PER_BLOCK, 0, st>>>(e->d);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(e->h_status, e->d.st_status, B * CZ_STATUS_BYTES, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    memcpy(status, e->h_status, B * CZ_STATUS_BYTES);
     return CZ_OK;
 }
 
 int cz_engine_status(cz_engine *e, void *stream, uint8_t *terminal, int8_t *winner, int32_t *ply, int32_t *rr, uint8_t *side, uint8_t *boards) {
     if (!e) return fail(CZ_EINVAL, "null engine");
-    cudaStream_t st = (cudaStream_t)stream;
     const size_t B = (size_t)e->d.B;
-    CUDA_TRY(cudaSetDevice(e->device));
-    CUDA_TRY(cudaStreamSynchronize(st));
-    if (terminal) CUDA_TRY(cudaMemcpy(terminal, e->d.terminal, B, cudaMemcpyDeviceToHost));
-    if (winner) CUDA_TRY(cudaMemcpy(winner, e->d.winner, B, cudaMemcpyDeviceToHost));
-    if (ply) CUDA_TRY(cudaMemcpy(ply, e->d.ply, B * 4, cudaMemcpyDeviceToHost));
-    if (rr) CUDA_TRY(cudaMemcpy(rr, e->d.rr, B * 4, cudaMemcpyDeviceToHost));
-    if (side) CUDA_TRY(cudaMemcpy(side, e->d.side, B, cudaMemcpyDeviceToHost));
-    if (boards) CUDA_TRY(cudaMemcpy2D(boards, 90, e->d.root_board, 96, 90, B, cudaMemcpyDeviceToHost));
+    std::vector<uint8_t> rec(B * CZ_STATUS_BYTES);
+    int rc = cz_engine_status_packed(e, stream, rec.data());   // one kernel, one device->host copy, one synchronisation
+    if (rc) return rc;
+    for (size_t g = 0; g < B; g++) {
+        const uint8_t *r = rec.data() + g * CZ_STATUS_BYTES;
+        int32_t w[4];
+        memcpy(w, r + 96, 16);
+        if (boards) memcpy(boards + g * 90, r, 90);
+        if (side) side[g] = r[90];
+        if (terminal) terminal[g] = r[91];
+        if (winner) winner[g] = (int8_t)r[92];
+        if (ply) ply[g] = w[0];
+        if (rr) rr[g] = w[1];
+    }
     return CZ_OK;
 }
+
+extern "C++" {
+static int fetch_headers(cz_engine *e, void *stream) {
+    CUDA_TRY(cudaSetDevice(e->device));
+    CUDA_TRY(cudaMemcpyAsync(e->h_hdr, e->d.hdr, (size_t)e->d.B * HW * 4, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    return CZ_OK;
+}
+}  // extern "C++"
 
 int cz_engine_counters(cz_engine *e, void *stream, int64_t *out) {
     if (!e || !out) return fail(CZ_EINVAL, "cz_engine_counters: null");
     const size_t B = (size_t)e->d.B;
-    CUDA_TRY(cudaSetDevice(e->device));
-    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    int rc = fetch_headers(e, stream);
+    if (rc) return rc;
     std::vector<unsigned long long> a(B), b(B), c(B), d(B), cc(B);
-    std::vector<uint32_t> er(B), ma(B);
-    std::vector<int32_t> md(B);
     CUDA_TRY(cudaMemcpy(a.data(), e->d.cnt_expand, B * 8, cudaMemcpyDeviceToHost));
     CUDA_TRY(cudaMemcpy(b.data(), e->d.cnt_playout, B * 8, cudaMemcpyDeviceToHost));
     CUDA_TRY(cudaMemcpy(c.data(), e->d.cnt_L, B * 8, cudaMemcpyDeviceToHost));
     CUDA_TRY(cudaMemcpy(d.data(), e->d.cnt_c, B * 8, cudaMemcpyDeviceToHost));
     CUDA_TRY(cudaMemcpy(cc.data(), e->d.cnt_C, B * 8, cudaMemcpyDeviceToHost));
-    CUDA_TRY(cudaMemcpy(er.data(), e->d.err, B * 4, cudaMemcpyDeviceToHost));
-    CUDA_TRY(cudaMemcpy(ma.data(), e->d.max_alloc, B * 4, cudaMemcpyDeviceToHost));
-    CUDA_TRY(cudaMemcpy(md.data(), e->d.max_depth, B * 4, cudaMemcpyDeviceToHost));
     for (int i = 0; i < 9; i++) out[i] = 0;
     out[6] = -1;
     for (size_t g = 0; g < B; g++) {
+        const uint32_t *h = e->h_hdr + g * HW;
         out[0] += (int64_t)a[g]; out[1] += (int64_t)b[g]; out[2] += (int64_t)c[g]; out[3] += (int64_t)d[g];
-        out[4] |= er[g];
-        if (ma[g] > out[5]) out[5] = ma[g];
-        if (er[g] && out[6] < 0) out[6] = (int64_t)g;
-        if (md[g] > out[7]) out[7] = md[g];
+        out[4] |= h[H_ERR];
+        if (h[H_MAXALLOC] > out[5]) out[5] = h[H_MAXALLOC];
+        if (h[H_ERR] && out[6] < 0) out[6] = (int64_t)g;
+        if (h[H_MAXDEPTH] > out[7]) out[7] = h[H_MAXDEPTH];
         out[8] += (int64_t)cc[g];
     }
     return CZ_OK;
 }
 
+int cz_engine_root_keys(cz_engine *e, void *stream, uint64_t *keys) {
+    if (!e || !keys) return fail(CZ_EINVAL, "cz_engine_root_keys: null");
+    int rc = fetch_headers(e, stream);
+    if (rc) return rc;
+    for (int g = 0; g < e->d.B; g++) keys[g] = (uint64_t)e->h_hdr[(size_t)g * HW + H_HASHLO] | ((uint64_t)e->h_hdr[(size_t)g * HW + H_HASHHI] << 32);
+    return CZ_OK;
+}
+
 int cz_engine_tree_signature(cz_engine *e, void *stream, int game, int64_t *out, int64_t cap, int64_t *n) {
     if (!e || !n || game < 0 || game >= e->d.B) return fail(CZ_EINVAL, "cz_engine_tree_signature: bad arguments");
-    CUDA_TRY(cudaSetDevice(e->device));
-    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
-    uint8_t cur;
-    uint32_t alloc, rbase;
-    int32_t rcnt;
-    CUDA_TRY(cudaMemcpy(&cur, e->d.cur + game, 1, cudaMemcpyDeviceToHost));
-    CUDA_TRY(cudaMemcpy(&alloc, e->d.alloc + game, 4, cudaMemcpyDeviceToHost));
-    CUDA_TRY(cudaMemcpy(&rbase, e->d.root_base + game, 4, cudaMemcpyDeviceToHost));
-    CUDA_TRY(cudaMemcpy(&rcnt, e->d.root_cnt + game, 4, cudaMemcpyDeviceToHost));
+    int rc = fetch_headers(e, stream);
+    if (rc) return rc;
+    const uint32_t *h = e->h_hdr + (size_t)game * HW;
+    const int cur = (h[H_FLAGS] & F_CUR) ? 1 : 0;
+    const uint32_t alloc = h[H_ALLOC], rbase = h[H_ROOTBASE];
+    const int32_t rcnt = (int32_t)h[H_ROOTCNT];
     std::vector<uint32_t> ar(alloc);
     if (alloc) CUDA_TRY(cudaMemcpy(ar.data(), e->d.arena + ((size_t)game * 2 + cur) * (size_t)e->d.A, (size_t)alloc * 4, cudaMemcpyDeviceToHost));
     int64_t k = 0;

@@ -8,7 +8,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import BF16, BOARD, F16, F32, MAXCHILD, EngineError, check, lib
+from ._lib import BF16, BOARD, F16, F32, MAXCHILD, STATUS_BYTES, EngineError, check, lib
 
 _DT = {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16, torch.uint8: BOARD}
 
@@ -83,14 +83,24 @@ class Engine:
         self.launches += 1
         check(lib().cz_engine_expand_backup(self.h, _stream(), logits.data_ptr(), value.data_ptr()), "cz_engine_expand_backup")
 
-    def use_prepared_leaves(self, on=True):
-        check(lib().cz_engine_use_prepared_leaves(self.h, 1 if on else 0), "cz_engine_use_prepared_leaves")
+    # ---- board hashing (Zobrist keys of the pending leaves; never used by the search) -------
+    def enable_hashing(self, on=True):
+        check(lib().cz_engine_enable_hashing(self.h, 1 if on else 0), "cz_engine_enable_hashing")
 
-    def prepare_leaves(self, stream=None):
-        """Move generation for the leaves of the last wave, meant for a side stream under the network (see capture_graph)."""
-        self.launches += 1
-        st = _stream() if stream is None else C.c_void_p(stream.cuda_stream)
-        check(lib().cz_engine_prepare_leaves(self.h, st), "cz_engine_prepare_leaves")
+    def leaf_hashes(self):
+        """int64 view (device tensor, [rows]) of the 64-bit Zobrist keys of the positions in the network batch rows."""
+        ptr = C.c_void_p()
+        check(lib().cz_engine_leaf_hashes(self.h, C.byref(ptr)), "cz_engine_leaf_hashes")
+        n = self.rows
+
+        class _Arr:                                            # __cuda_array_interface__ view of engine-owned memory
+            __cuda_array_interface__ = dict(shape=(n,), typestr="<i8", data=(ptr.value, False), version=2)
+        return torch.as_tensor(_Arr(), device="cuda:%d" % self.device)
+
+    def root_keys(self):
+        out = np.zeros(self.B, dtype=np.uint64)
+        check(lib().cz_engine_root_keys(self.h, _stream(), _hp(out)), "cz_engine_root_keys")
+        return out
 
     def unfinished(self):
         out = C.c_int32(0)
@@ -117,22 +127,29 @@ class Engine:
               "cz_engine_root_children")
         return dict(n=n, moves=mv, visits=vis, w=w, p=p, q=q)
 
-    def play(self, child_index):
+    def play(self, child_index, want_status=True):
+        """GameBoard update + update_tree for every game with child_index >= 0; returns the status of all games (see status())
+        from the same call: one kernel, one device->host copy, one synchronisation."""
         ci = np.ascontiguousarray(child_index, dtype=np.int32)
         assert ci.shape == (self.B,)
         self.launches += 1
-        check(lib().cz_engine_play(self.h, _stream(), _hp(ci)), "cz_engine_play")
+        rec = np.zeros((self.B, STATUS_BYTES), dtype=np.uint8) if want_status else None
+        check(lib().cz_engine_play_status(self.h, _stream(), _hp(ci), _hp(rec)), "cz_engine_play_status")
+        return self._unpack_status(rec) if want_status else None
+
+    @staticmethod
+    def _unpack_status(rec):
+        tail = np.ascontiguousarray(rec[:, 96:112]).view(np.int32)
+        return dict(boards=np.ascontiguousarray(rec[:, :90]), side=rec[:, 90].copy(), terminal=rec[:, 91].copy(),
+                    winner=rec[:, 92].copy().view(np.int8), ply=tail[:, 0].copy(), rr=tail[:, 1].copy(),
+                    q=np.ascontiguousarray(tail[:, 2]).view(np.float32), root_N=tail[:, 3].copy())
 
     def status(self, boards=True):
-        B = self.B
-        t = np.zeros(B, dtype=np.uint8)
-        w = np.zeros(B, dtype=np.int8)
-        ply = np.zeros(B, dtype=np.int32)
-        rr = np.zeros(B, dtype=np.int32)
-        side = np.zeros(B, dtype=np.uint8)
-        bd = np.zeros((B, 90), dtype=np.uint8) if boards else None
-        check(lib().cz_engine_status(self.h, _stream(), _hp(t), _hp(w), _hp(ply), _hp(rr), _hp(side), _hp(bd)), "cz_engine_status")
-        return dict(terminal=t, winner=w, ply=ply, rr=rr, side=side, boards=bd)
+        """terminal / winner / ply / restrict_round / side / boards of every game (check_end, main.py:1380-1392)."""
+        rec = np.zeros((self.B, STATUS_BYTES), dtype=np.uint8)
+        self.launches += 1
+        check(lib().cz_engine_status_packed(self.h, _stream(), _hp(rec)), "cz_engine_status_packed")
+        return self._unpack_status(rec)
 
     def counters(self):
         out = np.zeros(9, dtype=np.int64)

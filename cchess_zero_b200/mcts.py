@@ -131,8 +131,7 @@ class MCTS_tree(object):
         ch = self._children()
         idx = list(ch.keys()).index(act)   # KeyError/ValueError like root.child[act]
         self._root_N = ch[act].N
-        self.engine.play(np.array([idx], dtype=np.int32))
-        st = self.engine.status()
+        st = self.engine.play(np.array([idx], dtype=np.int32))
         self._state = rules.board_to_state(st["boards"][0])
         self._side, self._rr = int(st["side"][0]), int(st["rr"][0])
         self._cache = None

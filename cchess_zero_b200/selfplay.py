@@ -158,9 +158,9 @@ class _MultiEngine:
         parts = [l.engine.root_children(want_wpq) for l in self.lanes]
         return {k: (np.concatenate([p[k] for p in parts]) if parts[0][k] is not None else None) for k in parts[0]}
 
-    def play(self, child_index):
-        for l in self.lanes:
-            l.engine.play(child_index[l.lo:l.hi])
+    def play(self, child_index, want_status=True):
+        parts = [l.engine.play(child_index[l.lo:l.hi], want_status) for l in self.lanes]
+        return {k: np.concatenate([p[k] for p in parts]) for k in parts[0]} if want_status else None
 
     def status(self, boards=True):
         parts = [l.engine.status(boards) for l in self.lanes]
@@ -199,7 +199,7 @@ class SelfPlay:
 
     def __init__(self, n_games, forward, playouts, seeds=None, exploration=True, temperature=1,
                  nn_dtype=torch.float32, arena_words=0, auto_reset=True, device=None, keep_records=True, plan=None,
-                 plan_factory=None, lanes=1, overlap_movegen=False, engine=None):
+                 plan_factory=None, lanes=1, engine=None, hashing=False):
         """plan: an InferencePlan / NativePlan (defines the input buffer, writes logits/value in place).
         plan_factory(n) + lanes=2: two half-batches, each with its own engine and plan; the search pipelines them so
         that one half's tree kernel runs under the other half's network (see capture_graph)."""
@@ -222,6 +222,8 @@ class SelfPlay:
             # `engine`: an object with the Engine interface (tests drive the host loop with a CPU stand-in); the product
             # always constructs the CUDA engine here
             self.engine = engine if engine is not None else Engine(n_games, arena_words, device)
+            if hashing:                              # Zobrist keys of the pending leaves (must be on before a graph is captured)
+                self.engine.enable_hashing(True)
             dev = torch.device("cuda", self.engine.device) if engine is None else torch.device(getattr(engine, "torch_device", "cpu"))
             if plan is None and plan_factory is not None:
                 plan = plan_factory(n_games)
@@ -243,14 +245,14 @@ class SelfPlay:
         self.auto_reset = auto_reset
         self.keep_records = keep_records
         self.records = [GameRecord() for _ in range(n_games)]
-        self.boards = np.tile(rules.state_to_board(rules.START_STATE), (n_games, 1))
+        self._start_board = rules.state_to_board(rules.START_STATE)
+        self.boards = np.tile(self._start_board, (n_games, 1))
         self.sides = np.zeros(n_games, dtype=np.uint8)
         self.live = np.ones(n_games, dtype=bool)
         self.finished = []
         self.plies = 0
         self.waves = 0
         self.graph = None
-        self.overlap_movegen = overlap_movegen
         self._alphas = {}
         rules._init_tables()
 
@@ -338,19 +340,9 @@ class SelfPlay:
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         cs = torch.cuda.Stream()
-        side = torch.cuda.Stream()
-        if self.overlap_movegen:
-            self.engine.use_prepared_leaves(True)        # must precede the capture of the wave node
         with torch.cuda.graph(g, stream=cs):
             self.engine.wave(self.nn_in, self.logits, self.value)
-            if self.overlap_movegen:
-                # fork: the move generation of the new leaves runs under their network evaluation
-                side.wait_stream(cs)
-                with torch.cuda.stream(side):
-                    self.engine.prepare_leaves()
             self._eval(self.nn_in)
-            if self.overlap_movegen:
-                cs.wait_stream(side)
         self.graph = g
 
     def search(self):
@@ -385,9 +377,8 @@ class SelfPlay:
     def step(self):
         e = self.engine
         self.search()
-        rc = e.root_children(want_wpq=True)
+        rc = e.root_children(want_wpq=False)                      # n, moves, visits: what get_action reads (main.py:1339)
         choice = np.full(self.B, -1, dtype=np.int32)
-        win_rate = np.zeros(self.B, dtype=np.float32)
         live = np.nonzero(self.live)[0]
         if (rc["n"][live] <= 0).any():
             e.raise_on_error()
@@ -426,9 +417,8 @@ class SelfPlay:
                     rec.pi_val.append(probs)
                     rec._chosen.append(idx)
                     rec.visits.append(rc["visits"][g, :n].copy())
-            win_rate[live] = rc["q"][live, choice[live]]                                # mcts.Q(act), main.py:1350
-        e.play(choice)
-        st = e.status(boards=True)
+        st = e.play(choice)                                          # board update + re-root + status, one synchronisation
+        win_rate = np.where(choice >= 0, st["q"], 0.0).astype(np.float32)                 # mcts.Q(act), main.py:1350
         self.boards, self.sides = st["boards"], st["side"]
         self.plies += int(self.live.sum())
         done_now = []
@@ -446,14 +436,21 @@ class SelfPlay:
             self.finished.append((int(g), rec))
             self.records[g] = GameRecord()
         if done_now:
-            mask = np.zeros(self.B, dtype=np.uint8)
-            mask[[g for g, _ in done_now]] = 1
+            idx = [g for g, _ in done_now]
             if self.auto_reset:
+                mask = np.zeros(self.B, dtype=np.uint8)
+                mask[idx] = 1
                 e.reset(mask)                                                            # GameBoard.reload + mcts.reload
-                st = e.status(boards=True)
+                st = {k: v.copy() for k, v in st.items()}
+                st["boards"][idx] = self._start_board                                    # what reload() leaves: no second status read
+                st["side"][idx] = 0
+                st["terminal"][idx] = 0
+                st["winner"][idx] = -1
+                st["ply"][idx] = 0
+                st["rr"][idx] = 0
                 self.boards, self.sides = st["boards"], st["side"]
             else:
-                self.live[[g for g, _ in done_now]] = False
+                self.live[idx] = False
         return dict(choice=choice, win_rate=win_rate, finished=done_now, status=st)
 
     def pop_finished(self):

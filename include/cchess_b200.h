@@ -81,7 +81,7 @@ int cz_encode_dev(const uint8_t *boards, const uint8_t *sides, int n, void *out,
 typedef struct cz_engine cz_engine;
 
 /* arena_words: uint32 words of tree storage per game per half (two halves, ping-pong re-rooting);
- * 0 selects the default (2 Mi words = 8 MiB per half). */
+ * 0 selects the default (2 Mi words = 8 MiB per half; a 1200-playout self-play soak peaks at 0.74 Mi words). */
 int cz_engine_create(int n_games, int64_t arena_words, int device, cz_engine **out);
 /* Leaf-parallel variant: up to `leaves` (1..64) leaves per game per wave inside one tree (virtual-loss batching; the
  * search_threads > 1 idea of main.py:337-440 with a deterministic schedule of its own -- not bit-comparable with the
@@ -122,14 +122,14 @@ int cz_engine_wave(cz_engine *e, void *stream, void *nn_in, int nn_dtype, const 
 int cz_engine_select(cz_engine *e, void *stream, void *nn_in, int nn_dtype);
 int cz_engine_expand_backup(cz_engine *e, void *stream, const float *logits, const float *value);
 
-/* Optional overlap: generate the move lists (and label indices) of the leaves selected by the last wave.  Launch it
- * on a side stream while the network evaluates those leaves; the next cz_engine_wave then skips move generation for
- * every leaf that was prepared (identical results: same device code), provided cz_engine_use_prepared_leaves(e, 1)
- * was called before that wave was launched / captured.  Stream ordering is the caller's job:
- * after the wave, before the next wave.  Capturable. */
-int cz_engine_prepare_leaves(cz_engine *e, void *stream);
-/* Waves launched (or captured into a graph) after this call use the prepared lists when present (on != 0). */
-int cz_engine_use_prepared_leaves(cz_engine *e, int on);
+/* Board hashing (north_star): when switched on, every wave also leaves the 64-bit Zobrist key of each pending leaf's position
+ * (piece-square keys XOR side-to-move key, maintained incrementally along the descent; the root's key lives in the game's header
+ * line and is updated by cz_engine_play) in a device array indexed like the network batch rows.  The reference has no position
+ * hashing (nodes are keyed by object identity, main.py:246-247); the keys exist for evaluation de-duplication studies and
+ * transposition statistics, they never influence the search.  Capturable; read by waves launched / captured afterwards. */
+int cz_engine_enable_hashing(cz_engine *e, int on);
+int cz_engine_leaf_hashes(cz_engine *e, uint64_t **dev_keys /* out: device pointer, [n_games*leaves] */);
+int cz_engine_root_keys(cz_engine *e, void *stream, uint64_t *keys /* host [B] */);
 
 /* Number of games that still have playouts to run or a leaf pending (device->host, synchronises stream). */
 int cz_engine_unfinished(cz_engine *e, void *stream, int32_t *out_count);
@@ -148,6 +148,12 @@ int cz_engine_root_children(cz_engine *e, void *stream, int32_t *n_children /* [
  * subtree is compacted into the other arena half and becomes the root; terminal flags are updated
  * (main.py:1532-1545).  child_index is a HOST buffer. */
 int cz_engine_play(cz_engine *e, void *stream, const int32_t *child_index /* [B] */);
+/* Same, and returns every game's packed status record (one kernel, one device->host copy, one synchronisation):
+ * CZ_STATUS_BYTES per game: [0,90) board | 90 side | 91 terminal | 92 winner (int8) | 96 ply i32 | 100 restrict_round i32 |
+ * 104 Q (f32) of the move just played = MCTS_tree.Q(act), main.py:1350 | 108 N of the new root i32. */
+#define CZ_STATUS_BYTES 112
+int cz_engine_play_status(cz_engine *e, void *stream, const int32_t *child_index /* [B] */, uint8_t *status /* host [B][112] or NULL */);
+int cz_engine_status_packed(cz_engine *e, void *stream, uint8_t *status /* host [B][112] */);
 
 /* Game status (cchess_main.check_end main.py:1380-1392): HOST buffers, any may be NULL; synchronises.
  * terminal: 0 running, 1 king captured, 2 draw (restrict_round >= 60); winner: 0 'w', 1 'b', -1 none. */

@@ -223,8 +223,7 @@ def test_selfplay_many_games_vs_oracle(graph, O, R):
     from cchess_zero_b200.fakenet import FakeNet
     from cchess_zero_b200.selfplay import SelfPlay
     B, playouts, net = 48, 40, "hash_pos"
-    sp = SelfPlay(B, FakeNet(net), playouts, seeds=[1000 + i for i in range(B)], arena_words=1 << 20, auto_reset=False,
-                  overlap_movegen=graph)     # the graph variant also exercises the prepared-leaves side stream
+    sp = SelfPlay(B, FakeNet(net), playouts, seeds=[1000 + i for i in range(B)], arena_words=1 << 20, auto_reset=False)
     if graph:
         sp.capture_graph()
     out = sp.play_games()
@@ -291,9 +290,13 @@ def test_full_size_1024_games_1200_playouts_properties_and_samples(O, R):
     # step() = search + host move choice; the search is done, choose the moves by hand (any legal child will do)
     choice = np.array([int(np.random.RandomState(s).randint(44)) for s in seeds], dtype=np.int32)
     N_chosen = rc1["visits"][np.arange(B), choice]
-    e.play(choice)
+    st_play = e.play(choice)
     # ply 2 (tree re-use): children of the new root keep their statistics, then P more playouts are added
-    sp.boards, sp.sides = e.status()["boards"], e.status()["side"]
+    st_read = e.status()
+    for k in ("boards", "side", "terminal", "winner", "ply", "rr"):
+        assert np.array_equal(st_play[k], st_read[k]), k               # play() returns the status a separate read would give
+    assert np.array_equal(st_play["q"], rc1["q"][np.arange(B), choice]) and np.array_equal(st_play["root_N"], N_chosen)
+    sp.boards, sp.sides = st_read["boards"], st_read["side"]
     sp.search()
     rc2 = e.root_children()
     tot = np.array([rc2["visits"][g, : rc2["n"][g]].sum() for g in range(B)])
@@ -493,3 +496,41 @@ def test_rules_flip_symmetry_on_a_quarter_million_positions(R):
         boards, sides = nb, sides ^ 1
         boards[dead] = R.state_to_board(R.START_STATE); sides[dead] = 0
     assert n_checked == G * plies
+
+
+def test_board_hashing_keys_are_incremental_zobrist_and_never_touch_the_search(O, R):
+    """north_star "board hashing": the engine maintains a 64-bit Zobrist key per root (updated by every played move) and per
+    pending leaf (updated along the descent).  (1) the incrementally maintained root key equals the key computed from scratch
+    for the same position and side to move; (2) equal positions <=> equal keys across games; (3) hashing on / off gives the
+    same trees bit for bit; (4) leaf keys of games that evaluate the same position coincide, different positions differ."""
+    from cchess_zero_b200.engine import Engine
+    from cchess_zero_b200.fakenet import FakeNet
+    from cchess_zero_b200.selfplay import SelfPlay
+    B, P, net = 64, 24, "hash_pos"
+    seeds = [7 + (i % 16) for i in range(B)]                         # 16 distinct games, each played 4 times
+    sp = SelfPlay(B, FakeNet(net), P, seeds=seeds, arena_words=1 << 18, auto_reset=False, hashing=True)
+    sp0 = SelfPlay(B, FakeNet(net), P, seeds=seeds, arena_words=1 << 18, auto_reset=False)
+    for _ in range(6):
+        sp.step(); sp0.step()
+    for g in (0, 5, 17, 63):
+        assert np.array_equal(sp.engine.tree_signature(g), sp0.engine.tree_signature(g))          # (3)
+    keys = sp.engine.root_keys()
+    st = sp.engine.status()
+    e2 = Engine(B, 1 << 12)
+    e2.reset(None, st["boards"], st["side"], st["rr"])
+    assert np.array_equal(e2.root_keys(), keys)                                                    # (1)
+    by_pos = {}
+    for g in range(B):
+        by_pos.setdefault((st["boards"][g].tobytes(), int(st["side"][g])), set()).add(int(keys[g]))
+    assert all(len(v) == 1 for v in by_pos.values()) and len({next(iter(v)) for v in by_pos.values()}) == len(by_pos)   # (2)
+    assert len(by_pos) >= 8
+    # (4) one wave of the next search: rows of replicated games carry identical leaf keys
+    sp.engine.begin_search(P)
+    sp.engine.wave(sp.nn_in, sp.logits, sp.value)
+    sp._eval(sp.nn_in)
+    sp.engine.wave(sp.nn_in, sp.logits, sp.value)
+    lk = sp.engine.leaf_hashes().cpu().numpy()
+    assert (lk != 0).any()
+    for g in range(16):
+        assert len({int(lk[g + 16 * r]) for r in range(4)}) == 1
+    e2.close()

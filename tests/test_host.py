@@ -300,17 +300,23 @@ class _OracleEngine:
             k = len(m); n[g] = k; mv[g, :k] = m; vis[g, :k] = N; w[g, :k] = W; p[g, :k] = P; q[g, :k] = Q
         return dict(n=n, moves=mv, visits=vis, w=w, p=p, q=q)
 
-    def play(self, choice):
+    def play(self, choice, want_status=True):
+        q = np.zeros(self.B, np.float32)
         for g, c in enumerate(choice):
             if c < 0:
                 continue
-            m = self.trees[g].root_children()[0][c]
+            rc = self.trees[g].root_children()
+            m = rc[0][c]
+            q[g] = rc[4][c]
             self.trees[g].update(int(c))
             self.boards[g], cap = self.O.apply_move(self.boards[g], int(m))
             self.side[g] ^= 1; self.rr[g] = self.rr[g] + 1 if cap == 0 else 0; self.ply[g] += 1
             if cap == 1: self.terminal[g], self.winner[g] = 1, 1
             elif cap == 8: self.terminal[g], self.winner[g] = 1, 0
             elif self.rr[g] >= 60: self.terminal[g] = 2
+        st = self.status()
+        st["q"] = q
+        return st if want_status else None
 
     def status(self, boards=True):
         return dict(terminal=self.terminal.copy(), winner=self.winner.copy(), ply=self.ply.copy(), rr=self.rr.copy(),
