@@ -56,6 +56,10 @@ def _sig(L):
     L.cz_net_first_conv.argtypes = [vp, i32, vp, vp, vp, vp]
     L.cz_net_first_conv_tc.argtypes = [vp, i32, vp, vp, vp, vp]
     L.cz_net_heads.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.cz_net_heads_fc.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.cz_net_tower_blob_bytes.argtypes = [i32]
+    L.cz_net_tower_blob_bytes.restype = i64
+    L.cz_net_tower_small.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp]
 
 
 def lib():

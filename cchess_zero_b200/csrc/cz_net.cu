@@ -396,14 +396,13 @@ int cz_net_first_conv_tc(const uint8_t *canon_boards, int B, const void *w_umma,
     return cudaGetLastError() == cudaSuccess ? CZ_OK : CZ_ECUDA;
 }
 
-int cz_net_heads(const void *x, int B, const float *wh, const float *bh, const float *w1t, const float *b1, const float *w2, const float *b2,
-                 const void *wp, const float *bp, void *hp_scratch, float *hv_scratch, float *logits, float *value, void *stream) {
-    if (!x || !wh || !bh || !w1t || !b1 || !w2 || !b2 || !wp || !bp || !hp_scratch || !hv_scratch || !logits || !value || B <= 0) return CZ_EINVAL;
+// value MLP (side stream) || policy FC on already computed head features hp / hv
+int cz_net_heads_fc(const void *hp, const float *hv, int B, const float *w1t, const float *b1, const float *w2, const float *b2,
+                    const void *wp, const float *bp, float *logits, float *value, void *stream) {
+    if (!hp || !hv || !w1t || !b1 || !w2 || !b2 || !wp || !bp || !logits || !value || B <= 0) return CZ_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
     const int smem = 2 * 64 * LDS_ROW * (int)sizeof(__half);   // 51200 B > the 48 KB default: opt in (per device, so every call)
     if (cudaFuncSetAttribute(k_policy_fc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return CZ_ECUDA;
-    k_head_conv<<<B, 256, 0, st>>>((const __half *)x, B, wh, bh, (__half *)hp_scratch, hv_scratch);
-    if (cudaGetLastError() != cudaSuccess) return CZ_ECUDA;
     // The value MLP and the policy FC are independent: fork the value MLP onto a side stream (event fork/join, which
     // CUDA-graph capture records as two parallel branches) so that the two small kernels overlap.
     int dev = 0;
@@ -417,14 +416,22 @@ int cz_net_heads(const void *x, int B, const float *wh, const float *bh, const f
     }
     if (cudaEventRecord(ev_fork[dev], st) != cudaSuccess) return CZ_ECUDA;
     if (cudaStreamWaitEvent(side[dev], ev_fork[dev], 0) != cudaSuccess) return CZ_ECUDA;
-    k_value_mlp<<<(B + VM_POS - 1) / VM_POS, 256, 0, side[dev]>>>(hv_scratch, B, w1t, b1, w2, b2, value);
+    k_value_mlp<<<(B + VM_POS - 1) / VM_POS, 256, 0, side[dev]>>>(hv, B, w1t, b1, w2, b2, value);
     if (cudaGetLastError() != cudaSuccess) return CZ_ECUDA;
     if (cudaEventRecord(ev_join[dev], side[dev]) != cudaSuccess) return CZ_ECUDA;
     dim3 grid((B + 63) / 64, NPAD / 64);
-    k_policy_fc<<<grid, 128, smem, st>>>((const __half *)hp_scratch, B, (const __half *)wp, bp, logits);
+    k_policy_fc<<<grid, 128, smem, st>>>((const __half *)hp, B, (const __half *)wp, bp, logits);
     if (cudaGetLastError() != cudaSuccess) return CZ_ECUDA;
     if (cudaStreamWaitEvent(st, ev_join[dev], 0) != cudaSuccess) return CZ_ECUDA;
     return CZ_OK;
+}
+
+int cz_net_heads(const void *x, int B, const float *wh, const float *bh, const float *w1t, const float *b1, const float *w2, const float *b2,
+                 const void *wp, const float *bp, void *hp_scratch, float *hv_scratch, float *logits, float *value, void *stream) {
+    if (!x || !wh || !bh || !hp_scratch || !hv_scratch || B <= 0) return CZ_EINVAL;
+    k_head_conv<<<B, 256, 0, (cudaStream_t)stream>>>((const __half *)x, B, wh, bh, (__half *)hp_scratch, hv_scratch);
+    if (cudaGetLastError() != cudaSuccess) return CZ_ECUDA;
+    return cz_net_heads_fc(hp_scratch, hv_scratch, B, w1t, b1, w2, b2, wp, bp, logits, value, stream);
 }
 
 }  // extern "C"

@@ -1,0 +1,379 @@
+// cz_tower.cu -- the whole convolutional trunk of the policy-value network for a FEW positions (1..16) in ONE launch:
+// first conv3x3(14->128) + res_block_nums x [conv3x3 -> ReLU -> conv3x3 -> +skip -> ReLU] + the two 1x1 head convolutions
+// (policy_value_network.py:45-74, 151-162; batch norm folded into the weights), hand-written for sm_100a.
+//
+// Why: play mode (BASELINE config 5) and any single-tree search evaluate one leaf (or a handful) per network call.  At batch 1
+// the library path is 15+ launches of ~5 us each, every one re-reading its weights; here the activations of a position never
+// leave the SMs and the weights stream from L2 under the tensor cores.
+//
+// Shape: one thread-block CLUSTER of CL CTAs (CL = 1, 2, 4 or 8) per position; CTA r owns output channels
+// [r*128/CL, (r+1)*128/CL).  Per 3x3 convolution and CTA:
+//     D[128 rows][128/CL ch] (f32, TMEM) = sum over 9 taps of  A_tap[128][128] . B_tap[128][128/CL]      -- 72 tcgen05.mma (K = 16)
+//   * A = the position's activation image, fp16, resident in shared memory in the canonical K-major NO-SWIZZLE UMMA layout
+//     [16 k-chunks of 8 channels][152 rows][8 halves]: with SBO = 128 B consecutive rows are 16 bytes apart in every chunk, so a
+//     3x3 tap is nothing but a START-ADDRESS OFFSET of (dr*11 + df) rows in the A descriptor -- no im2col, no copies.  Rows are
+//     image cells in a padded raster: cell (r, f) of the reference's [9][10] image sits in row 12 + r*11 + f; the 11th column and
+//     the rows above / below are zeros, which gives the convolution's zero padding for free (99 of the 128 MMA rows are cells).
+//   * B = this CTA's slice of the layer's weights, streamed tap by tap from L2 by TMA (cp.async.bulk.tensor, SASS UTMALDG)
+//     through a ring of shared-memory stages (full / empty mbarriers); the producer runs ahead across layers.
+//   * epilogue: 4 warps read their TMEM lanes (tcgen05.ld), add bias (+ the residual skip), ReLU, convert to fp16 and write the
+//     8-channel chunks of the NEXT layer's A image into the shared memory of ALL CL CTAs of the cluster (DSMEM stores), then
+//     signal every CTA's `act_ready` mbarrier; a CTA's MMA warp starts the next layer when all CL*4 epilogue warps have signalled.
+//     No cluster-wide barrier on the critical path.
+// Warp roles: warps 0-3 epilogue (TMEM lane quarters), warp 4 TMA producer, warp 5 MMA issuer (one elected lane each).
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/cchess_b200.h"
+
+namespace {
+
+constexpr int ROWS = 152;                 // rows per k-chunk of an activation image (12 pad + 128 MMA rows + 12 pad)
+constexpr int P0 = 12;                    // row of image cell (0, 0)
+constexpr int LBO_A = ROWS * 16;          // bytes between k-chunks of A
+constexpr int A_BYTES = 16 * LBO_A;       // 38 912 B per activation image
+constexpr int NTHREADS = 192;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
+    // cute::UMMA::SmemDescriptor: start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout_type=0 (no swizzle) [61,64)
+    return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) | ((uint64_t)(128u >> 4) << 32) | (1ull << 46);
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t *b, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *b, uint32_t parity) {
+    const uint32_t a = smem_u32(b);
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
+                 ::"r"(a), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *b, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+// arrive (release at cluster scope) on the barrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t *b, uint32_t rank) {
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(b)), "r"(rank));
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
+}
+__device__ __forceinline__ void st_cluster_v4(uint32_t local_addr, uint32_t rank, uint4 v) {
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_addr), "r"(rank));
+    asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ra), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+struct TowerArgs {
+    const uint8_t *boards;     // [n][96] side-to-move canonical boards
+    const __half *w1;          // [9][14][128] folded first conv
+    const float *bias;         // [1 + 2*blocks][128] folded biases (layer 0 = first conv)
+    const float *wh;           // [3][128] folded 1x1 head convs (policy 2 + value 1)
+    const float *bh;           // [3]
+    __half *hp;                // out [n][192]
+    float *hv;                 // out [n][96]
+    int n_pos;
+    int n_conv;                // 2 * res_block_nums
+};
+
+template <int CL>
+__global__ void __launch_bounds__(NTHREADS, 1) k_tower_small(const __grid_constant__ CUtensorMap wmap, TowerArgs a) {
+    constexpr int NC = 128 / CL;                           // output channels of this CTA
+    constexpr int STAGE_BYTES = NC * 256;                  // one tap of this CTA's weight slice: [16 k-chunks][NC rows][8 halves]
+    constexpr int S = CL == 1 ? 4 : (CL == 2 ? 8 : 16);    // ring depth
+    constexpr uint32_t TMEM_COLS = NC < 32 ? 32 : NC;
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char *bufX = smem, *bufY = smem + A_BYTES, *ring = smem + 2 * A_BYTES;
+    float *s_bias = reinterpret_cast<float *>(ring + S * STAGE_BYTES);      // [n_layers][NC] this CTA's slice
+    __shared__ __align__(8) uint64_t full[S], empty[S], accum_full, act_ready[2];   // act_ready ping-pongs by layer parity: arrivals of consecutive layers never mix
+    __shared__ uint32_t tmem_slot;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = CL == 1 ? 0u : cluster_rank();
+    const int pos = blockIdx.x / CL;
+    const int n_layers = 1 + a.n_conv;
+
+    // ---- one-time setup ----
+    for (int i = tid; i < 2 * A_BYTES / 16; i += NTHREADS) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);   // zero images (padding rows stay zero)
+    for (int i = tid; i < n_layers * NC; i += NTHREADS) s_bias[i] = a.bias[(i / NC) * 128 + rank * NC + (i % NC)];
+    if (tid == 0) {
+        for (int s = 0; s < S; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(&accum_full, 1);
+        mbar_init(&act_ready[0], CL * 4);
+        mbar_init(&act_ready[1], CL * 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (CL > 1) cluster_sync_all();                      // every CTA's barriers and zeroed images exist before anyone writes remotely
+    const uint32_t tmem = tmem_slot;
+
+    if (warp == 4) {
+        // ===== TMA producer: taps of all layers, in order, as fast as the ring frees up =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int L = 0; L < a.n_conv; L++) {
+                for (int t = 0; t < 9; t++) {
+                    mbar_wait(&empty[stage], phase ^ 1u);
+                    mbar_expect_tx(&full[stage], STAGE_BYTES);
+                    const int row = ((L * 9 + t) * CL + (int)rank) * NC;          // 256-byte rows of the weight blob
+                    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                                 ::"r"(smem_u32(ring + stage * STAGE_BYTES)), "l"(&wmap), "r"(0), "r"(row), "r"(smem_u32(&full[stage])) : "memory");
+                    if (++stage == S) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 5) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            // instruction descriptor: c_format F32 (1<<4), a/b F16 K-major, N>>3 at bit 17, M>>4 at bit 24
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(NC >> 3) << 17) | (8u << 24);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int L = 0; L < a.n_conv; L++) {
+                mbar_wait(&act_ready[L & 1], (uint32_t)((L >> 1) & 1));   // image L (this layer's input) is complete in OUR shared memory
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t abase = smem_u32((L & 1) ? bufY : bufX);          // conv1 of a block reads X, conv2 reads Y
+                for (int t = 0; t < 9; t++) {
+                    mbar_wait(&full[stage], phase);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const int shift = (t / 3 - 1) * 11 + (t % 3 - 1);            // tap (dr, df) = a row offset in the padded raster
+                    const uint32_t arow = abase + (uint32_t)((P0 + shift) * 16);
+                    const uint32_t bbase = smem_u32(ring + stage * STAGE_BYTES);
+#pragma unroll
+                    for (int kk = 0; kk < 8; kk++) {                             // 128 input channels = 8 x K16
+                        const uint64_t da = umma_desc(arow + kk * 2 * LBO_A, LBO_A);
+                        const uint64_t db = umma_desc(bbase + kk * 2 * (NC * 16), NC * 16);
+                        const uint32_t acc = (t | kk) ? 1u : 0u;
+                        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                                     "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                                     ::"r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+                    }
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&empty[stage])) : "memory");
+                    if (++stage == S) { stage = 0; phase ^= 1u; }
+                }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&accum_full)) : "memory");
+            }
+        }
+    } else {
+        // ===== epilogue warps: thread = MMA row j = raster row P0 + j =====
+        const int j = tid;                                   // 0..127
+        const int rr = j / 11, ff = j - rr * 11;
+        const bool cell = rr < 9 && ff < 10;                 // a real image cell (else padding: must be written as zero)
+        const uint32_t rowoff = (uint32_t)((P0 + j) * 16);
+        // ---- layer 0: conv3x3(14 -> 128) straight from the board bytes (one-hot input: a gather-add of weight rows) ----
+        {
+            float acc[NC];
+#pragma unroll
+            for (int c = 0; c < NC; c++) acc[c] = s_bias[c];
+            if (cell) {
+                const uint8_t *bd = a.boards + (size_t)pos * 96;
+#pragma unroll 1
+                for (int t = 0; t < 9; t++) {
+                    const int r2 = rr + t / 3 - 1, f2 = ff + t % 3 - 1;
+                    if (r2 < 0 || r2 >= 9 || f2 < 0 || f2 >= 10) continue;
+                    const int pc = __ldg(bd + r2 * 9 + f2);                        // the reference's cell <- s[rank*9+file]
+                    if (!pc) continue;
+                    const __half *wr = a.w1 + ((size_t)(t * 14 + pc - 1) * 128 + rank * NC);
+#pragma unroll
+                    for (int c8 = 0; c8 < NC / 8; c8++) {
+                        const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(wr) + c8);
+                        const __half2 *h2 = reinterpret_cast<const __half2 *>(&raw);
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            const float2 v = __half22float2(h2[k]);
+                            acc[c8 * 8 + 2 * k] += v.x;
+                            acc[c8 * 8 + 2 * k + 1] += v.y;
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int c8 = 0; c8 < NC / 8; c8++) {
+                uint4 o;
+                __half2 *oh = reinterpret_cast<__half2 *>(&o);
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    oh[k] = cell ? __floats2half2_rn(fmaxf(acc[c8 * 8 + 2 * k], 0.f), fmaxf(acc[c8 * 8 + 2 * k + 1], 0.f)) : __floats2half2_rn(0.f, 0.f);
+                const uint32_t dst = smem_u32(bufX) + (uint32_t)((rank * (NC / 8) + c8) * LBO_A) + rowoff;
+#pragma unroll
+                for (int q = 0; q < CL; q++) {
+                    if (CL == 1) *reinterpret_cast<uint4 *>(bufX + (c8 * LBO_A) + rowoff) = o;
+                    else st_cluster_v4(dst, (uint32_t)q, o);
+                }
+            }
+            asm volatile("fence.proxy.async;" ::: "memory");                       // generic-proxy writes -> visible to the tensor cores
+            __syncwarp();
+            if (lane == 0) {
+#pragma unroll
+                for (int q = 0; q < CL; q++) mbar_arrive_remote(&act_ready[0], (uint32_t)q);      // image 0
+            }
+        }
+        // ---- residual tower epilogues ----
+        uint32_t fphase = 0;
+        for (int L = 0; L < a.n_conv; L++) {
+            mbar_wait(&accum_full, fphase);
+            fphase ^= 1u;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const bool second = L & 1;                        // conv2 of a block: + skip (the block input, still in X), result back into X
+            unsigned char *dstbuf = second ? bufX : bufY;
+            const float *bl = s_bias + (1 + L) * NC;
+#pragma unroll
+            for (int c16 = 0; c16 < NC / 16; c16++) {
+                uint32_t v[16];
+                const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c16 * 16);
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                             "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                             : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                               "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                             : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int h8 = 0; h8 < 2; h8++) {
+                    const int c8 = c16 * 2 + h8;                                   // 8-channel chunk within this CTA's slice
+                    const uint32_t choff = (uint32_t)((rank * (NC / 8) + c8) * LBO_A) + rowoff;
+                    float f[8];
+#pragma unroll
+                    for (int k = 0; k < 8; k++) f[k] = __uint_as_float(v[h8 * 8 + k]) + bl[c8 * 8 + k];
+                    if (second) {
+                        const uint4 sk = *reinterpret_cast<const uint4 *>(bufX + choff);
+                        const __half2 *s2 = reinterpret_cast<const __half2 *>(&sk);
+#pragma unroll
+                        for (int k = 0; k < 4; k++) { const float2 s = __half22float2(s2[k]); f[2 * k] += s.x; f[2 * k + 1] += s.y; }
+                    }
+                    uint4 o;
+                    __half2 *oh = reinterpret_cast<__half2 *>(&o);
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                        oh[k] = cell ? __floats2half2_rn(fmaxf(f[2 * k], 0.f), fmaxf(f[2 * k + 1], 0.f)) : __floats2half2_rn(0.f, 0.f);
+                    if (CL == 1) *reinterpret_cast<uint4 *>(dstbuf + choff) = o;
+                    else {
+#pragma unroll
+                        for (int q = 0; q < CL; q++) st_cluster_v4(smem_u32(dstbuf) + choff, (uint32_t)q, o);
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");       // our TMEM reads are done before the next layer's MMAs may overwrite
+            asm volatile("fence.proxy.async;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+#pragma unroll
+                for (int q = 0; q < CL; q++) mbar_arrive_remote(&act_ready[(L + 1) & 1], (uint32_t)q);   // image L + 1
+            }
+        }
+        // ---- heads: conv1x1 (128 -> 2 policy + 1 value) + bias + ReLU on the final image (in X), CTA 0 writes ----
+        {
+            mbar_wait(&act_ready[a.n_conv & 1], (uint32_t)((a.n_conv >> 1) & 1));       // the final image (index n_conv) is complete
+            if (rank == 0 && cell) {
+                float s0 = a.bh[0], s1 = a.bh[1], s2 = a.bh[2];
+#pragma unroll 4
+                for (int c8 = 0; c8 < 16; c8++) {
+                    const uint4 raw = *reinterpret_cast<const uint4 *>(bufX + c8 * LBO_A + rowoff);
+                    const __half2 *h2 = reinterpret_cast<const __half2 *>(&raw);
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const float2 x = __half22float2(h2[k]);
+                        const int c = c8 * 8 + 2 * k;
+                        s0 += x.x * __ldg(a.wh + c) + x.y * __ldg(a.wh + c + 1);
+                        s1 += x.x * __ldg(a.wh + 128 + c) + x.y * __ldg(a.wh + 128 + c + 1);
+                        s2 += x.x * __ldg(a.wh + 256 + c) + x.y * __ldg(a.wh + 256 + c + 1);
+                    }
+                }
+                const int ci = rr * 10 + ff;                                       // flatten order of tf.reshape on NHWC: cell*2 + c
+                *reinterpret_cast<__half2 *>(a.hp + (size_t)pos * 192 + ci * 2) = __floats2half2_rn(fmaxf(s0, 0.f), fmaxf(s1, 0.f));
+                a.hv[(size_t)pos * 96 + ci] = fmaxf(s2, 0.f);
+            }
+            if (rank == 0 && j < 12) a.hp[(size_t)pos * 192 + 180 + j] = __float2half(0.f);   // K padding of the policy GEMM
+        }
+    }
+    // ---- teardown: nobody leaves while a peer may still write into its shared memory ----
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (CL > 1) cluster_sync_all();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS));
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return nullptr;
+        fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+template <int CL>
+int launch_tower(const CUtensorMap &map, const TowerArgs &a, cudaStream_t st) {
+    constexpr int NC = 128 / CL, S = CL == 1 ? 4 : (CL == 2 ? 8 : 16);
+    const int n_layers = 1 + a.n_conv;
+    const size_t smem = 2 * (size_t)A_BYTES + (size_t)S * NC * 256 + (size_t)n_layers * NC * 4;
+    if (cudaFuncSetAttribute(k_tower_small<CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return CZ_ECUDA;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(a.n_pos * CL));
+    cfg.blockDim = dim3(NTHREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, k_tower_small<CL>, map, a) == cudaSuccess ? CZ_OK : CZ_ECUDA;
+}
+
+}  // namespace
+
+extern "C" {
+
+// Bytes of the weight blob cz_net_tower_small expects for `n_conv` 3x3 convolutions (independent of the cluster size).
+int64_t cz_net_tower_blob_bytes(int n_conv) { return (int64_t)n_conv * 9 * 128 * 256; }
+
+int cz_net_tower_small(const uint8_t *canon_boards, int n_pos, int cluster, int n_conv, const void *w1, const void *wblob, const float *bias,
+                       const float *wh, const float *bh, void *hp, float *hv, void *stream) {
+    if (!canon_boards || !w1 || !wblob || !bias || !wh || !bh || !hp || !hv || n_pos <= 0 || n_conv <= 0 || (n_conv & 1)) return CZ_EINVAL;
+    if (cluster != 1 && cluster != 2 && cluster != 4 && cluster != 8) return CZ_EINVAL;
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) return CZ_ECUDA;
+    // the blob as a 2-D tensor of 256-byte rows: [n_conv * 9 * 128 rows][128 halves]; one box = one tap of one CTA's slice
+    CUtensorMap map;
+    const cuuint64_t gdim[2] = {128, (cuuint64_t)n_conv * 9 * 128};
+    const cuuint64_t gstride[1] = {256};
+    const cuuint32_t box[2] = {128, (cuuint32_t)(128 / cluster)};
+    const cuuint32_t estr[2] = {1, 1};
+    if (enc(&map, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void *>(wblob), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return CZ_ECUDA;
+    TowerArgs a;
+    a.boards = canon_boards; a.w1 = (const __half *)w1; a.bias = bias; a.wh = wh; a.bh = bh; a.hp = (__half *)hp; a.hv = hv;
+    a.n_pos = n_pos; a.n_conv = n_conv;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (cluster) {
+        case 1: return launch_tower<1>(map, a, st);
+        case 2: return launch_tower<2>(map, a, st);
+        case 4: return launch_tower<4>(map, a, st);
+        default: return launch_tower<8>(map, a, st);
+    }
+}
+
+}  // extern "C"

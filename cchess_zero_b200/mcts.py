@@ -6,6 +6,7 @@ touch (`root.child[label].N/.Q`, `Q(move)`, `update_tree`, `reload`, `forward`, 
 Semantics: search_threads = 1 of the reference whatever `search_threads`
 is passed -- one playout at a time per tree is the deterministic schedule; concurrency comes from
 running thousands of trees per GPU (selfplay.SelfPlay), not from coroutines inside one tree."""
+import os
 from collections import OrderedDict
 
 import numpy as np
@@ -74,7 +75,9 @@ class MCTS_tree(object):
         if owner is not None and hasattr(owner, "native_plan") and getattr(owner, "precision", "") == "fp16":
             # the evaluator is this package's network: stay on the device (board bytes -> cz_net kernels -> tower) and
             # replay one CUDA graph per playout
-            self._plan = owner.native_plan(K)
+            # (<= 16 rows per call: the one-launch cluster trunk of csrc/cz_tower.cu; CCHESS_SMALL_TOWER=0 selects the library trunk)
+            small = K <= 16 and hasattr(owner, "small_plan") and os.environ.get("CCHESS_SMALL_TOWER", "1") != "0"
+            self._plan = owner.small_plan(K) if small else owner.native_plan(K)
             self._nn_in = self._plan.make_input(K)
             self._dev_forward = lambda x, lo, v: self._plan(x, lo, v)
         else:

@@ -307,6 +307,88 @@ class NativePlan:
         return None
 
 
+class SmallTowerPlan:
+    """fp16 plan for a FEW positions (play mode, single-tree search; BASELINE config 5): the whole convolutional trunk runs in
+    ONE launch of csrc/cz_tower.cu (a thread-block cluster per position, activations resident in shared memory, weights streamed
+    by TMA, tcgen05.mma into TMEM), followed by the value MLP || policy FC kernels of csrc/cz_net.cu:
+        board bytes --cz_net_tower_small--> head features --cz_net_heads_fc--> logits, value            (3 kernels per evaluation)
+    Same input / output contract as NativePlan (uint8 [B,96] canonical boards in, float32 logits / value written in place)."""
+
+    precision = "fp16"
+    dtype = torch.uint8
+    first_conv = "tower"
+
+    def __init__(self, net, max_batch, cluster=None, owner=None):
+        import ctypes as C
+        from ._lib import lib
+        self._C, self._lib = C, lib()
+        self.cluster = int(cluster or os.environ.get("CCHESS_TOWER_CLUSTER", "8"))
+        assert self.cluster in (1, 2, 4, 8)
+        self._base = InferencePlan(net, "fp16", owner=owner)
+        self.fused = True
+        self.net, self.owner, self.version = net, owner, self._base.version
+        self.n_conv = 2 * len(self._base.blocks)
+        for k, v in self._derive().items():
+            setattr(self, k, v)
+        dev = self._base.w_in[0].device
+        self.max_batch = max_batch
+        self.hp = torch.zeros((max_batch, 192), dtype=torch.float16, device=dev)
+        self.hv = torch.zeros((max_batch, 96), dtype=torch.float32, device=dev)
+
+    def _derive(self):
+        net, base, CL = self.net, self._base, self.cluster
+        NC = 128 // CL
+        dev = base.w_in[0].device
+        with torch.no_grad():
+            w, b = base.w_in
+            w1 = w.float().permute(2, 3, 1, 0).reshape(9, 14, 128).to(torch.float16).contiguous()
+            convs = [c for blk in base.blocks for c in blk]                       # (w [128,128,3,3] fp16, b [128]) in execution order
+            bias = torch.stack([b.float()] + [cb.float() for _, cb in convs]).contiguous()
+            # [conv][tap][rank][k-chunk 16][out channel NC][8 in channels]: the shared-memory image of one TMA stage, see cz_tower.cu
+            blob = torch.stack([cw.permute(2, 3, 0, 1).reshape(9, CL, NC, 16, 8).permute(0, 1, 3, 2, 4) for cw, _ in convs]).to(torch.float16).contiguous()
+            wh, bh = base.w_head
+            wp = torch.zeros((2112, 192), dtype=torch.float16, device=dev)
+            wp[:NLABEL, :180] = net.p_fc.weight.detach().to(torch.float16)
+            bp = torch.zeros((2112,), dtype=torch.float32, device=dev)
+            bp[:NLABEL] = net.p_fc.bias.detach().float()
+            return dict(w1=w1, bias=bias, blob=blob, wh=wh.float().reshape(3, 128).contiguous(), bh=bh.float().contiguous(),
+                        w1t=net.v_fc1.weight.detach().float().t().contiguous(), bv1=net.v_fc1.bias.detach().float().contiguous(),
+                        w2=net.v_fc2.weight.detach().float().reshape(256).contiguous(),
+                        b2t=net.v_fc2.bias.detach().float().reshape(1).contiguous(), wp=wp, bp=bp)
+
+    def refresh(self):
+        self._base.refresh()
+        with torch.no_grad():
+            for k, v in self._derive().items():
+                getattr(self, k).copy_(v)
+        self.version = self._base.version
+
+    def refresh_if_stale(self):
+        if self.owner is not None and self.owner.weights_version != self.version:
+            self.refresh()
+            return True
+        return False
+
+    def make_input(self, B):
+        return torch.zeros((B, 96), dtype=torch.uint8, device=self.hp.device)
+
+    @torch.no_grad()
+    def __call__(self, boards, logits_out, value_out):
+        B = boards.shape[0]
+        assert B <= self.max_batch and boards.dtype == torch.uint8 and logits_out.dtype == torch.float32
+        assert self.blob.numel() * 2 == self._lib.cz_net_tower_blob_bytes(self.n_conv)
+        st = self._C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        rc = self._lib.cz_net_tower_small(boards.data_ptr(), B, self.cluster, self.n_conv, self.w1.data_ptr(), self.blob.data_ptr(), self.bias.data_ptr(),
+                                          self.wh.data_ptr(), self.bh.data_ptr(), self.hp.data_ptr(), self.hv.data_ptr(), st)
+        if rc:
+            raise RuntimeError("cz_net_tower_small failed (%d)" % rc)
+        rc = self._lib.cz_net_heads_fc(self.hp.data_ptr(), self.hv.data_ptr(), B, self.w1t.data_ptr(), self.bv1.data_ptr(), self.w2.data_ptr(),
+                                       self.b2t.data_ptr(), self.wp.data_ptr(), self.bp.data_ptr(), logits_out.data_ptr(), value_out.data_ptr(), st)
+        if rc:
+            raise RuntimeError("cz_net_heads_fc failed (%d)" % rc)
+        return None
+
+
 class _Tf32:
     def __init__(self, on):
         self.on = on
@@ -397,6 +479,11 @@ class policy_value_network(object):
         """fp16 plan with the hand-written first-conv / head kernels (engine path); see NativePlan."""
         self.net.eval()
         return NativePlan(self.net, max_batch, first_conv, owner=self)
+
+    def small_plan(self, max_batch, cluster=None):
+        """fp16 plan for <= 16 positions per call: the whole trunk in one cluster kernel (csrc/cz_tower.cu); see SmallTowerPlan."""
+        self.net.eval()
+        return SmallTowerPlan(self.net, max_batch, cluster, owner=self)
 
     @property
     def nn_dtype(self):

@@ -187,6 +187,25 @@ int cz_net_first_conv_tc(const uint8_t *canon_boards, int B, const void *w_umma,
 int cz_net_heads(const void *x, int B, const float *wh, const float *bh, const float *w1t, const float *b1, const float *w2, const float *b2,
                  const void *wp, const float *bp, void *hp_scratch, float *hv_scratch, float *logits, float *value, void *stream);
 
+/* The second half of cz_net_heads alone: value MLP and policy FC on head features that are already computed
+ * (hp fp16 [B][192], hv f32 [B][96]) -- what follows cz_net_tower_small. */
+int cz_net_heads_fc(const void *hp, const float *hv, int B, const float *w1t, const float *b1, const float *w2, const float *b2,
+                    const void *wp, const float *bp, float *logits, float *value, void *stream);
+
+/* ---- the whole convolutional trunk for a FEW positions in one launch (play mode / single-tree search, BASELINE config 5) ----
+ * policy_value_network.py:45-74, 151-162 with batch norm folded: first conv3x3(14->128) from the canonical board bytes,
+ * n_conv = 2*res_block_nums 3x3 convolutions (residual blocks), the two 1x1 head convolutions; output = the head features
+ * hp fp16 [n_pos][192] / hv f32 [n_pos][96] that cz_net_heads_fc turns into logits and value.
+ * One thread-block cluster of `cluster` (1, 2, 4, 8) CTAs per position: activations stay in shared memory (UMMA K-major layout,
+ * 3x3 taps = descriptor start offsets), weights stream from L2 by TMA, tcgen05.mma accumulates in TMEM, epilogues exchange
+ * channel slices through distributed shared memory.  See csrc/cz_tower.cu.
+ *   w1     dev fp16 [9][14][128]   (as cz_net_first_conv);  bias dev f32 [1 + n_conv][128];  wh f32 [3][128], bh f32 [3]
+ *   wblob  dev fp16, cz_net_tower_blob_bytes(n_conv) bytes, arranged for THIS cluster size:
+ *          [conv][tap 9][rank `cluster`][k-chunk 16][out channel 128/cluster][8 in channels]   (in channel = 8*chunk + i) */
+int64_t cz_net_tower_blob_bytes(int n_conv);
+int cz_net_tower_small(const uint8_t *canon_boards, int n_pos, int cluster, int n_conv, const void *w1, const void *wblob, const float *bias,
+                       const float *wh, const float *bh, void *hp, float *hv, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

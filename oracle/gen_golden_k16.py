@@ -1,0 +1,84 @@
+"""Generates tests/golden/k16_stats.json.gz by RUNNING THE UNMODIFIED REFERENCE at its default search_threads=16.
+
+TEST INFRASTRUCTURE ONLY.  Usage (needs /root/reference or the staged copy; ~6 minutes on one core):
+    python oracle/gen_golden_k16.py
+
+Why a statistical fixture: with search_threads > 1 the reference's visit counts are defined by its asyncio / uvloop event loop
+-- coroutines that find their leaf `now_expanding` spin on `asyncio.sleep(1e-4)` (a FIFO yield under uvloop) while
+`prediction_worker` sleeps on a 1 ms wall-clock timer (main.py:354-355, 442-453), so whether a freshly admitted search descends
+before or after the spinners depends on the phase of that timer (oracle/probe_schedule.py: search_threads=2 gives different
+trees for evaluator latencies of 0 and 1 ms).  A bit-exact target therefore exists only for search_threads=1 (pinned elsewhere).
+What CAN be pinned at K=16 is the distribution: this file records, for a few hundred random-play positions, the root visit
+counts of the reference at K=16 (run twice, with 0 and 2 ms of injected evaluator latency, to measure the reference's own
+run-to-run spread) and at K=1; tests/test_gpu_k16_stats.py compares the engine's searches with them (move agreement, KL).
+"""
+import gzip
+import json
+import os
+import random
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import ref_harness as H  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "k16_stats.json.gz")
+START = "RNBAKABNR/9/1C5C1/P1P1P1P1P/9/9/p1p1p1p1p/1c5c1/9/rnbakabnr"
+NET, PLAYOUTS, N_POS = "hash_pos", 200, 240
+
+
+def positions(ref, n, seed=20260924):
+    """Random-play positions with their side to move and no-capture counter, plies spread over 0..80."""
+    rng = random.Random(seed)
+    out = []
+    while len(out) < n:
+        state, player, rr = START, "w", 0
+        stop = rng.randrange(0, 81)
+        for ply in range(stop):
+            moves = ref.GameBoard.get_legal_moves(state, player)
+            nxt = ref.GameBoard.sim_do_action(rng.choice(moves), state)
+            rr = rr + 1 if ref.is_kill_move(state, nxt) == 0 else 0
+            state, player = nxt, ("b" if player == "w" else "w")
+            if "K" not in state or "k" not in state or rr >= 59:
+                break
+        if "K" in state and "k" in state and rr < 50:
+            out.append((state, player, rr))
+    return out
+
+
+def search(ref, state, player, rr, K, delay=0.0):
+    base = H.FAKE_NETS[NET]
+
+    def fwd(x):
+        if delay:
+            time.sleep(delay)
+        return base(x)
+    t = H.make_mcts(fwd, K, state)
+    with np.errstate(all="ignore"):
+        t.main(state, player, rr, PLAYOUTS)
+    return [a for a in t.root.child], [int(c.N) for c in t.root.child.values()]
+
+
+def main():
+    ref = H.load_reference()
+    recs, same = [], 0
+    t0 = time.time()
+    for i, (state, player, rr) in enumerate(positions(ref, N_POS)):
+        moves, v16 = search(ref, state, player, rr, 16)
+        _, v16b = search(ref, state, player, rr, 16, delay=0.002)
+        _, v1 = search(ref, state, player, rr, 1)
+        same += int(v16 == v16b)
+        recs.append(dict(state=state, player=player, rr=rr, moves=" ".join(moves), k16=v16, k16_delay2ms=v16b, k1=v1))
+        if i % 20 == 0:
+            print(i, "%.0fs" % (time.time() - t0), "self-consistent so far:", same, flush=True)
+    out = dict(net=NET, playouts=PLAYOUTS, n=len(recs), reference_k16_identical_under_2ms_latency=same, records=recs,
+               how="oracle/gen_golden_k16.py: unmodified reference MCTS_tree.main, uvloop, search_threads 16 / 16 (+2 ms evaluator latency) / 1")
+    with gzip.open(OUT, "wb") as f:
+        f.write(json.dumps(out).encode())
+    print("wrote", OUT, "reference K=16 reproduced itself on %d / %d positions" % (same, len(recs)))
+
+
+if __name__ == "__main__":
+    main()

@@ -250,3 +250,37 @@ def test_data_parallel_train_step_over_nccl(tmp_path):
                         "--master-port", "29541", str(script)], capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "NCCL_DP_OK 2" in r.stdout
+
+
+@pytest.mark.parametrize("blocks,cluster,npos", [(2, 1, 1), (2, 8, 3), (7, 1, 2), (7, 2, 1), (7, 4, 5), (7, 8, 16), (19, 8, 1)])
+def test_small_tower_cluster_kernel_matches_library_plan_and_fp64(blocks, cluster, npos):
+    """csrc/cz_tower.cu (whole trunk in one launch: TMA-streamed weights, tcgen05.mma with tap-shifted A descriptors, TMEM epilogues
+    exchanging channel slices through distributed shared memory) against the cuDNN plan and an fp64 evaluation, for every cluster size."""
+    from cchess_zero_b200.net import NativePlan, PolicyValueNet, SmallTowerPlan
+    torch.manual_seed(1)
+    net = PolicyValueNet(blocks).eval()
+    with torch.no_grad():   # non-trivial biases / BN statistics so that every folded term is exercised
+        for m in net.modules():
+            if isinstance(m, (torch.nn.Conv2d, torch.nn.Linear)):
+                m.bias.uniform_(-0.1, 0.1)
+            if hasattr(m, "running_var"):
+                m.running_var.uniform_(0.5, 1.5); m.running_mean.uniform_(-0.2, 0.2)
+    x, canon = _positions(npos, seed=5 + npos)
+    with torch.no_grad():
+        rl, rv = net.double()(torch.from_numpy(x).double())
+    net = net.float().cuda().to(memory_format=torch.channels_last)
+    boards = torch.from_numpy(canon).cuda()
+    lo = torch.zeros((npos, 2086), device="cuda"); vo = torch.zeros((npos,), device="cuda")
+    lo2 = torch.zeros_like(lo); vo2 = torch.zeros_like(vo)
+    small = SmallTowerPlan(net, 16, cluster)
+    small(boards, lo, vo)
+    NativePlan(net, 16)(boards, lo2, vo2)
+    torch.cuda.synchronize()
+    e_small = max((lo.double().cpu() - rl).abs().max().item(), (vo.double().cpu() - rv.reshape(-1)).abs().max().item())
+    e_lib = max((lo2.double().cpu() - rl).abs().max().item(), (vo2.double().cpu() - rv.reshape(-1)).abs().max().item())
+    print("max abs err vs fp64: cluster trunk (CL=%d) %.3g, library trunk %.3g" % (cluster, e_small, e_lib))
+    assert e_small < (1e-3 if blocks <= 7 else 2e-3)
+    assert (lo - lo2).abs().max().item() < 2e-3 and (vo - vo2).abs().max().item() < 2e-3
+    small(boards, lo2, vo2)                               # run-to-run identical
+    torch.cuda.synchronize()
+    assert torch.equal(lo, lo2) and torch.equal(vo, vo2)
