@@ -46,7 +46,16 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_b
 __device__ __forceinline__ void mbar_init(uint64_t *b, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count));
 }
+// wait on a barrier whose arrivals all come from THIS CTA (threads, tcgen05.commit, TMA): CTA-scope acquire
 __device__ __forceinline__ void mbar_wait(uint64_t *b, uint32_t parity) {
+    const uint32_t a = smem_u32(b);
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
+                 ::"r"(a), "r"(parity) : "memory");
+}
+// wait on a barrier that peer CTAs arrive on after writing OUR shared memory: cluster-scope acquire.  ptxas turns that into an
+// L1 invalidate (CCTL.IVALL) per successful wait -- measured as THE dominant stall when every waiter did it -- so exactly one
+// thread per CTA and layer waits this way; everybody else is ordered behind it with CTA-scope synchronisation.
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t *b, uint32_t parity) {
     const uint32_t a = smem_u32(b);
     asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
                  ::"r"(a), "r"(parity) : "memory");
@@ -54,11 +63,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t *b, uint32_t parity) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *b, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
 }
-// arrive (release at cluster scope) on the barrier at the same shared-memory offset in CTA `rank` of the cluster
+// relaxed arrive on the barrier at the same shared-memory offset in CTA `rank`; the caller has issued fence.acq_rel.cluster
 __device__ __forceinline__ void mbar_arrive_remote(uint64_t *b, uint32_t rank) {
     uint32_t ra;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(b)), "r"(rank));
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
+}
+// publish this warp's image writes (generic proxy, local + remote shared memory) and signal every CTA of the cluster
+template <int CL>
+__device__ __forceinline__ void publish_image(uint64_t *bar, int lane) {
+    asm volatile("fence.proxy.async;" ::: "memory");                     // generic-proxy writes -> visible to the tensor cores (async proxy)
+    __syncwarp();
+    if (lane == 0) {
+        if (CL > 1) asm volatile("fence.acq_rel.cluster;" ::: "memory"); // one release for the whole warp's stores
+#pragma unroll
+        for (int q = 0; q < CL; q++) mbar_arrive_remote(bar, (uint32_t)q);
+    }
 }
 __device__ __forceinline__ void st_cluster_v4(uint32_t local_addr, uint32_t rank, uint4 v) {
     uint32_t ra;
@@ -147,7 +167,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tower_small(const __grid_consta
             int stage = 0;
             uint32_t phase = 0;
             for (int L = 0; L < a.n_conv; L++) {
-                mbar_wait(&act_ready[L & 1], (uint32_t)((L >> 1) & 1));   // image L (this layer's input) is complete in OUR shared memory
+                mbar_wait_cluster(&act_ready[L & 1], (uint32_t)((L >> 1) & 1));   // image L (this layer's input) is complete in OUR shared memory
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t abase = smem_u32((L & 1) ? bufY : bufX);          // conv1 of a block reads X, conv2 reads Y
                 for (int t = 0; t < 9; t++) {
@@ -218,12 +238,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tower_small(const __grid_consta
                     else st_cluster_v4(dst, (uint32_t)q, o);
                 }
             }
-            asm volatile("fence.proxy.async;" ::: "memory");                       // generic-proxy writes -> visible to the tensor cores
-            __syncwarp();
-            if (lane == 0) {
-#pragma unroll
-                for (int q = 0; q < CL; q++) mbar_arrive_remote(&act_ready[0], (uint32_t)q);      // image 0
-            }
+            publish_image<CL>(&act_ready[0], lane);                               // image 0
         }
         // ---- residual tower epilogues ----
         uint32_t fphase = 0;
@@ -270,16 +285,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tower_small(const __grid_consta
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");       // our TMEM reads are done before the next layer's MMAs may overwrite
-            asm volatile("fence.proxy.async;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) {
-#pragma unroll
-                for (int q = 0; q < CL; q++) mbar_arrive_remote(&act_ready[(L + 1) & 1], (uint32_t)q);   // image L + 1
-            }
+            publish_image<CL>(&act_ready[(L + 1) & 1], lane);                      // image L + 1
         }
         // ---- heads: conv1x1 (128 -> 2 policy + 1 value) + bias + ReLU on the final image (in X), CTA 0 writes ----
         {
-            mbar_wait(&act_ready[a.n_conv & 1], (uint32_t)((a.n_conv >> 1) & 1));       // the final image (index n_conv) is complete
+            if (tid == 0) mbar_wait_cluster(&act_ready[a.n_conv & 1], (uint32_t)((a.n_conv >> 1) & 1));   // the final image (index n_conv) is complete
+            asm volatile("bar.sync 1, 128;" ::: "memory");                         // the four epilogue warps, ordered behind thread 0's cluster-scope acquire
             if (rank == 0 && cell) {
                 float s0 = a.bh[0], s1 = a.bh[1], s2 = a.bh[2];
 #pragma unroll 4

@@ -39,6 +39,7 @@ def lib():
         L.co_tree_search.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, FWD_FN, C.c_void_p]
         L.co_tree_search_fake.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
         L.co_tree_search_multi.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.co_tree_search_fifo.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
         L.co_tree_root_children.argtypes = [C.c_void_p] + [C.c_void_p] * 5
         L.co_tree_update.argtypes = [C.c_void_p, C.c_int]
         L.co_tree_root_board.argtypes = [C.c_void_p, C.c_void_p]
@@ -172,6 +173,10 @@ class Tree:
     def search_multi(self, side, rr, playouts, K, net):
         """cchess_zero_b200's own leaf-parallel schedule (K leaves per wave), serial specification; see cchess_oracle.c."""
         return lib().co_tree_search_multi(self.h, side, rr, playouts, int(K), NET_IDS[net] if isinstance(net, str) else int(net))
+
+    def search_fifo(self, side, rr, playouts, K, net):
+        """The reference's search_threads = K schedule in canonical (deterministic FIFO) form; see cchess_oracle.c / detloop.py."""
+        return lib().co_tree_search_fifo(self.h, side, rr, playouts, int(K), NET_IDS[net] if isinstance(net, str) else int(net))
 
     def root_children(self):
         mv = np.zeros(136, dtype=np.uint16)

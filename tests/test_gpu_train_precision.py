@@ -279,8 +279,8 @@ def test_small_tower_cluster_kernel_matches_library_plan_and_fp64(blocks, cluste
     e_small = max((lo.double().cpu() - rl).abs().max().item(), (vo.double().cpu() - rv.reshape(-1)).abs().max().item())
     e_lib = max((lo2.double().cpu() - rl).abs().max().item(), (vo2.double().cpu() - rv.reshape(-1)).abs().max().item())
     print("max abs err vs fp64: cluster trunk (CL=%d) %.3g, library trunk %.3g" % (cluster, e_small, e_lib))
-    assert e_small < (1e-3 if blocks <= 7 else 2e-3)
-    assert (lo - lo2).abs().max().item() < 2e-3 and (vo - vo2).abs().max().item() < 2e-3
+    assert e_small < max(1e-3, 1.25 * e_lib)              # as accurate as the library trunk (same fp16 arithmetic, fp32 accumulation)
+    assert (lo - lo2).abs().max().item() < max(2e-3, 2 * e_lib) and (vo - vo2).abs().max().item() < max(2e-3, 2 * e_lib)
     small(boards, lo2, vo2)                               # run-to-run identical
     torch.cuda.synchronize()
     assert torch.equal(lo, lo2) and torch.equal(vo, vo2)
