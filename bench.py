@@ -405,9 +405,13 @@ def leg_config5(a, local_rank, pv):
     (main.py:1281-1284) -- then perform_AI -> select_move('mcts') (another `playouts` playouts on the re-used root)."""
     from cchess_zero_b200.selfplay import cchess_main
     out = {}
-    for K, moves in ((1, 12), (8, 24)):
+    modes = (("search_threads_1", 1, 1, 12, "one playout at a time: bit-exact with the reference at search_threads=1"),
+             ("search_threads_16", 16, 1, 24, "the reference's DEFAULT coroutine schedule (search_threads=16) in canonical FIFO form: "
+                                              "identical visit counts wherever the reference reproduces itself; up to 16 leaves per network call"),
+             ("leaf_parallel_8", 1, 8, 24, "the package's own virtual-loss batching of 8 leaves per network call (deterministic, not the reference's visit counts)"))
+    for name, T, K, moves, sem in modes:
         with contextlib.redirect_stdout(io.StringIO()):
-            m = cchess_main(playout=a.playouts, in_search_threads=16, network=pv, exploration=False, log_file=False, leaf_parallel=K)
+            m = cchess_main(playout=a.playouts, in_search_threads=T, network=pv, exploration=False, log_file=False, leaf_parallel=K)
         np.random.seed(0)
         lat, hint_s = [], []
         with contextlib.redirect_stdout(io.StringIO()):
@@ -422,10 +426,9 @@ def leg_config5(a, local_rank, pv):
                 if m.check_end()[0]:
                     m.game_borad.reload(); m.mcts.reload()
         lat = np.array(lat)
-        out["leaf_parallel_%d" % K] = dict(
+        out[name] = dict(
             p50_s=float(np.median(lat)), p95_s=float(np.percentile(lat, 95)), mean_s=float(lat.mean()), max_s=float(lat.max()), moves=len(lat),
-            get_hint_share=float(np.sum(hint_s) / np.sum(lat)), playouts_per_s=a.playouts / float(np.median(lat)),
-            semantics="bit-exact search_threads=1 schedule" if K == 1 else "virtual-loss batching of %d leaves per network call (deterministic, not the K=1 visit counts)" % K)
+            get_hint_share=float(np.sum(hint_s) / np.sum(lat)), playouts_per_s=a.playouts / float(np.median(lat)), semantics=sem)
         m.mcts.engine.close()
     out["config"] = "1 game, mcts vs mcts, %d playouts, res_block_nums=%d, exploration off, per move get_hint('mcts') + select_move('mcts')" % (a.playouts, a.res_blocks)
     return out

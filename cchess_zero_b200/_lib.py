@@ -32,6 +32,8 @@ def _sig(L):
     L.cz_encode_dev.argtypes = [vp, vp, i32, vp, i32, vp]
     L.cz_engine_create.argtypes = [i32, i64, i32, C.POINTER(vp)]
     L.cz_engine_create_ex.argtypes = [i32, i64, i32, i32, C.POINTER(vp)]
+    L.cz_engine_create_fifo.argtypes = [i32, i64, i32, i32, C.POINTER(vp)]
+    L.cz_engine_is_fifo.argtypes = [vp]
     L.cz_engine_leaves.argtypes = [vp]
     L.cz_engine_destroy.argtypes = [vp]
     L.cz_engine_n_games.argtypes = [vp]

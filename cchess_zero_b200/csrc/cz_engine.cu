@@ -119,6 +119,8 @@ struct Dev {
     long long A;
     int K;                            // leaves per game per wave (1 = the reference's search_threads=1 schedule)
     int hash_on;                      // maintain Zobrist keys of the pending leaves (board hashing; off by default)
+    int narr;                         // arrays per node block: 5 (P W N META CHILD), 6 in FIFO mode (+ stored Q, main.py:193)
+    uint32_t *fifo;                   // [B][FW] event-loop state of the search_threads = K schedule (k_wave_fifo); NULL otherwise
     uint32_t *hdr;                    // [B][HW]
     uint8_t *root_board;              // [B][96]
     uint8_t *leaf_board;              // [B][96]
@@ -210,7 +212,7 @@ __device__ int warp_leaf_moves(const Dev &E, WarpSmem &S, uint32_t &errf, int la
 __device__ int expand_reserve(const Dev &E, WarpSmem &S, uint32_t &alloc, uint32_t &base, uint32_t &errf, int lane) {
     uint32_t ef = 0;
     const int n = warp_leaf_moves(E, S, ef, lane);
-    const uint32_t cs = (uint32_t)((n + 7) & ~7), size = HDR + 5 * cs;
+    const uint32_t cs = (uint32_t)((n + 7) & ~7), size = HDR + (uint32_t)E.narr * cs;
     base = alloc;
     if ((long long)base + size > E.A) ef |= CZ_ERR_ARENA;
     ef = __reduce_or_sync(CZ_FULL, ef);
@@ -220,7 +222,7 @@ __device__ int expand_reserve(const Dev &E, WarpSmem &S, uint32_t &alloc, uint32
     return n;
 }
 // 2: prior gather (lg = this leaf's logits row), serial float32 normalisation, block write
-__device__ void expand_write(uint32_t *ar, WarpSmem &S, const float *lg, int n, uint32_t base, int lane) {
+__device__ void expand_write(uint32_t *ar, WarpSmem &S, const float *lg, int n, uint32_t base, int lane, bool with_q = false) {
     for (int i = lane; i < n; i += 32) S.ps[i] = __ldg(lg + S.li[i]);
     __syncwarp();
     const uint32_t cs = (uint32_t)((n + 7) & ~7);
@@ -236,6 +238,7 @@ __device__ void expand_write(uint32_t *ar, WarpSmem &S, const float *lg, int n, 
         blk[HDR + 2 * cs + i] = 0u;                                            // N = 0
         blk[HDR + 3 * cs + i] = live ? (uint32_t)S.moves[i] : 0u;              // META: move, no grandchildren yet
         blk[HDR + 4 * cs + i] = NONE;
+        if (with_q) blk[HDR + 5 * cs + i] = 0u;                                // stored Q = 0 (leaf_node.__init__, main.py:96)
     }
     __syncwarp();
 }
@@ -284,8 +287,9 @@ __device__ void store_leaf_at(uint8_t *leaf_board, WarpSmem &S, int side, T *nn_
 
 // The PUCT inputs of one node block in registers: lane l holds children l, l+32, l+64, l+96.
 struct BlockRegs {
-    uint32_t P[4], W[4], N[4], meta[4], child[4];
+    uint32_t P[4], W[4], N[4], meta[4], child[4], Q[4];
 };
+template <bool WITH_Q = false>
 __device__ __forceinline__ void load_block(const uint32_t *ar, uint32_t base, int cnt, int lane, BlockRegs &R) {
     const uint32_t cs = (uint32_t)((cnt + 7) & ~7);
     const uint32_t *blk = ar + base + HDR;
@@ -294,6 +298,7 @@ __device__ __forceinline__ void load_block(const uint32_t *ar, uint32_t base, in
         const int i = lane + 32 * k;
         if (i < cnt) {
             R.P[k] = blk[i]; R.W[k] = blk[cs + i]; R.N[k] = blk[2 * cs + i]; R.meta[k] = blk[3 * cs + i]; R.child[k] = blk[4 * cs + i];
+            if (WITH_Q) R.Q[k] = blk[5 * cs + i];
         }
     }
 }
@@ -301,8 +306,10 @@ __device__ __forceinline__ uint32_t pick(const uint32_t (&a)[4], int k) { return
 
 // select_new (main.py:158-159) over get_Q_plus_U_new (108-116) on a block held in registers: index of the FIRST maximum.
 // MULTI: Q is taken from the loss-free statistics (in-flight count in META bits 24-30), see k_wave_multi.
-template <bool MULTI>
+// MODE 2 (search_threads = K schedule): the STORED Q of the last back_up_value, exactly what get_Q_plus_U_new reads (main.py:116).
+template <int MODE>
 __device__ __forceinline__ uint32_t select_child(const BlockRegs &R, int cnt, int parentN, int lane) {
+    constexpr bool MULTI = MODE == 1;
     const double sq = __dsqrt_rn((double)parentN);
     double bs = 0.0;
     uint32_t bi = NONE;
@@ -319,7 +326,7 @@ __device__ __forceinline__ uint32_t select_child(const BlockRegs &R, int cnt, in
                 Nr = N - 3 * c;
                 if (c) W = __fadd_rn(W, (float)(3 * c));
             }
-            const float Q = Nr > 0 ? __fdiv_rn(W, (float)Nr) : 0.0f;                  // Q = W / N in float32 (of the last real backup)
+            const float Q = MODE == 2 ? __uint_as_float(R.Q[k]) : (Nr > 0 ? __fdiv_rn(W, (float)Nr) : 0.0f);   // Q = W / N in float32 (of the last real backup)
             const float p5 = __fmul_rn(5.0f, P);                                      // c_puct * P in float32
             const double U = __ddiv_rn(__dmul_rn((double)p5, sq), (double)(1 + N));
             double s = __dadd_rn((double)Q, U);
@@ -406,7 +413,7 @@ __global__ void __launch_bounds__(32 * MAX_WPB, 1) k_wave(Dev E, T *nn_in, const
             return;
         }
         // ---- round trip 3 (root block of the next descent) is requested BEFORE the logit gather (round trip 4) ----
-        if (DO_SELECT && pend == 1 && done < target) { load_block(ar, root_base, root_cnt, lane, R); have_root = true; }
+        if (DO_SELECT && pend == 1 && done < target) { load_block<false>(ar, root_base, root_cnt, lane, R); have_root = true; }
         if (ok) {
             expand_write(ar, S, logits + (size_t)g * CZ_NLABEL, n, base, lane);
             if (pend == 2) { root_base = base; root_cnt = n; }
@@ -459,7 +466,7 @@ __global__ void __launch_bounds__(32 * MAX_WPB, 1) k_wave(Dev E, T *nn_in, const
                 unsigned long long hash = rhash;
                 bool leaf = false, fault = false;
                 float tval = 0.0f;
-                if (!have_root) load_block(ar, base, cnt, lane, R);
+                if (!have_root) load_block<false>(ar, base, cnt, lane, R);
                 have_root = false;
                 for (;;) {
                     if (cnt <= 0 || depth >= MAXD) {
@@ -469,7 +476,7 @@ __global__ void __launch_bounds__(32 * MAX_WPB, 1) k_wave(Dev E, T *nn_in, const
                     }
                     const uint32_t cs = (uint32_t)((cnt + 7) & ~7);
                     uint32_t *blk = ar + base + HDR;
-                    const uint32_t e = select_child<false>(R, cnt, parentN, lane);
+                    const uint32_t e = select_child<0>(R, cnt, parentN, lane);
                     const int owner = e & 31, ke = (int)(e >> 5);
                     const uint32_t meta = __shfl_sync(CZ_FULL, pick(R.meta, ke), owner);
                     const uint32_t child = __shfl_sync(CZ_FULL, pick(R.child, ke), owner);
@@ -503,7 +510,7 @@ __global__ void __launch_bounds__(32 * MAX_WPB, 1) k_wave(Dev E, T *nn_in, const
                     base = child;
                     cnt = (int)((meta >> 16) & 0xFFu);
                     parentN = eN + 3;                            // the child's N carries the virtual loss just added
-                    load_block(ar, base, cnt, lane, R);          // one round trip per level: the pointer chase itself
+                    load_block<false>(ar, base, cnt, lane, R);   // one round trip per level: the pointer chase itself
                 }
                 if ((uint32_t)depth > maxdep) maxdep = (uint32_t)depth;
                 if (leaf) {
@@ -632,8 +639,8 @@ __global__ void __launch_bounds__(32 * MAX_WPB, 1) k_wave_multi(Dev E, T *nn_in,
                     }
                     const uint32_t cs = (uint32_t)((cnt + 7) & ~7);
                     uint32_t *blk = ar + base + HDR;
-                    load_block(ar, base, cnt, lane, R);
-                    const uint32_t e = select_child<true>(R, cnt, parentN, lane);
+                    load_block<false>(ar, base, cnt, lane, R);
+                    const uint32_t e = select_child<1>(R, cnt, parentN, lane);
                     const int owner = e & 31, ke = (int)(e >> 5);
                     const uint32_t meta = __shfl_sync(CZ_FULL, pick(R.meta, ke), owner);
                     const uint32_t child = __shfl_sync(CZ_FULL, pick(R.child, ke), owner);
@@ -708,6 +715,250 @@ __global__ void __launch_bounds__(32 * MAX_WPB, 1) k_wave_multi(Dev E, T *nn_in,
     if (lane < HW) hp[lane] = h;
 }
 
+
+// ---- search_threads = K: the reference's coroutine schedule in canonical FIFO form --------------------------------------
+// One warp per game runs the little event loop that oracle/detloop.py (the reference's own coroutines on a deterministic loop)
+// and oracle/cchess_oracle.c:co_tree_search_fifo specify, and that reproduces the real uvloop runs of the reference
+// (tests/golden/k16_stats.json.gz).  Every playout is a task; at most K are admitted (the semaphore, main.py:250, 342); the ready
+// queue is processed in batches ("iterations"); prediction_worker (442-464) is the last callback of every odd iteration and
+// evaluates whatever was queued.  Entries: STEP (start a playout, or re-check after a spin), AHOP (first hop of
+// asyncio.sleep(1e-4), main.py:354-355), RESUME (evaluation arrived: expand + unwind, 368-384).  Virtual losses of suspended
+// tasks stay on their paths; back_up_value stores Q = W / N of that moment (193), losses of other tasks included, so node blocks
+// carry a sixth array with the stored Q.  A launch runs iterations until an evaluation is needed (at most K rows per game:
+// network row g*K + slot) or the search is complete.
+enum { FI_ITER = 0, FI_NCUR, FI_NQ, FI_STARTED, FI_CUR = 4, FI_QUEUE = 20, FW = 28 };     // cur: 64 entry bytes, queue: 32 slot bytes
+#define EV_STEP 0u
+#define EV_AHOP 1u
+#define EV_RESUME 2u
+#define FIFO_MAX_ITERS 8
+
+__device__ __forceinline__ void backup_edge_q(uint32_t *ar, uint2 pe, int d, int depth, float val) {
+    const uint32_t slot = pe.x, cs = PE_CS(pe);
+    const float v = ((depth - 1 - d) & 1) ? -val : val;
+    const float W = __fadd_rn(__fadd_rn(__uint_as_float(ar[slot + cs]), 3.0f), v);     // node.W += virtual_loss; then W += value
+    const int N = (int)ar[slot + 2 * cs] - 3 + 1;
+    ar[slot + cs] = __float_as_uint(W);
+    ar[slot + 2 * cs] = (uint32_t)N;
+    ar[slot + 5 * cs] = __float_as_uint(__fdiv_rn(W, (float)N));                          // self.Q = self.W / self.N (main.py:193)
+}
+__device__ void warp_unwind_q(const uint2 *path, uint32_t *ar, int depth, float val, int lane) {
+    for (int d = lane; d < depth; d += 32) backup_edge_q(ar, path[d], d, depth, val);
+    __syncwarp();
+}
+
+template <typename T>
+__global__ void __launch_bounds__(32 * MAX_WPB, 1) k_wave_fifo(Dev E, T *nn_in, const float *logits, const float *value) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    WarpSmem *smem = reinterpret_cast<WarpSmem *>(smem_raw);
+    __shared__ uint8_t s_cur[MAX_WPB][64], s_nxt[MAX_WPB][64], s_queue[MAX_WPB][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int g = blockIdx.x * (blockDim.x >> 5) + w;
+    if (g >= E.B) return;
+    WarpSmem &S = smem[w];
+    uint8_t *cur = s_cur[w], *nxt = s_nxt[w], *queue = s_queue[w];
+    uint32_t *hp = E.hdr + (size_t)g * HW;
+    uint32_t h = lane < HW ? hp[lane] : 0u;
+    uint32_t *fp = E.fifo + (size_t)g * FW;
+    uint32_t fw = lane < FW ? fp[lane] : 0u;
+    const uint32_t rbw = lane < 24 ? reinterpret_cast<const uint32_t *>(E.root_board + (size_t)g * 96)[lane] : 0u;
+    uint32_t flags = HGET(H_FLAGS);
+    if (!(flags & F_ACTIVE)) return;
+    uint32_t *ar = arena_half(E, g, (flags & F_CUR) ? 1 : 0);
+    const int K = E.K;
+    int done = (int)HGET(H_DONE);
+    const int target = (int)HGET(H_TARGET);
+    uint32_t alloc = HGET(H_ALLOC), errf = 0, maxdep = HGET(H_MAXDEPTH);
+    uint32_t root_base = HGET(H_ROOTBASE);
+    int root_cnt = (int)HGET(H_ROOTCNT);
+    const int root_N = (int)HGET(H_ROOTN);
+    const int side0 = (flags & F_SIDE) ? 1 : 0, rr0 = (int)HGET(H_RR);
+    int pend = (int)F_PEND(flags);
+    int iter = (int)__shfl_sync(CZ_FULL, fw, FI_ITER), ncur = (int)__shfl_sync(CZ_FULL, fw, FI_NCUR);
+    int nq = (int)__shfl_sync(CZ_FULL, fw, FI_NQ), started = (int)__shfl_sync(CZ_FULL, fw, FI_STARTED);
+    {
+        const uint32_t cw0 = __shfl_sync(CZ_FULL, fw, (FI_CUR + lane) & 31), qw0 = __shfl_sync(CZ_FULL, fw, (FI_QUEUE + lane) & 31);
+        if (lane < 16) reinterpret_cast<uint32_t *>(cur)[lane] = cw0;
+        if (lane < 8) reinterpret_cast<uint32_t *>(queue)[lane] = qw0;
+    }
+    __syncwarp();
+    bool dead = false;
+
+    if (pend == 2) {       // the root's evaluation arrived (main.py:475-487; its value is discarded)
+        if (lane < 24) reinterpret_cast<uint32_t *>(S.board)[lane] = reinterpret_cast<const uint32_t *>(E.leafK + (size_t)g * K * 96)[lane];
+        __syncwarp();
+        uint32_t base;
+        const int n = expand_reserve(E, S, alloc, base, errf, lane);
+        if (n > 0) {
+            expand_write(ar, S, logits + (size_t)g * K * CZ_NLABEL, n, base, lane, true);
+            root_base = base; root_cnt = n;
+            if (lane == 0) { atomicAdd(E.cnt_expand + g, 1ull); atomicAdd(E.cnt_C + g, (unsigned long long)n); }
+        } else { flags &= ~F_ACTIVE; dead = true; }
+        pend = 0;
+    }
+    if (!dead && root_cnt < 0) {
+        if (lane < 24) reinterpret_cast<uint32_t *>(S.board)[lane] = rbw;
+        __syncwarp();
+        store_leaf_at<T>(E.leafK + (size_t)g * K * 96, S, side0, nn_in, (size_t)g * K, lane);
+        pend = 2;
+    } else if (!dead) {
+        if (iter == 0) {   // gather(): the first K playouts acquire the semaphore in iteration 1, the rest wait in FIFO order
+            iter = 1; nq = 0;
+            ncur = target < K ? target : K;
+            started = ncur;
+            if (lane < ncur) { cur[lane] = (uint8_t)(lane | (EV_STEP << 6)); E.plenK[(size_t)g * K + lane] = 0; }
+            __syncwarp();
+        }
+        unsigned long long accL = 0, accC = 0;
+        BlockRegs R;
+        bool need_nn = false;
+        for (int it = 0; it < FIFO_MAX_ITERS && !need_nn && done < target; it++) {
+            int nnxt = 0;
+            for (int e = 0; e < ncur; e++) {
+                const uint32_t ev = cur[e];
+                const int slot = (int)(ev & 63u), kind = (int)(ev >> 6);
+                const size_t idx = (size_t)g * K + slot;
+                if (kind == (int)EV_AHOP) { if (lane == 0) nxt[nnxt] = (uint8_t)(slot | (EV_STEP << 6)); nnxt++; continue; }
+                uint2 *path = E.pathK + idx * MAXD;
+                int plen = E.plenK[idx];
+                bool ended = false;
+                if (kind == (int)EV_RESUME) {
+                    if (lane < 24) reinterpret_cast<uint32_t *>(S.board)[lane] = reinterpret_cast<const uint32_t *>(E.leafK + idx * 96)[lane];
+                    __syncwarp();
+                    uint32_t base;
+                    const int n = expand_reserve(E, S, alloc, base, errf, lane);
+                    if (n > 0) {
+                        expand_write(ar, S, logits + idx * CZ_NLABEL, n, base, lane, true);
+                        if (lane == 0) {
+                            expand_link(ar, path[plen - 1], n, base, 0u);               // also clears `claimed`: now_expanding.remove(node)
+                            atomicAdd(E.cnt_expand + g, 1ull); atomicAdd(E.cnt_C + g, (unsigned long long)n);
+                        }
+                    } else if (lane == 0) {
+                        const uint2 pe = path[plen - 1];
+                        ar[pe.x + 3 * PE_CS(pe)] &= 0x7FFFFFFFu;                         // give the claim back
+                    }
+                    __syncwarp();
+                    warp_unwind_q(path, ar, plen, n > 0 ? -value[idx] : 0.0f, lane);     // return value[0] * -1, unwound through every frame
+                    ended = true;
+                } else {
+                    int side, rr, cnt, parentN;
+                    uint32_t base;
+                    bool go = true;
+                    if (plen == 0) {          // a fresh playout: start_tree_search(root)
+                        if (lane < 24) reinterpret_cast<uint32_t *>(S.board)[lane] = rbw;
+                        side = side0; rr = rr0; base = root_base; cnt = root_cnt; parentN = root_N;
+                    } else {                  // re-check after a spin: the node this task stands on
+                        if (lane < 24) reinterpret_cast<uint32_t *>(S.board)[lane] = reinterpret_cast<const uint32_t *>(E.leafK + idx * 96)[lane];
+                        __syncwarp();
+                        side = S.board[90]; rr = S.board[91];
+                        const uint2 pe = path[plen - 1];
+                        const uint32_t meta = ar[pe.x + 3 * PE_CS(pe)], child = ar[pe.x + 4 * PE_CS(pe)];
+                        parentN = (int)ar[pe.x + 2 * PE_CS(pe)];
+                        base = child; cnt = (int)((meta >> 16) & 0xFFu);
+                        if (meta & 0x80000000u) { if (lane == 0) nxt[nnxt] = (uint8_t)(slot | (EV_AHOP << 6)); nnxt++; go = false; }   // still now_expanding
+                        else if (child == NONE) {                                        // (its expansion failed: this task evaluates it)
+                            if (lane == 0) { ar[pe.x + 3 * PE_CS(pe)] = meta | 0x80000000u; queue[nq] = (uint8_t)slot; }
+                            nq++;
+                            store_leaf_at<T>(E.leafK + idx * 96, S, side, nn_in, idx, lane);
+                            go = false;
+                        }
+                    }
+                    __syncwarp();
+                    while (go) {
+                        if (cnt <= 0 || plen >= MAXD) { errf |= cnt <= 0 ? CZ_ERR_NOMOVES : CZ_ERR_DEPTH; warp_unwind_q(path, ar, plen, 0.0f, lane); ended = true; break; }
+                        const uint32_t cs = (uint32_t)((cnt + 7) & ~7);
+                        uint32_t *blk = ar + base + HDR;
+                        load_block<true>(ar, base, cnt, lane, R);
+                        const uint32_t c = select_child<2>(R, cnt, parentN, lane);
+                        const int owner = c & 31, ke = (int)(c >> 5);
+                        const uint32_t meta = __shfl_sync(CZ_FULL, pick(R.meta, ke), owner);
+                        const uint32_t child = __shfl_sync(CZ_FULL, pick(R.child, ke), owner);
+                        const int eN = (int)__shfl_sync(CZ_FULL, pick(R.N, ke), owner);
+                        if (lane == owner) {  // virtual loss (main.py:403-404); Q stays as stored
+                            blk[cs + c] = __float_as_uint(__fadd_rn(__uint_as_float(pick(R.W, ke)), -3.0f));
+                            blk[2 * cs + c] = (uint32_t)(eN + 3);
+                        }
+                        if (lane == 0) path[plen] = path_entry(base + HDR + c, cs, meta & 0xFFFFu);
+                        plen++;
+                        accL += 1; accC += (unsigned)cnt;
+                        const int src = meta & 127, dst = (meta >> 7) & 127;
+                        const int cap = S.board[dst], mover = S.board[src];
+                        __syncwarp();
+                        if (lane == 0) { S.board[dst] = (uint8_t)mover; S.board[src] = 0; }
+                        __syncwarp();
+                        side ^= 1;
+                        rr = cap == 0 ? rr + 1 : 0;
+                        if (cap == 1 || cap == 8) {                                      // main.py:409-414
+                            const float v = cap == 1 ? (side == 1 ? 1.0f : -1.0f) : (side == 1 ? -1.0f : 1.0f);
+                            warp_unwind_q(path, ar, plen, -v, lane);
+                            ended = true; break;
+                        }
+                        if (rr >= 60) { warp_unwind_q(path, ar, plen, 0.0f, lane); ended = true; break; }   // 415-416
+                        // start_tree_search(child): now_expanding? unexpanded? (main.py:354-357)
+                        if (meta & 0x80000000u) {
+                            if (lane == 0) { S.board[90] = (uint8_t)side; S.board[91] = (uint8_t)rr; }
+                            __syncwarp();
+                            if (lane < 24) reinterpret_cast<uint32_t *>(E.leafK + idx * 96)[lane] = reinterpret_cast<const uint32_t *>(S.board)[lane];
+                            if (lane == 0) nxt[nnxt] = (uint8_t)(slot | (EV_AHOP << 6));
+                            nnxt++;
+                            break;
+                        }
+                        if (child == NONE) {
+                            if (lane == 0) { blk[3 * cs + c] = meta | 0x80000000u; queue[nq] = (uint8_t)slot; S.board[91] = (uint8_t)rr; }
+                            nq++;
+                            store_leaf_at<T>(E.leafK + idx * 96, S, side, nn_in, idx, lane);   // features queued (push_queue, main.py:362-366)
+                            break;
+                        }
+                        base = child;
+                        cnt = (int)((meta >> 16) & 0xFFu);
+                        parentN = eN + 3;
+                    }
+                    if ((uint32_t)plen > maxdep) maxdep = (uint32_t)plen;
+                }
+                __syncwarp();
+                if (ended) {              // the task ends; its semaphore release wakes the next waiting playout (FIFO)
+                    done++;
+                    plen = 0;
+                    if (lane == 0) atomicAdd(E.cnt_playout + g, 1ull);
+                    if (started < target) { started++; if (lane == 0) nxt[nnxt] = (uint8_t)(slot | (EV_STEP << 6)); nnxt++; }
+                }
+                if (lane == 0) E.plenK[idx] = plen;
+                __syncwarp();
+            }
+            if (iter & 1) {               // prediction_worker: last callback of every odd iteration
+                if (nq > 0) {
+                    if (lane < nq) nxt[nnxt + lane] = (uint8_t)(queue[lane] | (EV_RESUME << 6));
+                    nnxt += nq; nq = 0; need_nn = true;
+                }
+            }
+            __syncwarp();
+            iter++;
+            uint8_t *tsw = cur; cur = nxt; nxt = tsw; ncur = nnxt;
+        }
+        if (lane == 0 && accL) { atomicAdd(E.cnt_L + g, accL); atomicAdd(E.cnt_c + g, accC); }
+        if (done >= target) { iter = 0; ncur = 0; }       // the search is complete: the next begin_search starts a fresh event loop
+    }
+    __syncwarp();
+    // ---- state back ----
+    uint32_t cw = lane < 16 ? reinterpret_cast<const uint32_t *>(cur)[lane] : 0u, qw = lane < 8 ? reinterpret_cast<const uint32_t *>(queue)[lane] : 0u;
+    if (lane == FI_ITER) fw = (uint32_t)iter;
+    if (lane == FI_NCUR) fw = (uint32_t)ncur;
+    if (lane == FI_NQ) fw = (uint32_t)nq;
+    if (lane == FI_STARTED) fw = (uint32_t)started;
+    const uint32_t cws = __shfl_sync(CZ_FULL, cw, (lane - FI_CUR) & 15), qws = __shfl_sync(CZ_FULL, qw, (lane - FI_QUEUE) & 7);
+    if (lane >= FI_CUR && lane < FI_CUR + 16) fw = cws;
+    if (lane >= FI_QUEUE && lane < FI_QUEUE + 8) fw = qws;
+    if (lane < FW) fp[lane] = fw;
+    HSET(H_FLAGS, F_SETPEND(flags, pend));
+    HSET(H_DONE, done);
+    HSET(H_ALLOC, alloc);
+    HSET(H_ROOTBASE, root_base);
+    HSET(H_ROOTCNT, root_cnt);
+    HSET(H_MAXDEPTH, maxdep);
+    if (lane == H_MAXALLOC && alloc > h) h = alloc;
+    if (lane == H_ERR) h |= errf;
+    if (lane < HW) hp[lane] = h;
+}
+
 // ---- GameBoard.reload + MCTS_tree.reload -------------------------------------------------
 __global__ void k_reset(Dev E, const uint8_t *mask, const uint8_t *boards, const uint8_t *sides, const int32_t *rr) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
@@ -726,6 +977,7 @@ __global__ void k_reset(Dev E, const uint8_t *mask, const uint8_t *boards, const
     h[H_HASHLO] = (uint32_t)z; h[H_HASHHI] = (uint32_t)(z >> 32);
     h[H_ERR] = keep_err; h[H_MAXALLOC] = keep_ma; h[H_MAXDEPTH] = keep_md;      // diagnostics live for the engine's lifetime
     if (E.pendK) for (int s = 0; s < E.K; s++) E.pendK[(size_t)g * E.K + s] = 0;
+    if (E.fifo) for (int i = 0; i < FW; i++) E.fifo[(size_t)g * FW + i] = 0;
 }
 
 __global__ void k_set_meta(Dev E, const uint8_t *mask, const uint8_t *sides, const int32_t *rr) {
@@ -750,6 +1002,7 @@ __global__ void k_begin(Dev E, const uint8_t *mask, int playouts) {
     h[H_DONE] = 0;
     h[H_TARGET] = (uint32_t)playouts;
     h[H_FLAGS] = f | F_ACTIVE;
+    if (E.fifo) E.fifo[(size_t)g * FW + FI_ITER] = 0;      // a fresh event loop for this search (MCTS_tree.main creates new coroutines)
 }
 
 __global__ void k_unfinished(Dev E, int32_t *out) {
@@ -784,7 +1037,7 @@ __global__ void k_root_children(Dev E) {
         E.st_p[o] = __uint_as_float(blk[i]);
         E.st_w[o] = W;
         E.st_visits[o] = N;
-        E.st_q[o] = N > 0 ? __fdiv_rn(W, (float)N) : 0.0f;
+        E.st_q[o] = E.narr == 6 ? __uint_as_float(blk[5 * cs + i]) : (N > 0 ? __fdiv_rn(W, (float)N) : 0.0f);
         E.st_moves[o] = (uint16_t)(blk[3 * cs + i] & 0xFFFFu);
     }
 }
@@ -834,7 +1087,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_play(Dev E) {
     const uint32_t meta = rblk[3 * rcs + choice], child = rblk[4 * rcs + choice];
     const int N = (int)rblk[2 * rcs + choice];
     const float Wc = __uint_as_float(rblk[rcs + choice]);
-    const float q = N > 0 ? __fdiv_rn(Wc, (float)N) : 0.0f;
+    const float q = E.narr == 6 ? __uint_as_float(rblk[5 * rcs + choice]) : (N > 0 ? __fdiv_rn(Wc, (float)N) : 0.0f);
     const int src = meta & 127, dst = (meta >> 7) & 127;
     const int cap = b[dst], mover = b[src];
     const int rr_old = (int)h[H_RR], ply_old = (int)h[H_PLY];
@@ -844,7 +1097,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_play(Dev E) {
     int ncnt = -1;
     if (child != NONE) {
         ncnt = (int)((meta >> 16) & 0xFFu);
-        uint32_t size = HDR + 5 * (uint32_t)((ncnt + 7) & ~7);
+        uint32_t size = HDR + (uint32_t)E.narr * (uint32_t)((ncnt + 7) & ~7);
         for (uint32_t i = lane; i < size; i += 32) neu[i] = old[child + i];
         alloc = size;
         __syncwarp();
@@ -858,7 +1111,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_play(Dev E) {
                 uint32_t oc = NONE, sz = 0;
                 if (i < c) {
                     oc = blk[4 * cs + i];
-                    if (oc != NONE) sz = HDR + 5 * ((((blk[3 * cs + i] >> 16) & 0xFFu) + 7) & ~7u);
+                    if (oc != NONE) sz = HDR + (uint32_t)E.narr * ((((blk[3 * cs + i] >> 16) & 0xFFu) + 7) & ~7u);
                 }
                 int tot;
                 const uint32_t off = alloc + (uint32_t)cz::warp_excl_scan((int)sz, lane, tot);
@@ -873,7 +1126,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_play(Dev E) {
                 alloc += (uint32_t)tot;
                 __syncwarp();
             }
-            scan += HDR + 5 * cs;
+            scan += HDR + (uint32_t)E.narr * cs;
         }
     }
     __syncwarp();
@@ -1176,9 +1429,21 @@ int cz_engine_create(int n_games, int64_t arena_words, int device, cz_engine **o
 
 int cz_engine_leaves(const cz_engine *e) { return e ? e->d.K : CZ_EINVAL; }
 
+extern "C++" { static int create_engine(int n_games, int64_t arena_words, int device, int leaves, bool fifo, cz_engine **out); }
+
 int cz_engine_create_ex(int n_games, int64_t arena_words, int device, int leaves, cz_engine **out) {
+    return create_engine(n_games, arena_words, device, leaves, false, out);
+}
+int cz_engine_create_fifo(int n_games, int64_t arena_words, int device, int search_threads, cz_engine **out) {
+    if (search_threads < 1 || search_threads > 32) return fail(CZ_EINVAL, "cz_engine_create_fifo: search_threads must be 1..32");
+    return create_engine(n_games, arena_words, device, search_threads, true, out);
+}
+int cz_engine_is_fifo(const cz_engine *e) { return e ? (e->d.fifo != nullptr) : CZ_EINVAL; }
+
+extern "C++" {
+static int create_engine(int n_games, int64_t arena_words, int device, int leaves, bool fifo, cz_engine **out) {
     if (n_games <= 0 || !out) return fail(CZ_EINVAL, "cz_engine_create: bad arguments");
-    const bool multi = leaves != 1;            // leaves == -1: the leaf-parallel kernel with one slot (test hook)
+    const bool multi = fifo || leaves != 1;    // leaves == -1: the leaf-parallel kernel with one slot (test hook)
     const int K = leaves < 0 ? -leaves : leaves;
     if (K < 1 || K > 64) return fail(CZ_EINVAL, "cz_engine_create_ex: leaves must be 1..64");
     if (arena_words <= 0) arena_words = 2ll << 20;     // 8 MiB per half: 2.7x the high-water mark of a 1200-playout self-play soak (0.74 Mi words)
@@ -1192,6 +1457,7 @@ int cz_engine_create_ex(int n_games, int64_t arena_words, int device, int leaves
     d.B = n_games;
     d.A = arena_words;
     d.K = K;
+    d.narr = fifo ? 6 : 5;
     {
         int sms = 148;
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sms <= 0) sms = 148;
@@ -1207,6 +1473,7 @@ int cz_engine_create_ex(int n_games, int64_t arena_words, int device, int leaves
     AL(d.st_w, B * CZ_MAXCHILD); AL(d.st_p, B * CZ_MAXCHILD); AL(d.st_q, B * CZ_MAXCHILD); AL(d.st_count, 8); AL(d.st_status, B * CZ_STATUS_BYTES);
     AL(e->d_mask, B); AL(e->d_boards, B * 90); AL(e->d_sides, B); AL(e->d_rr, B);
     if (multi) { AL(d.pendK, B * K); AL(d.plenK, B * K); AL(d.pathK, B * K * MAXD); AL(d.leafK, B * K * 96); }
+    if (fifo) { AL(d.fifo, B * FW); }
     if (!rc) { uint32_t *a = nullptr; rc = dalloc(e, &a, B * 2 * (size_t)arena_words, false); d.arena = a; }
 #undef AL
     if (rc) { const std::string keep = g_err; cz_engine_destroy(e); g_err = keep; return rc; }
@@ -1230,6 +1497,7 @@ int cz_engine_create_ex(int n_games, int64_t arena_words, int device, int leaves
     *out = e;
     return CZ_OK;
 }
+}  // extern "C++"
 
 int cz_engine_destroy(cz_engine *e) {
     if (!e) return CZ_OK;
@@ -1303,6 +1571,18 @@ static int launch_wave(cz_engine *e, void *stream, void *nn_in, int dt, const fl
 
 int cz_engine_wave(cz_engine *e, void *stream, void *nn_in, int nn_dtype, const float *logits, const float *value) {
     if (!e || !nn_in || !logits || !value) return fail(CZ_EINVAL, "cz_engine_wave: null");
+    if (e->d.fifo) {    // search_threads = K schedule of the reference (canonical FIFO form)
+        dim3 gr(nblk(e->d.B, e->wpb)), bl(32 * e->wpb);
+        const size_t sm = (size_t)e->wpb * sizeof(WarpSmem);
+        cudaStream_t st = (cudaStream_t)stream;
+        if (nn_dtype == CZ_F32) k_wave_fifo<float><<<gr, bl, sm, st>>>(e->d, (float *)nn_in, logits, value);
+        else if (nn_dtype == CZ_BF16) k_wave_fifo<__nv_bfloat16><<<gr, bl, sm, st>>>(e->d, (__nv_bfloat16 *)nn_in, logits, value);
+        else if (nn_dtype == CZ_F16) k_wave_fifo<__half><<<gr, bl, sm, st>>>(e->d, (__half *)nn_in, logits, value);
+        else if (nn_dtype == CZ_BOARD) k_wave_fifo<uint8_t><<<gr, bl, sm, st>>>(e->d, (uint8_t *)nn_in, logits, value);
+        else return fail(CZ_EINVAL, "wave: nn_dtype");
+        CUDA_TRY(cudaGetLastError());
+        return CZ_OK;
+    }
     if (e->d.pendK) {   // leaf-parallel engine
         dim3 gr(nblk(e->d.B, e->wpb)), bl(32 * e->wpb);
         const size_t sm = (size_t)e->wpb * sizeof(WarpSmem);
@@ -1501,6 +1781,7 @@ int cz_engine_tree_signature(cz_engine *e, void *stream, int game, int64_t *out,
         float W, Q;
         memcpy(&W, &blk[cs + i], 4);
         Q = N > 0 ? W / (float)N : 0.0f;
+        if (e->d.narr == 6) memcpy(&Q, &blk[5 * cs + i], 4);     // FIFO mode: the stored Q of the last back_up_value
         uint32_t qb;
         memcpy(&qb, &Q, 4);
         const int nch = child != NONE ? (int)((meta >> 16) & 0xFFu) : 0;

@@ -22,17 +22,23 @@ def _stream():
 
 
 class Engine:
-    def __init__(self, n_games, arena_words=0, device=None, leaves=1):
+    def __init__(self, n_games, arena_words=0, device=None, leaves=1, search_threads=None):
         """leaves > 1: leaf-parallel engine (up to `leaves` leaves per game per wave; network rows = n_games*leaves).
-        leaves == -1: the leaf-parallel kernel with one slot (test hook)."""
+        leaves == -1: the leaf-parallel kernel with one slot (test hook).
+        search_threads = K: the reference's search_threads schedule in canonical FIFO form (bit-exact with the reference's
+        uvloop runs wherever those are reproducible); network rows = n_games*K."""
         if not torch.cuda.is_available():
             raise EngineError("cchess_zero_b200 needs a CUDA device (no CPU fallback exists)")
         self.device = torch.cuda.current_device() if device is None else int(device)
         self.B = int(n_games)
-        self.leaves = abs(int(leaves))
+        self.fifo = search_threads is not None
+        self.leaves = int(search_threads) if self.fifo else abs(int(leaves))
         self.rows = self.B * self.leaves
         h = C.c_void_p()
-        check(lib().cz_engine_create_ex(self.B, int(arena_words), self.device, int(leaves), C.byref(h)), "cz_engine_create_ex")
+        if self.fifo:
+            check(lib().cz_engine_create_fifo(self.B, int(arena_words), self.device, int(search_threads), C.byref(h)), "cz_engine_create_fifo")
+        else:
+            check(lib().cz_engine_create_ex(self.B, int(arena_words), self.device, int(leaves), C.byref(h)), "cz_engine_create_ex")
         self.h = h
         self.launches = 0   # kernels of csrc/cz_engine.cu launched through this handle
         self._count = torch.zeros(1, dtype=torch.int32, device="cuda:%d" % self.device)

@@ -3,9 +3,12 @@ one-game device engine.  Same constructor, same methods, same attribute names th
 touch (`root.child[label].N/.Q`, `Q(move)`, `update_tree`, `reload`, `forward`, `generate_inputs`,
 `try_flip`, `state_to_positions`, `is_black_turn`).
 
-Semantics: search_threads = 1 of the reference whatever `search_threads`
-is passed -- one playout at a time per tree is the deterministic schedule; concurrency comes from
-running thousands of trees per GPU (selfplay.SelfPlay), not from coroutines inside one tree."""
+Semantics: `search_threads` is honoured.  1 = one playout at a time, bit-exact with the reference.
+K > 1 = the reference's coroutine schedule (semaphore of K playouts, now_expanding spins, prediction_worker batching,
+main.py:337-470) in its canonical deterministic form -- the engine's k_wave_fifo, specified by oracle/detloop.py and pinned to
+real uvloop runs of the reference: identical visit counts wherever the reference reproduces itself (it is timing-dependent on a
+few per cent of positions).  Up to K leaves are evaluated per network call.  `leaf_parallel=K` selects the
+package's own virtual-loss batching schedule instead (not the reference's visit counts)."""
 import os
 from collections import OrderedDict
 
@@ -64,8 +67,11 @@ class MCTS_tree(object):
         self.forward = in_forward
         self.virtual_loss = 3
         self.search_threads = search_threads
-        self.K = max(1, int(leaf_parallel))
-        self.engine = Engine(1, arena_words, leaves=self.K)
+        self.fifo = int(leaf_parallel) <= 1 and int(search_threads) > 1
+        if self.fifo and int(search_threads) > 32:
+            raise ValueError("search_threads > 32 is not supported by the device event loop")
+        self.K = int(search_threads) if self.fifo else max(1, int(leaf_parallel))
+        self.engine = Engine(1, arena_words, search_threads=self.K) if self.fifo else Engine(1, arena_words, leaves=self.K)
         dev = torch.device("cuda", self.engine.device)
         owner = getattr(in_forward, "__self__", None)
         K = self.K

@@ -89,6 +89,15 @@ int cz_engine_create(int n_games, int64_t arena_words, int device, cz_engine **o
  * logits [n_games*leaves][2086], value [n_games*leaves].  leaves == 1 is cz_engine_create; leaves == -1 runs the
  * leaf-parallel kernel with a single slot (test hook: must equal the one-leaf kernel bit for bit). */
 int cz_engine_create_ex(int n_games, int64_t arena_words, int device, int leaves, cz_engine **out);
+/* search_threads = K > 1 EXACTLY as the reference schedules it (main.py:337-470 on uvloop), in canonical deterministic form: every
+ * playout is a task, at most K hold the semaphore, the event loop's FIFO batches, the two-hop asyncio.sleep(1e-4) spin on
+ * now_expanding nodes and prediction_worker's batching are simulated per game by one warp (k_wave_fifo); node blocks carry the
+ * stored Q of back_up_value (main.py:193) because concurrent virtual losses make it differ from W/N.  Specification:
+ * oracle/detloop.py (the reference's own coroutines on a deterministic loop) and oracle/cchess_oracle.c:co_tree_search_fifo, both
+ * pinned to real uvloop runs of the reference (tests/golden/k16_stats.json.gz).  Network rows as for `leaves`: g*K + slot.
+ * search_threads: 1..32 (1 reproduces cz_engine_create's results with the 6-array blocks). */
+int cz_engine_create_fifo(int n_games, int64_t arena_words, int device, int search_threads, cz_engine **out);
+int cz_engine_is_fifo(const cz_engine *e);
 int cz_engine_leaves(const cz_engine *e);
 int cz_engine_destroy(cz_engine *e);
 int cz_engine_n_games(const cz_engine *e);

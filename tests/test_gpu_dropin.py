@@ -84,7 +84,7 @@ def test_mcts_tree_dropin_against_reference_vectors():
     for c in load_golden("tree.json")["cases"]:
         if c["playouts"] > 300:
             continue
-        t = MCTS_tree(c["state"], FAKE_NETS[c["net"]], 16)
+        t = MCTS_tree(c["state"], FAKE_NETS[c["net"]], 1)          # the goldens are search_threads=1 runs of the reference
         t._set_position(c["state"], c["player"], c["rr"])
         t.main(c["state"], c["player"], c["rr"], c["playouts"])
         got = [[a, n.N] for a, n in t.root.child.items()]
@@ -105,7 +105,7 @@ def test_cchess_main_selfplay_dropin_against_reference_vectors(tmp_path, monkeyp
             self.forward = f
 
     for g in load_golden("selfplay.json")["games"][:2]:
-        m = cchess_main(playout=g["playouts"], in_search_threads=16, network=Net(FAKE_NETS[g["net"]]), log_file=False)
+        m = cchess_main(playout=g["playouts"], in_search_threads=1, network=Net(FAKE_NETS[g["net"]]), log_file=False)
         np.random.seed(g["seed"])
         import contextlib, io
         with contextlib.redirect_stdout(io.StringIO()):
@@ -218,7 +218,7 @@ def test_mcts_tree_with_package_network_and_move_latency(tmp_path, monkeypatch):
     from cchess_zero_b200.net import policy_value_network
     from cchess_zero_b200.selfplay import cchess_main
     pv = policy_value_network(res_block_nums=7)
-    m = cchess_main(playout=200, in_search_threads=16, network=pv, exploration=False, log_file=False)
+    m = cchess_main(playout=200, in_search_threads=1, network=pv, exploration=False, log_file=False)
     np.random.seed(0)
     lat = []
     with contextlib.redirect_stdout(io.StringIO()):
@@ -301,7 +301,7 @@ def test_leaf_parallel_move_latency_mode(tmp_path, monkeypatch):
     pv = policy_value_network(res_block_nums=7)
     lat = {}
     for K in (1, 8):
-        m = cchess_main(playout=400, in_search_threads=16, network=pv, exploration=False, log_file=False, leaf_parallel=K)
+        m = cchess_main(playout=400, in_search_threads=1, network=pv, exploration=False, log_file=False, leaf_parallel=K)
         np.random.seed(0)
         ts = []
         with contextlib.redirect_stdout(io.StringIO()):

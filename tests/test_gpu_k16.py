@@ -1,0 +1,100 @@
+"""search_threads = 16 (the reference's default, main.py:1570): the engine's FIFO-schedule kernel against its two specifications
+(the C oracle co_tree_search_fifo, bit for bit on whole trees) and against REAL uvloop runs of the unmodified reference
+(tests/golden/k16_stats.json.gz: root visit counts of 240 random-play positions, each searched twice by the reference)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(records, K, playouts, net, lo=0, hi=None):
+    from cchess_zero_b200 import rules
+    from cchess_zero_b200.engine import Engine
+    from cchess_zero_b200.fakenet import FakeNet
+    recs = records[lo:hi]
+    B = len(recs)
+    e = Engine(B, 1 << 17, search_threads=K)
+    boards = np.stack([rules.state_to_board(r["state"]) for r in recs])
+    sides = np.array([0 if r["player"] == "w" else 1 for r in recs], dtype=np.uint8)
+    rr = np.array([r["rr"] for r in recs], dtype=np.int32)
+    e.reset(None, boards, sides, rr)
+    fn = FakeNet(net)
+    nn_in = torch.zeros((e.rows, 9, 10, 14), device="cuda")
+    logits = torch.zeros((e.rows, 2086), device="cuda")
+    value = torch.zeros((e.rows,), device="cuda")
+
+    def fwd(x):
+        l, v = fn(x)
+        logits.copy_(l); value.copy_(v)
+    e.search(fwd, playouts, nn_in, logits, value)
+    c = e.raise_on_error()
+    assert c["n_playout"] == B * playouts
+    return e, e.root_children()
+
+
+def test_fifo_schedule_equals_c_specification_bit_for_bit():
+    """Whole-tree signatures (visits, W / P / Q bits of every node) of k_wave_fifo vs oracle co_tree_search_fifo, K = 16, 4 and 1;
+    with K = 1 the schedule is the reference's search_threads=1 search (golden k1 visits)."""
+    from oracle import oracle as O
+    d = load_golden("k16_stats.json.gz")
+    recs = d["records"][:48]
+    for K in (16, 4, 1):
+        e, rc = _run(recs, K, d["playouts"], d["net"])
+        for g, r in enumerate(recs):
+            t = O.Tree(O.from_state(r["state"]))
+            assert t.search_fifo(0 if r["player"] == "w" else 1, r["rr"], d["playouts"], K, d["net"]) == 0
+            assert np.array_equal(t.signature(), e.tree_signature(g)), (K, g)
+            if K == 1:
+                assert [int(x) for x in rc["visits"][g, : rc["n"][g]]] == r["k1"]
+        e.close()
+
+
+def test_fifo_schedule_reproduces_real_reference_runs_at_search_threads_16():
+    """Root visit counts vs the unmodified reference on uvloop, 240 positions x 200 playouts.  The reference itself is timing-dependent
+    on a few per cent of positions (its two recorded runs differ there); the engine must equal one of the two runs everywhere and the
+    first run on at least 95 %."""
+    from cchess_zero_b200 import rules
+    d = load_golden("k16_stats.json.gz")
+    recs = d["records"]
+    e, rc = _run(recs, 16, d["playouts"], d["net"])
+    first = either = 0
+    for g, r in enumerate(recs):
+        n = rc["n"][g]
+        assert " ".join(rules.move_to_label(m) for m in rc["moves"][g, :n]) == r["moves"]
+        v = [int(x) for x in rc["visits"][g, :n]]
+        first += v == r["k16"]
+        either += v == r["k16"] or v == r["k16_delay2ms"]
+    print("engine == reference run 1 on %d / %d positions, == one of its two runs on %d" % (first, len(recs), either))
+    assert either == len(recs)
+    assert first >= 0.95 * len(recs)
+    e.close()
+
+
+def test_mcts_tree_honours_search_threads_and_play_continues_on_the_reused_tree(tmp_path, monkeypatch):
+    """MCTS_tree(state, forward, 16): the facade runs the FIFO engine; update_tree keeps the subtree with its stored Q; a second
+    search on the re-used root equals the C specification run through the same two searches."""
+    monkeypatch.chdir(tmp_path)
+    from cchess_zero_b200 import rules
+    from cchess_zero_b200.mcts import MCTS_tree
+    from oracle import oracle as O
+    from oracle.fakenets_np import FAKE_NETS
+    t = MCTS_tree(rules.START_STATE, FAKE_NETS["hash_pos"], 16)
+    assert t.fifo and t.K == 16
+    t.main(rules.START_STATE, "w", 0, 160)
+    o = O.Tree()
+    assert o.search_fifo(0, 0, 160, 16, "hash_pos") == 0
+    mv, N, W, P, Q = o.root_children()
+    assert [[a, n.N] for a, n in t.root.child.items()] == [[O.move_str(m), int(x)] for m, x in zip(mv, N)]
+    best = int(np.argmax(N))
+    act = O.move_str(mv[best])
+    assert np.float32(t.Q(act)).tobytes() == np.float32(Q[best]).tobytes()           # the STORED Q
+    t.update_tree(act)
+    o.update(best)
+    state2 = rules.GameBoard.sim_do_action(act, rules.START_STATE)
+    t.main(state2, "b", 1, 160)
+    assert o.search_fifo(1, 1, 160, 16, "hash_pos") == 0
+    mv, N, W, P, Q = o.root_children()
+    assert [[a, n.N] for a, n in t.root.child.items()] == [[O.move_str(m), int(x)] for m, x in zip(mv, N)]

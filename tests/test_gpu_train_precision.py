@@ -156,7 +156,7 @@ def test_search_uses_trained_weights_after_train_step_and_restore(tmp_path, monk
     from cchess_zero_b200.net import policy_value_network
     from cchess_zero_b200.selfplay import SelfPlay
     pv = policy_value_network(res_block_nums=2)
-    t = MCTS_tree(rules.START_STATE, pv.forward, 16)
+    t = MCTS_tree(rules.START_STATE, pv.forward, 1)
     sp = SelfPlay(8, None, 8, seeds=range(8), arena_words=1 << 16, plan=pv.native_plan(8), auto_reset=False)
     sp.capture_graph()
 

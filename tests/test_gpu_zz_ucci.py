@@ -21,7 +21,7 @@ def test_ucci_session_on_the_device_engine(tmp_path, monkeypatch):
             self.forward = f
 
     def make(options):
-        return cchess_main(playout=options["playouts"], in_search_threads=16, network=Net(FAKE_NETS["hash_signed"]),
+        return cchess_main(playout=options["playouts"], in_search_threads=1, network=Net(FAKE_NETS["hash_signed"]),
                            exploration=False, log_file=False)
 
     def top(tree):

@@ -155,3 +155,55 @@ def test_tree_extra_cases_against_reference():
         t.search(0 if c["player"] == "w" else 1, c["rr"], c["playouts"], c["net"])
         sig = t.signature()
         assert sig.shape[0] == c["n_nodes"] and sha(sig.tobytes()) == c["sha_sig"], (c["state"], c["player"], c["rr"])
+
+
+def test_fifo_schedule_spec_reproduces_real_reference_runs_at_search_threads_16():
+    """oracle co_tree_search_fifo (the canonical FIFO form of the reference's search_threads > 1 schedule) against REAL uvloop runs
+    of the unmodified reference at search_threads=16 (tests/golden/k16_stats.json.gz; every position was searched twice by the
+    reference, the second time with 2 ms of evaluator latency).  The reference differs from itself on a few per cent of the
+    positions (timing-dependent spins); the specification must equal one of its two runs on every position."""
+    from conftest import load_golden
+    d = load_golden("k16_stats.json.gz")
+    first = either = self_consistent = 0
+    for r in d["records"]:
+        side = 0 if r["player"] == "w" else 1
+        t = O.Tree(O.from_state(r["state"]))
+        assert t.search_fifo(side, r["rr"], d["playouts"], 16, d["net"]) == 0
+        mv, N, W, P, Q = t.root_children()
+        assert " ".join(O.move_str(m) for m in mv) == r["moves"]
+        v = [int(x) for x in N]
+        first += v == r["k16"]
+        either += v == r["k16"] or v == r["k16_delay2ms"]
+        self_consistent += r["k16"] == r["k16_delay2ms"]
+        t1 = O.Tree(O.from_state(r["state"]))
+        assert t1.search_fifo(side, r["rr"], d["playouts"], 1, d["net"]) == 0
+        assert [int(x) for x in t1.root_children()[1]] == r["k1"]            # K = 1 degenerates to the search_threads=1 reference
+    assert either == len(d["records"]) and first >= 0.95 * len(d["records"])
+    assert self_consistent == d["reference_k16_identical_under_2ms_latency"]
+
+
+def test_deterministic_event_loop_runs_the_reference_coroutines_to_the_same_trees():
+    """oracle/detloop.py: the UNMODIFIED coroutines of the reference (tree_search / start_tree_search / prediction_worker) on a
+    deterministic event loop give the visit counts of the real uvloop run AND of the C restatement.  Needs the reference (live or
+    staged)."""
+    import os
+    import sys
+    from conftest import ROOT
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import stage_reference as S
+    if S.staged_dir() is None:
+        pytest.skip("reference not present")
+    import detloop as D
+    import ref_harness as H
+    from conftest import load_golden
+    d = load_golden("k16_stats.json.gz")
+    for r in d["records"][:12]:
+        ref, t, loop = D.make_tree(H, H.FAKE_NETS[d["net"]], 16, r["state"], "busy")
+        with np.errstate(all="ignore"):
+            D.run_reference_search(ref, t, r["state"], r["player"], r["rr"], d["playouts"], loop)
+        loop.close()
+        v = [int(c.N) for c in t.root.child.values()]
+        assert v == r["k16"] or v == r["k16_delay2ms"]
+        o = O.Tree(O.from_state(r["state"]))
+        o.search_fifo(0 if r["player"] == "w" else 1, r["rr"], d["playouts"], 16, d["net"])
+        assert v == [int(x) for x in o.root_children()[1]]
