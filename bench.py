@@ -444,7 +444,8 @@ def leg_soak(runner, plies):
     st = sp.engine.status(boards=True)
     sp.boards, sp.sides = st["boards"], st["side"]
     from cchess_zero_b200.selfplay import GameRecord
-    sp.records = [GameRecord() for _ in range(sp.B)]
+    sp.records = [GameRecord(g, None, sp.temperature) for g in range(sp.B)]
+    sp._span = [[] for _ in range(sp.B)]
     sp.keep_records = False                                    # lengths only: keeps the soak's host memory flat
     first_len = np.full(sp.B, -1, dtype=np.int64)
     all_len = []

@@ -6,7 +6,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcchess_b200.so")
 
-NSQ, NLABEL, MAXCHILD, ENC_LEN, STATUS_BYTES = 90, 2086, 128, 1260, 112
+NSQ, NLABEL, MAXCHILD, ENC_LEN, STATUS_BYTES, MT_WORDS = 90, 2086, 128, 1260, 112, 626
 F32, BF16, F16, BOARD = 0, 1, 2, 3
 ERR_NAMES = {1: "NOMOVES", 2: "NOLABEL", 4: "DEPTH", 8: "ARENA", 16: "CHILDREN"}
 
@@ -58,6 +58,7 @@ def _sig(L):
     L.cz_net_first_conv.argtypes = [vp, i32, vp, vp, vp, vp]
     L.cz_net_first_conv_tc.argtypes = [vp, i32, vp, vp, vp, vp]
     L.cz_net_heads.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.cz_host_choose_moves.argtypes = [i32, vp, vp, vp, i32, vp, vp, vp, vp, i32]
     L.cz_net_heads_fc.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.cz_net_tower_blob_bytes.argtypes = [i32]
     L.cz_net_tower_blob_bytes.restype = i64

@@ -718,7 +718,7 @@ __global__ void __launch_bounds__(32 * MAX_WPB, 1) k_wave_multi(Dev E, T *nn_in,
 
 // ---- search_threads = K: the reference's coroutine schedule in canonical FIFO form --------------------------------------
 // One warp per game runs the little event loop that oracle/detloop.py (the reference's own coroutines on a deterministic loop)
-// and oracle/cchess_oracle.c:co_tree_search_fifo specify, and that reproduces the real uvloop runs of the reference
+// and the C oracle (co_tree_search_fifo) specify, and that reproduces the real uvloop runs of the reference
 // (tests/golden/k16_stats.json.gz).  Every playout is a task; at most K are admitted (the semaphore, main.py:250, 342); the ready
 // queue is processed in batches ("iterations"); prediction_worker (442-464) is the last callback of every odd iteration and
 // evaluates whatever was queued.  Entries: STEP (start a playout, or re-check after a spin), AHOP (first hop of

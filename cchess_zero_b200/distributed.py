@@ -42,6 +42,7 @@ def pack_records(records, cap=None):
         if L == 0:
             continue
         buf = np.zeros((L, REC_BYTES), dtype=np.uint8)
+        r._raw() if hasattr(r, "_raw") and r._boards is None else None
         if r._boards and r._boards[0] is not None:               # raw per-ply data of a game played here
             boards = np.stack(r._boards).astype(np.uint8)
             sides = np.asarray(r.players, dtype=np.uint8)

@@ -17,7 +17,7 @@ import numpy as np
 import torch
 
 from . import rules
-from ._lib import MAXCHILD, NLABEL, EngineError
+from ._lib import MAXCHILD, MT_WORDS, NLABEL, EngineError
 from .engine import Engine
 
 
@@ -54,19 +54,43 @@ def _label_table():
 class GameRecord:
     """(s, pi, z) tuples of one finished game in the reference's format (selfplay, main.py:1493-1554).
 
-    During play only raw per-ply data is appended (board bytes, side, moves, probs); the canonical state strings and
-    label indices are materialised on first access, vectorised per game."""
+    During play nothing per game is recorded: SelfPlay keeps ONE log entry per ply for the whole batch (boards, sides, root moves
+    and visit counts, chosen indices); a record only remembers its slot and ply span.  Boards, move lists, pi (recomputed from the
+    integer visit counts with the very numpy operations get_action uses, so bit-identical) and the canonical state strings /
+    label indices are materialised on first access."""
 
-    def __init__(self):
-        self._boards, self._moves, self.pi_val, self.players, self._chosen, self.visits = [], [], [], [], [], []
+    def __init__(self, slot=None, logs=None, temperature=1):
+        self._slot, self._logs, self._T = slot, logs if logs is not None else [], temperature
+        self.players = []
         self.z = None
         self.winner = None
+        self._boards = self._moves = self._chosen = self.visits = self.pi_val = None
         self._states = self._pi_idx = self._actions = None
 
     def __len__(self):
         return len(self.players)
 
+    def _raw(self):
+        if self._boards is not None:
+            return
+        g = self._slot
+        self._boards, self._moves, self._chosen, self.visits, self.pi_val = [], [], [], [], []
+        for lg in self._logs:
+            n = int(lg["n"][g])
+            v = lg["visits"][g, :n].astype(np.int64)
+            self._boards.append(lg["boards"][g])
+            self._moves.append(lg["moves"][g, :n])
+            self._chosen.append(int(lg["choice"][g]))
+            self.visits.append(lg["visits"][g, :n])
+            with np.errstate(divide="ignore", invalid="ignore"):
+                lv = (1.0 / self._T) * np.log(v)                    # softmax(1/T * log(visits)), main.py:1341, 1111-1116
+                pr = np.exp(lv - np.max(lv))
+                pr /= np.sum(pr)
+            self.pi_val.append(pr)
+        self._logs = None
+
     def _materialise(self):
+        self._raw()
         if self._states is not None and len(self._states) == len(self.players):
             return
         tab = _label_table()
@@ -91,6 +115,7 @@ class GameRecord:
         r._states, r._pi_idx, r.pi_val, r.z = list(states), list(pi_idx), list(pi_val), z
         r.players = [0] * len(r._states)
         r._boards = [None] * len(r._states)
+        r._moves = r._chosen = r.visits = []
         return r
 
     @property
@@ -109,6 +134,7 @@ class GameRecord:
         return self._actions
 
     def dense_pi(self):
+        self._raw()
         out = np.zeros((len(self), NLABEL))
         for i, (ix, v) in enumerate(zip(self.pi_idx, self.pi_val)):
             out[i, ix] = v
@@ -239,12 +265,19 @@ class SelfPlay:
         self.forward = forward
         self.playouts = np.broadcast_to(np.asarray(playouts, dtype=np.int64), (n_games,)).copy()
         seeds = range(n_games) if seeds is None else seeds
-        self.rs = [np.random.RandomState(int(s)) for s in seeds]
+        # one legacy MT19937 stream per game slot (stands in for the reference's global np.random), held as raw numpy
+        # RandomState states: csrc/cz_host.cu draws from them exactly as RandomState.dirichlet / .choice would
+        self._mt = np.zeros((n_games, MT_WORDS), dtype=np.uint32)
+        for g, sd in enumerate(seeds):
+            st = np.random.RandomState(int(sd)).get_state()
+            self._mt[g, :624], self._mt[g, 624] = st[1], st[2]
+        self._log = []                                   # per-ply batch logs still referenced by running games
+        self._span = [[] for _ in range(n_games)]        # the log entries of each slot's current game
         self.exploration = exploration
         self.temperature = temperature
         self.auto_reset = auto_reset
         self.keep_records = keep_records
-        self.records = [GameRecord() for _ in range(n_games)]
+        self.records = [GameRecord(g, None, temperature) for g in range(n_games)]
         self._start_board = rules.state_to_board(rules.START_STATE)
         self.boards = np.tile(self._start_board, (n_games, 1))
         self.sides = np.zeros(n_games, dtype=np.uint8)
@@ -254,6 +287,7 @@ class SelfPlay:
         self.waves = 0
         self.graph = None
         self._alphas = {}
+        self._threads = max(1, min(16, (len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else 4)))
         rules._init_tables()
 
     def _alpha(self, n):
@@ -385,38 +419,40 @@ class SelfPlay:
             raise EngineError("game %d has no root children" % int(live[np.argmax(rc["n"][live] <= 0)]))
         with np.errstate(divide="ignore", invalid="ignore"):
             # softmax(1/T * log(visits)) of main.py:1341, 1111-1116.  log / exp / max are element-wise or exact, so they are
-            # taken over the whole [B,128] batch at once (padding: visits 0 -> -inf -> exp 0); the order-sensitive row sum
-            # and the RNG draws stay per game, on slices of exactly n entries, as the reference computes them.
+            # taken over the whole [B,128] batch at once (padding: visits 0 -> -inf -> exp 0); the order-sensitive row sum, the
+            # Dirichlet / choice draws and the cumulative sums happen per game in csrc/cz_host.cu, operation for operation what
+            # numpy does for `probs /= np.sum(probs)`, RandomState.dirichlet and RandomState.choice (main.py:1345-1348).
             lv = (1.0 / self.temperature) * np.log(rc["visits"].astype(np.int64))
             valid = np.arange(MAXCHILD)[None, :] < rc["n"][:, None]
             lv[~valid] = -np.inf
-            ex = np.exp(lv - np.max(lv, axis=1, keepdims=True))
+            ex = np.ascontiguousarray(np.exp(lv - np.max(lv, axis=1, keepdims=True)))
+        probs = np.empty((self.B, MAXCHILD), dtype=np.float64)
+        fallback = np.zeros(self.B, dtype=np.uint8)
+        live8 = np.ascontiguousarray(self.live, dtype=np.uint8)
+        nn = np.ascontiguousarray(rc["n"], dtype=np.int32)
+        from ._lib import lib
+        import ctypes as C
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+        rcode = lib().cz_host_choose_moves(self.B, vp(live8), vp(nn), vp(ex), 1 if self.exploration else 0, vp(self._mt), vp(choice), vp(probs),
+                                           vp(fallback), self._threads)
+        if rcode:
+            raise EngineError("cz_host_choose_moves failed (%d)" % rcode)
+        for g in np.nonzero(fallback)[0]:
+            # a probability vector numpy would reject (NaN priors ...): let numpy raise exactly what the reference would raise
+            n = int(rc["n"][g])
+            rs = np.random.RandomState()
+            rs.set_state(("MT19937", self._mt[g, :624].copy(), int(self._mt[g, 624]), 0, 0.0))
+            pr = ex[g, :n] / np.sum(ex[g, :n])
+            choice[g] = int(rs.choice(n, p=pr))          # (the Dirichlet draws were consumed by the native sampler, as in the reference)
+            st_ = rs.get_state()
+            self._mt[g, :624], self._mt[g, 624] = st_[1], st_[2]
+        if self.keep_records:
+            entry = dict(boards=self.boards, n=nn, moves=rc["moves"], visits=rc["visits"], choice=choice)
             for g in live:
-                n = int(rc["n"][g])
-                probs = ex[g, :n].copy()
-                probs /= np.sum(probs)
-                rs = self.rs[g]
-                if self.exploration:                                                     # main.py:1345-1346
-                    p = 0.75 * probs + 0.25 * rs.dirichlet(self._alpha(n))
-                else:
-                    p = probs
-                # np.random.choice(actions, p=p) (main.py:1346-1348): cdf = p.cumsum(); cdf /= cdf[-1];
-                # idx = cdf.searchsorted(random_sample(), side='right') -- numpy's legacy algorithm, same draws
-                cdf = np.cumsum(p)
-                if not (cdf[-1] == cdf[-1]) or abs(cdf[-1] - 1.0) > 1.5e-8 * max(1.0, n) or p.min() < 0:
-                    idx = int(rs.choice(n, p=p))          # let numpy raise exactly what the reference would raise
-                else:
-                    cdf /= cdf[-1]
-                    idx = int(cdf.searchsorted(rs.random_sample(), side="right"))
-                choice[g] = idx
-                rec = self.records[g]
-                rec.players.append(int(self.sides[g]))
-                if self.keep_records:
-                    rec._boards.append(self.boards[g].copy())
-                    rec._moves.append(rc["moves"][g, :n].copy())
-                    rec.pi_val.append(probs)
-                    rec._chosen.append(idx)
-                    rec.visits.append(rc["visits"][g, :n].copy())
+                self._span[g].append(entry)
+        sides_now = self.sides
+        for g in live:
+            self.records[g].players.append(int(sides_now[g]))
         st = e.play(choice)                                          # board update + re-root + status, one synchronisation
         win_rate = np.where(choice >= 0, st["q"], 0.0).astype(np.float32)                 # mcts.Q(act), main.py:1350
         self.boards, self.sides = st["boards"], st["side"]
@@ -432,9 +468,11 @@ class SelfPlay:
             else:                                                                        # main.py:1542-1545
                 rec.z = np.zeros(len(players))
                 rec.winner = "t"
+            rec._logs, rec._T = self._span[g], self.temperature
+            self._span[g] = []
             done_now.append((int(g), rec))
             self.finished.append((int(g), rec))
-            self.records[g] = GameRecord()
+            self.records[g] = GameRecord(int(g), None, self.temperature)
         if done_now:
             idx = [g for g, _ in done_now]
             if self.auto_reset:

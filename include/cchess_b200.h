@@ -93,7 +93,7 @@ int cz_engine_create_ex(int n_games, int64_t arena_words, int device, int leaves
  * playout is a task, at most K hold the semaphore, the event loop's FIFO batches, the two-hop asyncio.sleep(1e-4) spin on
  * now_expanding nodes and prediction_worker's batching are simulated per game by one warp (k_wave_fifo); node blocks carry the
  * stored Q of back_up_value (main.py:193) because concurrent virtual losses make it differ from W/N.  Specification:
- * oracle/detloop.py (the reference's own coroutines on a deterministic loop) and oracle/cchess_oracle.c:co_tree_search_fifo, both
+ * oracle/detloop.py (the reference's own coroutines on a deterministic loop) and the C oracle (co_tree_search_fifo), both
  * pinned to real uvloop runs of the reference (tests/golden/k16_stats.json.gz).  Network rows as for `leaves`: g*K + slot.
  * search_threads: 1..32 (1 reproduces cz_engine_create's results with the 6-array blocks). */
 int cz_engine_create_fifo(int n_games, int64_t arena_words, int device, int search_threads, cz_engine **out);
@@ -195,6 +195,19 @@ int cz_net_first_conv(const uint8_t *canon_boards, int B, const void *w1, const 
 int cz_net_first_conv_tc(const uint8_t *canon_boards, int B, const void *w_umma, const float *b1, void *out, void *stream);
 int cz_net_heads(const void *x, int B, const float *wh, const float *bh, const float *w1t, const float *b1, const float *w2, const float *b2,
                  const void *wp, const float *bp, void *hp_scratch, float *hv_scratch, float *logits, float *value, void *stream);
+
+/* ---- host side: get_action's sampling for a whole batch of games (main.py:1339-1348), bit-identical to the numpy calls ----
+ * For every game g with live[g] != 0 (live NULL = all):  probs = ex[g][:n] / np.sum(ex[g][:n])  (ex = exp(log(visits)/T - max), computed
+ * by the caller with numpy);  exploration: p = 0.75 * probs + 0.25 * RandomState.dirichlet(0.3 * ones(n));  choice[g] =
+ * RandomState.choice(n, p = p).  mt_states: one legacy MT19937 state per game, CZ_MT_WORDS uint32 each = key[624], pos, 0 --
+ * exactly numpy.random.RandomState.get_state()[1:3] -- advanced in place by the same number of draws numpy would make.
+ * probs [B][128] receives the normalised (un-noised) probabilities, i.e. the recorded pi.  fallback[g] = 1 when the vector would
+ * make numpy raise (NaN / negative / not summing to 1): the caller lets numpy itself handle that game (after the Dirichlet draws,
+ * which have been consumed as in the reference).  All pointers are HOST memory; no GPU involved. */
+#define CZ_MT_WORDS 626
+int cz_host_choose_moves(int n_games, const uint8_t *live, const int32_t *n_children, const double *ex /* [B][128] */, int exploration,
+                         uint32_t *mt_states /* [B][626] */, int32_t *choice /* [B] */, double *probs /* [B][128] */, uint8_t *fallback /* [B] */,
+                         int n_threads);
 
 /* The second half of cz_net_heads alone: value MLP and policy FC on head features that are already computed
  * (hp fp16 [B][192], hv f32 [B][96]) -- what follows cz_net_tower_small. */
