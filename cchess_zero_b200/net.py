@@ -322,7 +322,7 @@ class SmallTowerPlan:
         import ctypes as C
         from ._lib import lib
         self._C, self._lib = C, lib()
-        self.cluster = int(cluster or os.environ.get("CCHESS_TOWER_CLUSTER", "8"))
+        self.cluster = int(cluster or os.environ.get("CCHESS_TOWER_CLUSTER", "2"))   # measured: 92 us per evaluation for every cluster size (the per-layer chain, not the MMAs, bounds it); 2 CTAs leave the most SMs free
         assert self.cluster in (1, 2, 4, 8)
         self._base = InferencePlan(net, "fp16", owner=owner)
         self.fused = True
