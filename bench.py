@@ -20,6 +20,8 @@ Further bounded legs, reported under `extra` of the same JSON line (each can be 
   config4   : BASELINE configs[3], 19 residual blocks                       -> extra.config4           (N = 1)
   config5   : BASELINE configs[4], play-mode move latency p50/p95 through get_hint + select_move (ChessGame.py:153-181)
                                                                              -> extra.config5           (N = 1)
+  threads16 : batched self-play with the reference's search_threads=16 schedule inside every game     -> extra.search_threads_16 (N = 1)
+  dedup     : board hashing: share of the evaluated leaves of one ply that repeat a position            -> extra.eval_dedup        (N = 1)
   soak      : every game slot plays on for >= 3 mean game lengths; games/hour from plies/s and the measured
               game-length distribution (no short-game selection bias)       -> extra.games_per_hour
   cpu       : the reference's own CPU self-play beside it                    -> cpu_baseline             (N = 1)
@@ -42,7 +44,7 @@ import torch  # noqa: E402
 
 METRIC = "mcts_node_expansions_per_sec"
 FLOPS_PER_EVAL = {7: 375.4e6, 19: 1012.4e6}
-ALL_LEGS = "precision,config3,config4,config5,soak,cpu"
+ALL_LEGS = "precision,config3,config4,config5,threads16,dedup,soak,cpu"
 
 
 def parse():
@@ -434,6 +436,71 @@ def leg_config5(a, local_rank, pv):
     return out
 
 
+def leg_threads16(a, rank, world, local_rank, pv):
+    """256 games x `playouts` playouts with search_threads = 16 inside every game (the reference's default schedule, exact): the
+    network batch is 256 x 16 rows per wave, ~14 of 16 rows of a game carry a leaf."""
+    from cchess_zero_b200.selfplay import SelfPlay
+    games, K = 256, 16
+    sp = SelfPlay(games, None, a.playouts, seeds=[rank * games + g for g in range(games)], device=local_rank, auto_reset=True, keep_records=False,
+                  plan_factory=lambda n: pv.native_plan(n, a.first_conv), search_threads=K, arena_words=1 << 21)
+    sp.capture_graph()
+    e = sp.engine
+    for _ in range(2):
+        sp.step()
+    torch.cuda.synchronize()
+    c0, w0 = e.counters(), sp.waves
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    steps = 4
+    for _ in range(steps):
+        sp.step()
+    ev1.record()
+    torch.cuda.synchronize()
+    c1 = e.raise_on_error()
+    ms = ev0.elapsed_time(ev1)
+    n = c1["n_expand"] - c0["n_expand"]
+    out = dict(workload="%d concurrent games x %d playouts, search_threads=%d inside every game (k_wave_fifo), res_block_nums=%d" % (games, a.playouts, K, a.res_blocks),
+               e2e=n / (ms * 1e-3), unit="expansions/s", plies_timed=steps, ms_per_step=ms / steps, waves_per_step=(sp.waves - w0) / steps,
+               network_rows_per_wave=games * K, leaves_per_wave=n / max(1, sp.waves - w0),
+               semantics="every game follows the reference's search_threads=16 coroutine schedule (canonical FIFO form, pinned to real uvloop runs)")
+    e.close()
+    return out
+
+
+def leg_dedup(a, rank, world, local_rank, pv):
+    """Board hashing (north_star): Zobrist keys of every evaluated leaf of one ply of the main workload.  Reports how many evaluations
+    a position-keyed cache could have saved: repeats inside a game (transpositions in one tree) and identical positions in the same
+    network batch (across games).  The keys never influence the search."""
+    from cchess_zero_b200.selfplay import SelfPlay
+    B = a.games
+    sp = SelfPlay(B, None, a.playouts, seeds=[rank * B + g for g in range(B)], device=local_rank, auto_reset=True, keep_records=False,
+                  plan=pv.native_plan(B, a.first_conv), hashing=True, arena_words=1 << 20)
+    sp.capture_graph()
+    for _ in range(6):                                          # six plies in: the games have diverged from the common start position
+        sp.step()
+    e = sp.engine
+    e.begin_search(a.playouts)
+    keys = []
+    lk = e.leaf_hashes()
+    for _ in range(a.playouts + 2):
+        sp.graph.replay()
+        keys.append(lk.clone())
+    torch.cuda.synchronize()
+    k = torch.stack(keys)                                        # [waves, B]; 0 = no leaf from that game in that wave
+    live = k != 0
+    total = int(live.sum())
+    srt, _ = torch.sort(k, dim=0)
+    per_game_unique = int(((srt[1:] != srt[:-1]) & (srt[1:] != 0)).sum() + (srt[0] != 0).sum())
+    srt_w, _ = torch.sort(k, dim=1)
+    per_wave_unique = int(((srt_w[:, 1:] != srt_w[:, :-1]) & (srt_w[:, 1:] != 0)).sum() + (srt_w[:, 0] != 0).sum())
+    all_unique = int(torch.unique(k[live]).numel())
+    e.close()
+    return dict(evaluated_leaves=total, repeats_within_a_game=1.0 - per_game_unique / max(1, total),
+                repeats_within_a_network_batch=1.0 - per_wave_unique / max(1, total), repeats_overall=1.0 - all_unique / max(1, total),
+                note="one ply (ply 7) of the main workload; a repeat = a leaf whose Zobrist key (position + side to move) was already evaluated "
+                     "in the same game's search / in the same wave's batch / anywhere in the ply")
+
+
 def leg_soak(runner, plies):
     """games/hour without selection bias.  All slots restart from the start position at ply 0 of the soak; L = length of the
     FIRST game of every slot, observed exactly up to the window T (longer ones are censored at T), so
@@ -529,6 +596,10 @@ def run_ours(a, rank, world, local_rank):
                                           "BASELINE configs[3]: %d games x %d playouts, res_block_nums=19" % (a.games, a.playouts))
         if "config5" in legs:
             extra["config5"] = leg_config5(a, local_rank, pv)
+        if "threads16" in legs:
+            extra["search_threads_16"] = leg_threads16(a, rank, world, local_rank, pv)
+        if "dedup" in legs:
+            extra["eval_dedup"] = leg_dedup(a, rank, world, local_rank, pv)
     cpu = None
     if rank == 0 and world == 1 and "cpu" in legs:
         try:

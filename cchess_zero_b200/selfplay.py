@@ -225,11 +225,13 @@ class SelfPlay:
 
     def __init__(self, n_games, forward, playouts, seeds=None, exploration=True, temperature=1,
                  nn_dtype=torch.float32, arena_words=0, auto_reset=True, device=None, keep_records=True, plan=None,
-                 plan_factory=None, lanes=1, engine=None, hashing=False):
+                 plan_factory=None, lanes=1, engine=None, hashing=False, search_threads=1):
         """plan: an InferencePlan / NativePlan (defines the input buffer, writes logits/value in place).
         plan_factory(n) + lanes=2: two half-batches, each with its own engine and plan; the search pipelines them so
         that one half's tree kernel runs under the other half's network (see capture_graph)."""
         self.B = n_games
+        # search_threads = K > 1: every game runs the reference's K-coroutine schedule (k_wave_fifo); the network batch has K rows per game
+        self.K = max(1, int(search_threads))
         if lanes > 1:
             assert plan_factory is not None and n_games % lanes == 0
             per = n_games // lanes
@@ -247,19 +249,21 @@ class SelfPlay:
         else:
             # `engine`: an object with the Engine interface (tests drive the host loop with a CPU stand-in); the product
             # always constructs the CUDA engine here
-            self.engine = engine if engine is not None else Engine(n_games, arena_words, device)
+            self.engine = engine if engine is not None else (Engine(n_games, arena_words, device, search_threads=self.K) if self.K > 1
+                                                             else Engine(n_games, arena_words, device))
             if hashing:                              # Zobrist keys of the pending leaves (must be on before a graph is captured)
                 self.engine.enable_hashing(True)
             dev = torch.device("cuda", self.engine.device) if engine is None else torch.device(getattr(engine, "torch_device", "cpu"))
+            rows = n_games * self.K
             if plan is None and plan_factory is not None:
-                plan = plan_factory(n_games)
-            self.logits = torch.zeros((n_games, NLABEL), dtype=torch.float32, device=dev)
-            self.value = torch.zeros((n_games,), dtype=torch.float32, device=dev)
+                plan = plan_factory(rows)
+            self.logits = torch.zeros((rows, NLABEL), dtype=torch.float32, device=dev)
+            self.value = torch.zeros((rows,), dtype=torch.float32, device=dev)
             if plan is not None:
-                self.nn_in = plan.make_input(n_games)
+                self.nn_in = plan.make_input(rows)
                 forward = lambda x: plan(x, self.logits, self.value)  # noqa: E731
             else:
-                self.nn_in = torch.zeros((n_games, 9, 10, 14), dtype=nn_dtype, device=dev)
+                self.nn_in = torch.zeros((rows, 9, 10, 14), dtype=nn_dtype, device=dev)
             self.lanes = None
         self.plan = plan
         self.forward = forward
@@ -301,8 +305,8 @@ class SelfPlay:
         out = self.forward(nn_in)
         if out is not None:
             lo, v = out
-            self.logits.copy_(lo.reshape(self.B, NLABEL))
-            self.value.copy_(v.reshape(self.B))
+            self.logits.copy_(lo.reshape(self.B * self.K, NLABEL))
+            self.value.copy_(v.reshape(self.B * self.K))
 
     def _capture_pipeline(self, warmup=3):
         """Two-lane software pipeline in ONE CUDA graph:
@@ -397,7 +401,7 @@ class SelfPlay:
             else:
                 e.wave(self.nn_in, self.logits, self.value)
             waves += 1
-            if waves > pmax and e.unfinished() == 0:
+            if waves > pmax // self.K and e.unfinished() == 0:       # (K leaves per game and wave in the search_threads = K schedule)
                 break
             if self.graph is None:
                 self._eval(self.nn_in)

@@ -98,3 +98,32 @@ def test_mcts_tree_honours_search_threads_and_play_continues_on_the_reused_tree(
     assert o.search_fifo(1, 1, 160, 16, "hash_pos") == 0
     mv, N, W, P, Q = o.root_children()
     assert [[a, n.N] for a, n in t.root.child.items()] == [[O.move_str(m), int(x)] for m, x in zip(mv, N)]
+
+
+def test_batched_selfplay_with_search_threads_16_equals_the_specification_game_by_game():
+    """SelfPlay(search_threads=16): every game follows the reference's K-coroutine schedule; the moves played (same per-game RNG
+    streams) and the visit counts equal a host loop over the C specification with tree re-use."""
+    from cchess_zero_b200.fakenet import FakeNet
+    from cchess_zero_b200.selfplay import SelfPlay
+    from oracle import oracle as O
+    B, P, net = 12, 64, "hash_pos"
+    sp = SelfPlay(B, FakeNet(net), P, seeds=[300 + i for i in range(B)], arena_words=1 << 18, auto_reset=False, search_threads=16)
+    for _ in range(5):
+        sp.step()
+    for g in (0, 5, 11):
+        rec, span = sp.records[g], sp._span[g]
+        t = O.Tree()
+        side, rr = 0, 0
+        for ply, lg in enumerate(span):
+            assert t.search_fifo(side, rr, P, 16, net) == 0
+            mv, N, W, Pp, Q = t.root_children()
+            n = int(lg["n"][g])
+            assert [int(x) for x in lg["visits"][g, :n]] == [int(x) for x in N], (g, ply)
+            c = int(lg["choice"][g])
+            b = np.zeros(90, np.uint8); t_board = O.Tree  # noqa: F841
+            root = np.zeros(90, np.uint8)
+            O.lib().co_tree_root_board(t.h, root.ctypes.data_as(__import__("ctypes").c_void_p))
+            cap = root[int(mv[c]) >> 7]
+            t.update(c)
+            side ^= 1
+            rr = rr + 1 if cap == 0 else 0
