@@ -120,10 +120,8 @@ def test_batched_selfplay_with_search_threads_16_equals_the_specification_game_b
             n = int(lg["n"][g])
             assert [int(x) for x in lg["visits"][g, :n]] == [int(x) for x in N], (g, ply)
             c = int(lg["choice"][g])
-            b = np.zeros(90, np.uint8); t_board = O.Tree  # noqa: F841
-            root = np.zeros(90, np.uint8)
-            O.lib().co_tree_root_board(t.h, root.ctypes.data_as(__import__("ctypes").c_void_p))
-            cap = root[int(mv[c]) >> 7]
+            assert np.array_equal(t.root_board(), lg["boards"][g])
+            cap = t.root_board()[int(mv[c]) >> 7]
             t.update(c)
             side ^= 1
             rr = rr + 1 if cap == 0 else 0
