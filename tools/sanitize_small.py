@@ -22,3 +22,21 @@ for _ in range(3):
     sp2.step()
 sp2.engine.raise_on_error()
 print("sanitize run ok", cnt[:2], enc.sum(), sp.plies, sp2.plies)
+# round 2: the search_threads = K event-loop kernel, the leaf-parallel kernel, hashing, and the cluster trunk (all cluster sizes)
+sp3 = SelfPlay(4, FakeNet("hash_pos"), 48, seeds=range(4), arena_words=1 << 16, auto_reset=True, search_threads=16)
+for _ in range(3):
+    sp3.step()
+sp3.engine.raise_on_error()
+sp4 = SelfPlay(8, FakeNet("hash_signed"), 24, seeds=range(8), arena_words=1 << 16, auto_reset=True, hashing=True)
+for _ in range(3):
+    sp4.step()
+sp4.engine.raise_on_error()
+from cchess_zero_b200.mcts import MCTS_tree
+t = MCTS_tree(rules.START_STATE, pv.forward, 1, leaf_parallel=4)
+t.main(rules.START_STATE, "w", 0, 32)
+boards = torch.zeros((3, 96), dtype=torch.uint8, device="cuda"); boards[:, :90] = torch.from_numpy(np.stack([b] * 3)).cuda()
+lo = torch.zeros((3, 2086), device="cuda"); vo = torch.zeros((3,), device="cuda")
+for cl in (1, 2, 4, 8):
+    pv.small_plan(4, cl)(boards, lo, vo)
+torch.cuda.synchronize()
+print("round-2 kernels ok", sp3.plies, sp4.plies, float(lo.abs().max()))
