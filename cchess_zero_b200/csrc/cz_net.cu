@@ -13,6 +13,8 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "../../include/cchess_b200.h"
 
@@ -267,33 +269,31 @@ __global__ void __launch_bounds__(256) k_head_conv(const __half *__restrict__ x 
     if (threadIdx.x < 12) hp[(size_t)pos * 192 + 180 + threadIdx.x] = __float2half(0.f);   // K padding of the policy GEMM
 }
 
-// heads, stage 2a: value MLP 90 -> 256 ReLU -> 1 tanh (policy_value_network.py:73-74), 4 positions per CTA
-constexpr int VM_POS = 4;
+// heads, stage 2a: value MLP 90 -> 256 ReLU -> 1 tanh (policy_value_network.py:73-74), 8 positions per CTA.
+// Thread t owns hidden unit t: its 90 first-layer weights are requested up front (90 independent coalesced loads, one L2 round trip
+// instead of nine), the positions' features are broadcast from shared memory.
+constexpr int VM_POS = 8;
 __global__ void __launch_bounds__(256) k_value_mlp(const float *__restrict__ hv /* [B][96] */, int B, const float *__restrict__ w1t /* [90][256] */,
                                                     const float *__restrict__ b1, const float *__restrict__ w2, const float *__restrict__ b2, float *__restrict__ value) {
     __shared__ float sh[VM_POS][96];
     __shared__ float red[VM_POS][8];
     const int p0 = blockIdx.x * VM_POS, t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    float wv[90];
+#pragma unroll
+    for (int k = 0; k < 90; k++) wv[k] = __ldg(w1t + k * 256 + t);
     for (int i = t; i < VM_POS * 96; i += 256) {
         const int p = i / 96;
         sh[p][i - p * 96] = p0 + p < B ? hv[(size_t)(p0 + p) * 96 + (i - p * 96)] : 0.f;
     }
+    const float bb = b1[t], w2v = w2[t];
     __syncthreads();
     float a[VM_POS];
-    const float bb = b1[t];
 #pragma unroll
     for (int p = 0; p < VM_POS; p++) a[p] = bb;
-#pragma unroll 1
-    for (int k0 = 0; k0 < 90; k0 += 10) {
-        float wv[10];
 #pragma unroll
-        for (int j = 0; j < 10; j++) wv[j] = __ldg(w1t + (k0 + j) * 256 + t);   // 10 independent coalesced loads in flight
+    for (int k = 0; k < 90; k++)
 #pragma unroll
-        for (int j = 0; j < 10; j++)
-#pragma unroll
-            for (int p = 0; p < VM_POS; p++) a[p] += wv[j] * sh[p][k0 + j];
-    }
-    const float w2v = w2[t];
+        for (int p = 0; p < VM_POS; p++) a[p] += wv[k] * sh[p][k];
 #pragma unroll
     for (int p = 0; p < VM_POS; p++) {
         float s = fmaxf(a[p], 0.f) * w2v;
@@ -317,6 +317,169 @@ __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], 
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+// ------------------------------------------------------------------------------------------
+// heads, stage 1 on the (legacy) tensor path: the same conv1x1 (128 -> 3) as one streaming pass.
+// k_head_conv above spends 5.5 M warp instructions on shuffles and conversions to read 23.6 MB (13 us, 22 % of DRAM peak).  Here a CTA
+// (one position, 6 warps) stages its 90 x 128 fp16 cells in shared memory with cp.async (rows padded to 272 B: conflict-free
+// ldmatrix), each warp multiplies its 16 cells with mma.sync m16n8k16 against the head weights held in registers as B fragments
+// (N = 8: policy 2 + value 1 + 5 zero columns).  The f32 weights enter as hi + lo fp16 pairs (two MMAs per k-step), so the result
+// equals the fp32-weight dot product to ~1e-7 relative: no precision is traded for the speed.  ~2 instructions per cell.
+// ------------------------------------------------------------------------------------------
+constexpr int HC_ROW = 136;   // halves per staged row (128 + 8 pad = 272 B)
+// TILED: hp is written in the UMMA operand layout k_policy_fc_tc consumes: [position tile of 128][k-chunk 24][128 positions][8 halves].
+template <bool TILED>
+__global__ void __launch_bounds__(192) k_head_conv_mma(const __half *__restrict__ x /* [B][90][128] */, int B, const float *__restrict__ wh /* [3][128] */,
+                                                        const float *__restrict__ bh /* [3] */, __half *__restrict__ hp /* [B][192] or tiled */,
+                                                        float *__restrict__ hv /* [B][96] */) {
+    __shared__ __align__(16) __half sx[96 * HC_ROW];
+    const int pos = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const __half *src = x + (size_t)pos * 90 * 128;
+    for (int i = tid; i < 96 * 16; i += 192) {                   // 16-byte chunks: row i / 16, chunk i % 16
+        const int r = i >> 4, c = i & 15;
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(sx + r * HC_ROW + c * 8);
+        if (r < 90) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + r * 128 + c * 8) : "memory");
+        else *reinterpret_cast<uint4 *>(sx + r * HC_ROW + c * 8) = make_uint4(0, 0, 0, 0);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    // B fragments (col-major K x N): lane (g = lane >> 2 -> output n, t = lane & 3) holds k = 16*ks + 2t, 2t+1 and + 8
+    const int g = lane >> 2, t = lane & 3;
+    uint32_t bhi[8][2], blo[8][2];
+#pragma unroll
+    for (int ks = 0; ks < 8; ks++)
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int k = ks * 16 + h * 8 + t * 2;
+            const float w0 = g < 3 ? __ldg(wh + g * 128 + k) : 0.f, w1 = g < 3 ? __ldg(wh + g * 128 + k + 1) : 0.f;
+            const __half h0 = __float2half_rn(w0), h1 = __float2half_rn(w1);
+            const __half l0 = __float2half_rn(w0 - __half2float(h0)), l1 = __float2half_rn(w1 - __half2float(h1));
+            __half2 hh = __halves2half2(h0, h1), ll = __halves2half2(l0, l1);
+            bhi[ks][h] = *reinterpret_cast<uint32_t *>(&hh);
+            blo[ks][h] = *reinterpret_cast<uint32_t *>(&ll);
+        }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const int row0 = warp * 16;
+    // ldmatrix.x4: lanes 0-15 address rows row0 + (lane & 15) at k-offset 0, lanes 16-31 the same rows at k-offset 8
+    const uint32_t abase = (uint32_t)__cvta_generic_to_shared(sx + (row0 + (lane & 15)) * HC_ROW + (lane >> 4) * 8);
+#pragma unroll
+    for (int ks = 0; ks < 8; ks++) {
+        uint32_t a[4];
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]) : "r"(abase + ks * 32));
+        mma16816(acc, a, bhi[ks]);
+        mma16816(acc, a, blo[ks]);
+    }
+    // accumulator layout: rows row0 + g and row0 + g + 8, columns 2t, 2t + 1
+    const float b0 = bh[0], b1 = bh[1], b2 = bh[2];
+#pragma unroll
+    for (int hlf = 0; hlf < 2; hlf++) {
+        const int cell = row0 + g + hlf * 8;
+        if (cell < 90) {
+            // flatten order of tf.reshape on NHWC (policy_value_network.py:62, 72): index = cell*2 + c
+            if (t == 0) {
+                const __half2 v = __floats2half2_rn(fmaxf(acc[hlf * 2] + b0, 0.f), fmaxf(acc[hlf * 2 + 1] + b1, 0.f));
+                const int k = cell * 2;                              // feature index (even): chunk k / 8, offset k % 8
+                if (TILED) *reinterpret_cast<__half2 *>(hp + ((size_t)(pos >> 7) * 24 + (k >> 3)) * 1024 + (size_t)(pos & 127) * 8 + (k & 7)) = v;
+                else *reinterpret_cast<__half2 *>(hp + (size_t)pos * 192 + k) = v;
+            }
+            if (t == 1) hv[(size_t)pos * 96 + cell] = fmaxf(acc[hlf * 2] + b2, 0.f);
+        }
+    }
+    if (tid < 12) {                                                  // K padding of the policy GEMM (features 180..191)
+        const int k = 180 + tid;
+        if (TILED) hp[((size_t)(pos >> 7) * 24 + (k >> 3)) * 1024 + (size_t)(pos & 127) * 8 + (k & 7)] = __float2half(0.f);
+        else hp[(size_t)pos * 192 + k] = __float2half(0.f);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// heads, stage 2b on the 5th-generation tensor cores: logits[pos][label] = hp[pos] . wp[label] + bp[label]   (tcgen05 + TMEM)
+//   D[128 labels][128 positions] (f32, TMEM) = A[128][192] . B[192][128]: A = a 128-label tile of the FC weights, B = a 128-position
+//   tile of the head features, both already in the canonical K-major no-swizzle UMMA layout in global memory (weights: prepared once
+//   on the host; features: written that way by k_head_conv_mma<true>), so each operand is ONE 48 KB bulk async copy
+//   (cp.async.bulk, SASS UBLKCP) signalling an mbarrier.  One elected thread issues 12 tcgen05.mma (M128 N128 K16), commits; the four
+//   warps read their TMEM lane quarter (lane = label) 32 positions at a time and store logits[pos][label0 .. label0+31] -- 128
+//   contiguous bytes per warp and position.  136 CTAs for 1024 positions x 2086 labels, one tile each.
+// ------------------------------------------------------------------------------------------
+constexpr int FC_TILE_BYTES = 24 * 128 * 16;   // 49 152 B per operand tile
+__global__ void __launch_bounds__(128) k_policy_fc_tc(const uint4 *__restrict__ hp_tiled, int B, const uint4 *__restrict__ wp_tiled,
+                                                       const float *__restrict__ bp /* [>= 2176] */, float *__restrict__ logits /* [B][2086] */) {
+    extern __shared__ __align__(128) unsigned char smem_fc_tc[];
+    unsigned char *sA = smem_fc_tc, *sB = smem_fc_tc + FC_TILE_BYTES;
+    __shared__ __align__(8) uint64_t bar_ld, bar_mma;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int mt = blockIdx.y, nt = blockIdx.x;                     // label tile, position tile
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(128u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar_ld)), "r"(1u));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar_mma)), "r"(1u));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_slot;
+    if (tid == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bar_ld)), "r"(2u * FC_TILE_BYTES) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(sA)), "l"(reinterpret_cast<const unsigned char *>(wp_tiled) + (size_t)mt * FC_TILE_BYTES), "r"(FC_TILE_BYTES), "r"(smem_u32(&bar_ld)) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(sB)), "l"(reinterpret_cast<const unsigned char *>(hp_tiled) + (size_t)nt * FC_TILE_BYTES), "r"(FC_TILE_BYTES), "r"(smem_u32(&bar_ld)) : "memory");
+        {   // operands landed
+            const uint32_t bar = smem_u32(&bar_ld);
+            asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
+                         ::"r"(bar), "r"(0u) : "memory");
+        }
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t idesc = (1u << 4) | (16u << 17) | (8u << 24);          // f32 accumulate, f16 x f16, N = 128, M = 128
+        const uint64_t da = umma_desc_kmajor_noswizzle(smem_u32(sA)), db = umma_desc_kmajor_noswizzle(smem_u32(sB));
+#pragma unroll
+        for (int ks = 0; ks < 12; ks++) {
+            const uint64_t a = da + (uint64_t)((ks * 4096) >> 4), b = db + (uint64_t)((ks * 4096) >> 4);   // two k-chunks per MMA
+            const uint32_t acc = ks > 0 ? 1u : 0u;
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                         ::"r"(tmem), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar_mma)) : "memory");
+    }
+    {
+        const uint32_t bar = smem_u32(&bar_mma);
+        asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
+                     ::"r"(bar), "r"(0u) : "memory");
+    }
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int label = mt * 128 + warp * 32 + lane;
+    const float bias = bp[label];
+    const bool lab_ok = label < CZ_NLABEL;
+#pragma unroll 1
+    for (int q = 0; q < 4; q++) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(q * 32);
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                     "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                     "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                       "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                       "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                       "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                     : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+            const int pos = nt * 128 + q * 32 + j;
+            if (lab_ok && pos < B) logits[(size_t)pos * CZ_NLABEL + label] = __uint_as_float(v[j]) + bias;
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128u));
 }
 
 constexpr int NPAD = 2112;   // 33 * 64 >= 2086
@@ -429,9 +592,44 @@ int cz_net_heads_fc(const void *hp, const float *hv, int B, const float *w1t, co
 int cz_net_heads(const void *x, int B, const float *wh, const float *bh, const float *w1t, const float *b1, const float *w2, const float *b2,
                  const void *wp, const float *bp, void *hp_scratch, float *hv_scratch, float *logits, float *value, void *stream) {
     if (!x || !wh || !bh || !hp_scratch || !hv_scratch || B <= 0) return CZ_EINVAL;
-    k_head_conv<<<B, 256, 0, (cudaStream_t)stream>>>((const __half *)x, B, wh, bh, (__half *)hp_scratch, hv_scratch);
+    static const bool legacy = getenv("CCHESS_HEAD_CONV") && !strcmp(getenv("CCHESS_HEAD_CONV"), "simt");
+    if (legacy) k_head_conv<<<B, 256, 0, (cudaStream_t)stream>>>((const __half *)x, B, wh, bh, (__half *)hp_scratch, hv_scratch);
+    else k_head_conv_mma<false><<<B, 192, 0, (cudaStream_t)stream>>>((const __half *)x, B, wh, bh, (__half *)hp_scratch, hv_scratch);
     if (cudaGetLastError() != cudaSuccess) return CZ_ECUDA;
     return cz_net_heads_fc(hp_scratch, hv_scratch, B, w1t, b1, w2, b2, wp, bp, logits, value, stream);
+}
+
+
+// The heads for large batches: conv1x1 on mma.sync writing the policy features in the UMMA-tiled layout, value MLP on a side stream,
+// policy FC on tcgen05 (k_policy_fc_tc).  wp_tiled: dev fp16 [17 label tiles][24 k-chunks][128 labels][8] (labels >= 2086 zero),
+// bp: dev f32 [2176]; hp_tiled scratch: fp16, ceil(B/128) * 49152 bytes, ZERO-INITIALISED by the caller (rows beyond B stay zero).
+int cz_net_heads_tc(const void *x, int B, const float *wh, const float *bh, const float *w1t, const float *b1, const float *w2, const float *b2,
+                    const void *wp_tiled, const float *bp, void *hp_tiled_scratch, float *hv_scratch, float *logits, float *value, void *stream) {
+    if (!x || !wh || !bh || !w1t || !b1 || !w2 || !b2 || !wp_tiled || !bp || !hp_tiled_scratch || !hv_scratch || !logits || !value || B <= 0) return CZ_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int smem = 2 * FC_TILE_BYTES;
+    if (cudaFuncSetAttribute(k_policy_fc_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return CZ_ECUDA;
+    k_head_conv_mma<true><<<B, 192, 0, st>>>((const __half *)x, B, wh, bh, (__half *)hp_tiled_scratch, hv_scratch);
+    if (cudaGetLastError() != cudaSuccess) return CZ_ECUDA;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return CZ_ECUDA;
+    static cudaStream_t side[64] = {nullptr};
+    static cudaEvent_t ev_fork[64] = {nullptr}, ev_join[64] = {nullptr};
+    if (!side[dev]) {   // created on the first (eager, warm-up) call, never during capture
+        if (cudaStreamCreateWithFlags(&side[dev], cudaStreamNonBlocking) != cudaSuccess) return CZ_ECUDA;
+        if (cudaEventCreateWithFlags(&ev_fork[dev], cudaEventDisableTiming) != cudaSuccess) return CZ_ECUDA;
+        if (cudaEventCreateWithFlags(&ev_join[dev], cudaEventDisableTiming) != cudaSuccess) return CZ_ECUDA;
+    }
+    if (cudaEventRecord(ev_fork[dev], st) != cudaSuccess) return CZ_ECUDA;
+    if (cudaStreamWaitEvent(side[dev], ev_fork[dev], 0) != cudaSuccess) return CZ_ECUDA;
+    k_value_mlp<<<(B + VM_POS - 1) / VM_POS, 256, 0, side[dev]>>>(hv_scratch, B, w1t, b1, w2, b2, value);
+    if (cudaGetLastError() != cudaSuccess) return CZ_ECUDA;
+    if (cudaEventRecord(ev_join[dev], side[dev]) != cudaSuccess) return CZ_ECUDA;
+    dim3 grid((B + 127) / 128, 17);
+    k_policy_fc_tc<<<grid, 128, smem, st>>>((const uint4 *)hp_tiled_scratch, B, (const uint4 *)wp_tiled, bp, logits);
+    if (cudaGetLastError() != cudaSuccess) return CZ_ECUDA;
+    if (cudaStreamWaitEvent(st, ev_join[dev], 0) != cudaSuccess) return CZ_ECUDA;
+    return CZ_OK;
 }
 
 }  // extern "C"

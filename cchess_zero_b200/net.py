@@ -238,6 +238,9 @@ class NativePlan:
         self.x1 = torch.empty((max_batch, 9, 10, 128), dtype=torch.float16, device=dev)
         self.hp = torch.zeros((max_batch, 192), dtype=torch.float16, device=dev)
         self.hv = torch.zeros((max_batch, 96), dtype=torch.float32, device=dev)
+        # policy features in the UMMA-tiled layout of the tcgen05 policy FC (rows beyond the batch stay zero)
+        self.hp_tiled = torch.zeros(((max_batch + 127) // 128, 24, 128, 8), dtype=torch.float16, device=dev)
+        self.heads = os.environ.get("CCHESS_HEADS", "tc")          # "tc": tcgen05 policy FC (batches >= 128); "mma": the mma.sync kernels
 
     def _derive(self):
         """Kernel-layout copies of the ends' weights, derived from the folded base plan."""
@@ -257,7 +260,13 @@ class NativePlan:
             wp[:NLABEL, :180] = net.p_fc.weight.detach().to(torch.float16)
             bp = torch.zeros((2112,), dtype=torch.float32, device=dev)
             bp[:NLABEL] = net.p_fc.bias.detach().float()
+            # policy FC weights as tcgen05 operand tiles: [17 label tiles][24 k-chunks][128 labels][8 features]
+            wp_pad = torch.zeros((2176, 192), dtype=torch.float16, device=dev)
+            wp_pad[:2112] = wp
+            bp_pad = torch.zeros((2176,), dtype=torch.float32, device=dev)
+            bp_pad[:2112] = bp
             return dict(w1=w1, b1=b1, w1_umma=wpad.reshape(18, 8, 16, 8).permute(0, 2, 3, 1).contiguous(),
+                        wp_tiled=wp_pad.reshape(17, 128, 24, 8).permute(0, 2, 1, 3).contiguous(), bp_pad=bp_pad,
                         wh=wh.float().reshape(3, 128).contiguous(), bh=bh.float().contiguous(),
                         w1t=net.v_fc1.weight.detach().float().t().contiguous(),        # [90,256]
                         bv1=net.v_fc1.bias.detach().float().contiguous(),
@@ -298,9 +307,14 @@ class NativePlan:
             x = self._base._conv_add_relu(y, c2, x)
         if not x.is_contiguous(memory_format=torch.channels_last):
             x = x.contiguous(memory_format=torch.channels_last)
-        rc = self._lib.cz_net_heads(x.data_ptr(), B, self.wh.data_ptr(), self.bh.data_ptr(), self.w1t.data_ptr(), self.bv1.data_ptr(),
-                                    self.w2.data_ptr(), self.b2t.data_ptr(), self.wp.data_ptr(), self.bp.data_ptr(), self.hp.data_ptr(), self.hv.data_ptr(),
-                                    logits_out.data_ptr(), value_out.data_ptr(), st)
+        if self.heads == "tc" and B >= 128:
+            rc = self._lib.cz_net_heads_tc(x.data_ptr(), B, self.wh.data_ptr(), self.bh.data_ptr(), self.w1t.data_ptr(), self.bv1.data_ptr(),
+                                           self.w2.data_ptr(), self.b2t.data_ptr(), self.wp_tiled.data_ptr(), self.bp_pad.data_ptr(),
+                                           self.hp_tiled.data_ptr(), self.hv.data_ptr(), logits_out.data_ptr(), value_out.data_ptr(), st)
+        else:
+            rc = self._lib.cz_net_heads(x.data_ptr(), B, self.wh.data_ptr(), self.bh.data_ptr(), self.w1t.data_ptr(), self.bv1.data_ptr(),
+                                        self.w2.data_ptr(), self.b2t.data_ptr(), self.wp.data_ptr(), self.bp.data_ptr(), self.hp.data_ptr(), self.hv.data_ptr(),
+                                        logits_out.data_ptr(), value_out.data_ptr(), st)
         if rc:
             raise RuntimeError("cz_net_heads failed (%d)" % rc)
         self._keep = x

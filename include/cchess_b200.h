@@ -209,6 +209,12 @@ int cz_host_choose_moves(int n_games, const uint8_t *live, const int32_t *n_chil
                          uint32_t *mt_states /* [B][626] */, int32_t *choice /* [B] */, double *probs /* [B][128] */, uint8_t *fallback /* [B] */,
                          int n_threads);
 
+/* cz_net_heads for large batches: policy FC on tcgen05 + TMEM (operands bulk-copied in the UMMA layout), 1x1 head convolution on
+ * mma.sync, value MLP concurrently.  wp_tiled: dev fp16 [17 label tiles][24 k-chunks][128 labels][8 features] (labels >= 2086 zero),
+ * bp f32 [2176]; hp_tiled_scratch: fp16, ceil(B/128) * 49152 bytes, zero-initialised once by the caller. */
+int cz_net_heads_tc(const void *x, int B, const float *wh, const float *bh, const float *w1t, const float *b1, const float *w2, const float *b2,
+                    const void *wp_tiled, const float *bp, void *hp_tiled_scratch, float *hv_scratch, float *logits, float *value, void *stream);
+
 /* The second half of cz_net_heads alone: value MLP and policy FC on head features that are already computed
  * (hp fp16 [B][192], hv f32 [B][96]) -- what follows cz_net_tower_small. */
 int cz_net_heads_fc(const void *hp, const float *hv, int B, const float *w1t, const float *b1, const float *w2, const float *b2,

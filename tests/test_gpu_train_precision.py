@@ -182,7 +182,7 @@ def test_search_uses_trained_weights_after_train_step_and_restore(tmp_path, monk
     p1, b1 = root_priors(), batch_priors()
     assert not np.array_equal(p0, p1), "MCTS_tree searched with stale weights"
     assert not np.array_equal(b0, b1), "SelfPlay searched with stale weights"
-    assert np.allclose(p1, b1, rtol=1e-6, atol=1e-7)                   # both paths now evaluate the same (new) network
+    assert np.allclose(p1, b1, rtol=2e-2, atol=2e-3)                   # both paths now evaluate the same (new) network (cluster trunk vs cuDNN trunk: fp16 rounding apart)
     path = pv.save(3)
     for _ in range(2):
         pv.train_step(x, pi, z, 0.05)
@@ -284,3 +284,37 @@ def test_small_tower_cluster_kernel_matches_library_plan_and_fp64(blocks, cluste
     small(boards, lo2, vo2)                               # run-to-run identical
     torch.cuda.synchronize()
     assert torch.equal(lo, lo2) and torch.equal(vo, vo2)
+
+
+@pytest.mark.parametrize("B", [128, 203, 1024])
+def test_tcgen05_policy_fc_and_mma_head_conv_match_the_simt_heads(B):
+    """cz_net_heads_tc (mma.sync head conv writing UMMA-tiled features, tcgen05 policy FC, 8-position value MLP) against the round-1
+    kernels (cz_net_heads with CCHESS_HEAD_CONV=simt semantics) and against fp64, on a random trunk output."""
+    from cchess_zero_b200.net import NativePlan, PolicyValueNet
+    torch.manual_seed(2)
+    net = PolicyValueNet(2).eval()
+    with torch.no_grad():
+        for m in net.modules():
+            if isinstance(m, (torch.nn.Conv2d, torch.nn.Linear)):
+                m.bias.uniform_(-0.2, 0.2)
+    net = net.cuda().to(memory_format=torch.channels_last)
+    x, canon = _positions(B, seed=11)
+    boards = torch.from_numpy(canon).cuda()
+    outs = {}
+    for mode in ("tc", "mma"):
+        plan = NativePlan(net, B)
+        plan.heads = mode
+        lo = torch.zeros((B, 2086), device="cuda"); vo = torch.zeros((B,), device="cuda")
+        plan(boards, lo, vo)
+        plan(boards, lo, vo)
+        torch.cuda.synchronize()
+        outs[mode] = (lo, vo)
+    with torch.no_grad():
+        rl, rv = net.double()(torch.from_numpy(x).double().cuda())
+    d_l = (outs["tc"][0] - outs["mma"][0]).abs().max().item()
+    d_v = (outs["tc"][1] - outs["mma"][1]).abs().max().item()
+    e_tc = max((outs["tc"][0].double() - rl).abs().max().item(), (outs["tc"][1].double() - rv.reshape(-1)).abs().max().item())
+    e_mma = max((outs["mma"][0].double() - rl).abs().max().item(), (outs["mma"][1].double() - rv.reshape(-1)).abs().max().item())
+    print("B=%d: tc vs mma heads: logits %.3g value %.3g; vs fp64: tc %.3g, mma %.3g" % (B, d_l, d_v, e_tc, e_mma))
+    assert d_l < 1e-4 and d_v < 1e-5          # same fp16 operands, fp32 accumulation: only the summation order differs
+    assert e_tc < max(1e-3, 1.25 * e_mma)

@@ -34,7 +34,7 @@ for it in range(300):
         y = plan._base._conv_relu(x, c1, 1)
         x = plan._base._conv_add_relu(y, c2, x)
     t[3].record()
-    lib.cz_net_heads(x.data_ptr(), B, plan.wh.data_ptr(), plan.bh.data_ptr(), plan.w1t.data_ptr(), plan.bv1.data_ptr(), plan.w2.data_ptr(), plan.b2,
+    lib.cz_net_heads(x.data_ptr(), B, plan.wh.data_ptr(), plan.bh.data_ptr(), plan.w1t.data_ptr(), plan.bv1.data_ptr(), plan.w2.data_ptr(), plan.b2t.data_ptr(),
                      plan.wp.data_ptr(), plan.bp.data_ptr(), plan.hp.data_ptr(), plan.hv.data_ptr(), sp.logits.data_ptr(), sp.value.data_ptr(), st)
     t[4].record()
     if it >= 50:
