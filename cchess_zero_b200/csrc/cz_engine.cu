@@ -283,6 +283,7 @@ __device__ void store_leaf_at(uint8_t *leaf_board, WarpSmem &S, int side, T *nn_
     } else {
         cz::warp_encode<T>(S.board, side, nn_in + row * CZ_ENC_LEN, lane);
     }
+    __syncwarp();      // every lane is done reading S.board before the caller stages the next position in it (racecheck, round 2)
 }
 
 // The PUCT inputs of one node block in registers: lane l holds children l, l+32, l+64, l+96.

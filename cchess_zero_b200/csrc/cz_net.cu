@@ -1,15 +1,20 @@
 // cz_net.cu -- hand-written sm_100a kernels for the two ends of the policy-value network
 // (policy_value_network.py:45-74): the first convolution evaluated straight from board bytes, and the
-// fused policy / value heads.  The residual tower in between stays on the library tcgen05 path.
+// fused policy / value heads.  The batch-1024 residual tower in between stays on the library tcgen05 path.
 //
-//   k_first_conv : canonical board bytes -> conv3x3(14->128)+bias+ReLU output, fp16 NHWC [B][90][128].
-//                  The 14-plane input is one-hot and <= 32 of its 1260 cells are set, so the convolution is a
-//                  gather-add of weight rows: out[cell][:] = b + sum over the 3x3 neighbourhood of W[tap][piece][:].
-//                  The [9][10][14] tensor (and the reference's rank*9+file indexing, main.py:550-555) is never
-//                  materialised: image cell (r, f) reads canonical board byte r*9+f.
-//   k_head_conv  : conv1x1(128->3)+bias+ReLU (policy 2 ch + value 1 ch), then the value MLP
-//                  90 -> 256 ReLU -> 1 tanh; writes hp fp16 [B][192] (flatten order (h, w, c), zero padded).
-//   k_policy_fc  : logits[B][2086] = hp . Wp^T + bp with mma.sync m16n8k16 (fp16 in, fp32 accumulate, fp32 out).
+//   k_first_conv      : canonical board bytes -> conv3x3(14->128)+bias+ReLU output, fp16 NHWC [B][90][128].
+//                       The 14-plane input is one-hot and <= 32 of its 1260 cells are set, so the convolution is a
+//                       gather-add of weight rows: out[cell][:] = b + sum over the 3x3 neighbourhood of W[tap][piece][:].
+//                       The [9][10][14] tensor (and the reference's rank*9+file indexing, main.py:550-555) is never
+//                       materialised: image cell (r, f) reads canonical board byte r*9+f.
+//   k_first_conv_tc   : the same layer on tcgen05 + TMEM (one-hot im2col operand built in shared memory).
+//   k_head_conv_mma   : conv1x1(128->3)+bias+ReLU (policy 2 ch + value 1 ch) as one streaming pass on mma.sync (hi+lo fp16
+//                       weight split: fp32-weight accuracy); writes the policy features hp either row-major fp16 [B][192]
+//                       (flatten order (h, w, c), zero padded) or directly as tcgen05 operand tiles.  k_head_conv: round-1 SIMT form.
+//   k_value_mlp       : 90 -> 256 ReLU -> 1 tanh, 8 positions per CTA, all 90 weights of a hidden unit requested up front.
+//   k_policy_fc_tc    : logits[B][2086] = hp . Wp^T + bp on tcgen05 + TMEM; both operands arrive as 48 KB bulk async copies
+//                       (cp.async.bulk) already in the UMMA layout; fp32 logits stored 128 B per warp and position.
+//   k_policy_fc       : the same on mma.sync m16n8k16 (small batches, row-major hp).
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
