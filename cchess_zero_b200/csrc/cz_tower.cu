@@ -25,6 +25,8 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "../../include/cchess_b200.h"
 
@@ -85,6 +87,16 @@ __device__ __forceinline__ void st_cluster_v4(uint32_t local_addr, uint32_t rank
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_addr), "r"(rank));
     asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ra), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+// Async-proxy store of 16 bytes into CTA `rank`'s shared memory that completes 16 tx-bytes on THAT CTA's mbarrier: the designed
+// DSMEM producer -> consumer path.  Written through the async proxy, so the tensor cores (async proxy) need no proxy fence, and the
+// barrier completes by byte count: no arrive loop, no release fence on the critical path.
+__device__ __forceinline__ void st_async_v4(uint32_t local_addr, uint32_t local_bar, uint32_t rank, uint4 v) {
+    uint32_t ra, rb;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_addr), "r"(rank));
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rb) : "r"(local_bar), "r"(rank));
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+                 ::"r"(ra), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(rb) : "memory");
+}
 __device__ __forceinline__ uint32_t cluster_rank() {
     uint32_t r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -106,8 +118,10 @@ struct TowerArgs {
     int n_conv;                // 2 * res_block_nums
 };
 
-template <int CL>
+// ASYNC_ST: image slices travel by st.async (complete_tx on the receiver's barrier) instead of generic stores + proxy fence + arrives.
+template <int CL, bool ASYNC_ST>
 __global__ void __launch_bounds__(NTHREADS, 1) k_tower_small(const __grid_constant__ CUtensorMap wmap, TowerArgs a) {
+    constexpr uint32_t IMAGE_TX = 128u * 16u * 16u;        // bytes every CTA receives per image: 128 rows x 16 chunks x 16 B
     constexpr int NC = 128 / CL;                           // output channels of this CTA
     constexpr int STAGE_BYTES = NC * 256;                  // one tap of this CTA's weight slice: [16 k-chunks][NC rows][8 halves]
     constexpr int S = CL == 1 ? 4 : (CL == 2 ? 8 : 16);    // ring depth
@@ -129,14 +143,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tower_small(const __grid_consta
     if (tid == 0) {
         for (int s = 0; s < S; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(&accum_full, 1);
-        mbar_init(&act_ready[0], CL * 4);
-        mbar_init(&act_ready[1], CL * 4);
+        mbar_init(&act_ready[0], ASYNC_ST ? 1 : CL * 4);     // ASYNC_ST: one arrive.expect_tx by the MMA warp + IMAGE_TX bytes
+        mbar_init(&act_ready[1], ASYNC_ST ? 1 : CL * 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
+    asm volatile("fence.proxy.async;" ::: "memory");     // the zeroed images (generic proxy) are what the tensor cores will read as padding
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -167,6 +182,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tower_small(const __grid_consta
             int stage = 0;
             uint32_t phase = 0;
             for (int L = 0; L < a.n_conv; L++) {
+                if (ASYNC_ST) mbar_expect_tx(&act_ready[L & 1], IMAGE_TX);      // our arrival + the byte count of image L
                 mbar_wait_cluster(&act_ready[L & 1], (uint32_t)((L >> 1) & 1));   // image L (this layer's input) is complete in OUR shared memory
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t abase = smem_u32((L & 1) ? bufY : bufX);          // conv1 of a block reads X, conv2 reads Y
@@ -234,11 +250,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tower_small(const __grid_consta
                 const uint32_t dst = smem_u32(bufX) + (uint32_t)((rank * (NC / 8) + c8) * LBO_A) + rowoff;
 #pragma unroll
                 for (int q = 0; q < CL; q++) {
-                    if (CL == 1) *reinterpret_cast<uint4 *>(bufX + (c8 * LBO_A) + rowoff) = o;
+                    if (ASYNC_ST) st_async_v4(dst, smem_u32(&act_ready[0]), (uint32_t)q, o);
+                    else if (CL == 1) *reinterpret_cast<uint4 *>(bufX + (c8 * LBO_A) + rowoff) = o;
                     else st_cluster_v4(dst, (uint32_t)q, o);
                 }
             }
-            publish_image<CL>(&act_ready[0], lane);                               // image 0
+            if (!ASYNC_ST) publish_image<CL>(&act_ready[0], lane);                // image 0
         }
         // ---- residual tower epilogues ----
         uint32_t fphase = 0;
@@ -248,6 +265,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tower_small(const __grid_consta
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const bool second = L & 1;                        // conv2 of a block: + skip (the block input, still in X), result back into X
             unsigned char *dstbuf = second ? bufX : bufY;
+            // the skip operand (image L - 1, in X) arrived through the async proxy: observe its barrier before reading it generically
+            if (ASYNC_ST && second) mbar_wait(&act_ready[(L - 1) & 1], (uint32_t)(((L - 1) >> 1) & 1));
             const float *bl = s_bias + (1 + L) * NC;
 #pragma unroll
             for (int c16 = 0; c16 < NC / 16; c16++) {
@@ -277,7 +296,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tower_small(const __grid_consta
 #pragma unroll
                     for (int k = 0; k < 4; k++)
                         oh[k] = cell ? __floats2half2_rn(fmaxf(f[2 * k], 0.f), fmaxf(f[2 * k + 1], 0.f)) : __floats2half2_rn(0.f, 0.f);
-                    if (CL == 1) *reinterpret_cast<uint4 *>(dstbuf + choff) = o;
+                    if (ASYNC_ST) {
+#pragma unroll
+                        for (int q = 0; q < CL; q++) st_async_v4(smem_u32(dstbuf) + choff, smem_u32(&act_ready[(L + 1) & 1]), (uint32_t)q, o);
+                    } else if (CL == 1) *reinterpret_cast<uint4 *>(dstbuf + choff) = o;
                     else {
 #pragma unroll
                         for (int q = 0; q < CL; q++) st_cluster_v4(smem_u32(dstbuf) + choff, (uint32_t)q, o);
@@ -285,11 +307,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tower_small(const __grid_consta
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");       // our TMEM reads are done before the next layer's MMAs may overwrite
-            publish_image<CL>(&act_ready[(L + 1) & 1], lane);                      // image L + 1
+            if (!ASYNC_ST) publish_image<CL>(&act_ready[(L + 1) & 1], lane);       // image L + 1
         }
         // ---- heads: conv1x1 (128 -> 2 policy + 1 value) + bias + ReLU on the final image (in X), CTA 0 writes ----
         {
-            if (tid == 0) mbar_wait_cluster(&act_ready[a.n_conv & 1], (uint32_t)((a.n_conv >> 1) & 1));   // the final image (index n_conv) is complete
+            if (tid == 0) {
+                if (ASYNC_ST) mbar_expect_tx(&act_ready[a.n_conv & 1], IMAGE_TX);
+                mbar_wait_cluster(&act_ready[a.n_conv & 1], (uint32_t)((a.n_conv >> 1) & 1));                // the final image (index n_conv) is complete
+            }
             asm volatile("bar.sync 1, 128;" ::: "memory");                         // the four epilogue warps, ordered behind thread 0's cluster-scope acquire
             if (rank == 0 && cell) {
                 float s0 = a.bh[0], s1 = a.bh[1], s2 = a.bh[2];
@@ -334,12 +359,12 @@ EncodeTiledFn encode_tiled() {
     return fn;
 }
 
-template <int CL>
+template <int CL, bool ASYNC_ST>
 int launch_tower(const CUtensorMap &map, const TowerArgs &a, cudaStream_t st) {
     constexpr int NC = 128 / CL, S = CL == 1 ? 4 : (CL == 2 ? 8 : 16);
     const int n_layers = 1 + a.n_conv;
     const size_t smem = 2 * (size_t)A_BYTES + (size_t)S * NC * 256 + (size_t)n_layers * NC * 4;
-    if (cudaFuncSetAttribute(k_tower_small<CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return CZ_ECUDA;
+    if (cudaFuncSetAttribute(k_tower_small<CL, ASYNC_ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return CZ_ECUDA;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(a.n_pos * CL));
     cfg.blockDim = dim3(NTHREADS);
@@ -350,7 +375,7 @@ int launch_tower(const CUtensorMap &map, const TowerArgs &a, cudaStream_t st) {
     attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, k_tower_small<CL>, map, a) == cudaSuccess ? CZ_OK : CZ_ECUDA;
+    return cudaLaunchKernelEx(&cfg, k_tower_small<CL, ASYNC_ST>, map, a) == cudaSuccess ? CZ_OK : CZ_ECUDA;
 }
 
 }  // namespace
@@ -379,11 +404,20 @@ int cz_net_tower_small(const uint8_t *canon_boards, int n_pos, int cluster, int 
     a.boards = canon_boards; a.w1 = (const __half *)w1; a.bias = bias; a.wh = wh; a.bh = bh; a.hp = (__half *)hp; a.hv = hv;
     a.n_pos = n_pos; a.n_conv = n_conv;
     cudaStream_t st = (cudaStream_t)stream;
+    static const bool generic_st = getenv("CCHESS_TOWER_ST") && !strcmp(getenv("CCHESS_TOWER_ST"), "generic");
+    if (generic_st) {
+        switch (cluster) {
+            case 1: return launch_tower<1, false>(map, a, st);
+            case 2: return launch_tower<2, false>(map, a, st);
+            case 4: return launch_tower<4, false>(map, a, st);
+            default: return launch_tower<8, false>(map, a, st);
+        }
+    }
     switch (cluster) {
-        case 1: return launch_tower<1>(map, a, st);
-        case 2: return launch_tower<2>(map, a, st);
-        case 4: return launch_tower<4>(map, a, st);
-        default: return launch_tower<8>(map, a, st);
+        case 1: return launch_tower<1, true>(map, a, st);
+        case 2: return launch_tower<2, true>(map, a, st);
+        case 4: return launch_tower<4, true>(map, a, st);
+        default: return launch_tower<8, true>(map, a, st);
     }
 }
 
