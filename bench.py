@@ -311,16 +311,15 @@ class Runner:
         ev0.record()
         for _ in range(steps):
             out = sp.step()
-            if self.gather is not None:                         # previous step's gather completes here, under this step's search
+            if self.gather is not None:                         # counts of step s, payload of step s-1, landed tuples of step s-2: all asynchronous
+                self.gather.start([r for _, r in out["finished"]])
                 tb = self.gather.finish()
                 if tb is not None:
                     self.tuples_gathered += len(tb)
-                self.gather.start([r for _, r in out["finished"]])
             if on_step:
                 on_step(out)
         if self.gather is not None:
-            tb = self.gather.finish()
-            self.tuples_gathered += len(tb) if tb is not None else 0
+            self.tuples_gathered += len(self.gather.drain())
         ev1.record()
         self.barrier()
         wall = time.perf_counter() - t0

@@ -115,64 +115,86 @@ def unpack_records(buf, n):
 
 
 class AsyncTupleGather:
-    """start(records) launches the gather of this step's finished games; finish() (next step) returns a TupleBatch."""
+    """Pipelined gather with no host synchronisation on the step's critical path:
+         start(records) at step s      packs this rank's finished games and launches an ASYNC all_gather of the per-rank counts;
+         start(...) at step s + 1       reads the (long finished) counts of step s, sizes the payload exactly and launches its async
+                                        all_gather + device->host copy on a side stream;
+         finish()                       returns the TupleBatch of every payload that has landed (usually the one of step s - 1).
+       drain() completes everything in flight (end of a run).  Nothing is dropped and nothing fixed-size is shipped."""
 
     def __init__(self, device, group=None):
         self.device, self.group = torch.device(device), group
         self.world = dist.get_world_size(group)
         self.cuda = self.device.type == "cuda"
         self.side = torch.cuda.Stream(self.device) if self.cuda else None
-        self._pending = None
+        self._counting = []      # stage 1: (buf, k, count tensor, all-counts tensor, work)
+        self._moving = []        # stage 2: (counts, m, allr / host, event or work)
         self.bytes_gathered = 0
 
+    def _launch_payload(self):
+        while self._counting:
+            buf, k, cnt, allc, work = self._counting.pop(0)
+            work.wait()
+            counts = allc.cpu().numpy().astype(np.int64)
+            m = int(counts.max())
+            if m == 0:
+                self._moving.append((counts, 0, None, None))
+                continue
+            mine = torch.zeros((m, REC_BYTES), dtype=torch.uint8, device=self.device)
+            if k:
+                src = torch.from_numpy(buf)
+                mine[:k].copy_(src.pin_memory() if self.cuda else src, non_blocking=True)
+            allr = torch.empty((self.world * m, REC_BYTES), dtype=torch.uint8, device=self.device)
+            w2 = dist.all_gather_into_tensor(allr, mine, group=self.group, async_op=True)
+            if self.cuda:
+                host = torch.empty((self.world * m, REC_BYTES), dtype=torch.uint8).pin_memory()
+                with torch.cuda.stream(self.side):
+                    w2.wait()                                                      # the side stream waits for the collective only
+                    host.copy_(allr, non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(self.side)
+                self._moving.append((counts, m, (allr, mine, host), ev))
+            else:
+                self._moving.append((counts, m, allr, w2))
+            self.bytes_gathered += int(self.world * m * REC_BYTES)
+
     def start(self, records):
-        assert self._pending is None, "finish() the previous gather first"
+        self._launch_payload()                                                     # counts of the previous step(s) are in by now
         buf, k, _ = pack_records(records)
         cnt = torch.tensor([k], dtype=torch.int32, device=self.device)
         allc = torch.empty((self.world,), dtype=torch.int32, device=self.device)
-        dist.all_gather_into_tensor(allc, cnt, group=self.group)                   # 4 B per rank; sizes the payload exactly
-        counts = allc.cpu().numpy().astype(np.int64)
-        m = int(counts.max())
-        if m == 0:
-            self._pending = (None, None, counts, 0)
-            return
-        mine = torch.zeros((m, REC_BYTES), dtype=torch.uint8, device=self.device)
-        if k:
-            src = torch.from_numpy(buf)
-            mine[:k].copy_(src.pin_memory() if self.cuda else src, non_blocking=True)
-        allr = torch.empty((self.world * m, REC_BYTES), dtype=torch.uint8, device=self.device)
-        work = dist.all_gather_into_tensor(allr, mine, group=self.group, async_op=True)
-        host = None
-        if self.cuda:
-            host = torch.empty((self.world * m, REC_BYTES), dtype=torch.uint8).pin_memory()
-            with torch.cuda.stream(self.side):
-                work.wait()                                                        # side stream waits for the collective only
-                host.copy_(allr, non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(self.side)
-            self._pending = ((allr, mine, host, ev), None, counts, m)
-        else:
-            self._pending = (None, (work, allr), counts, m)
-        self.bytes_gathered += int(self.world * m * REC_BYTES)
+        work = dist.all_gather_into_tensor(allc, cnt, group=self.group, async_op=True)    # 4 B per rank; nobody waits for it here
+        self._counting.append((buf, k, cnt, allc, work))
 
-    def finish(self):
-        """TupleBatch of every rank's tuples of the round started last (rank-major), or None if no round is pending."""
-        if self._pending is None:
-            return None
-        gpu, cpu, counts, m = self._pending
-        self._pending = None
-        if m == 0:
-            return TupleBatch(np.zeros((0, REC_BYTES), dtype=np.uint8))
-        if gpu is not None:
-            allr, mine, host, ev = gpu
-            ev.synchronize()
-            arr = host.numpy()
-        else:
-            work, allr = cpu
-            work.wait()
-            arr = allr.numpy()
-        arr = arr.reshape(self.world, m, REC_BYTES)
-        return TupleBatch(np.concatenate([arr[r, :int(counts[r])] for r in range(self.world)]))
+    def _take(self, block):
+        out = []
+        while self._moving:
+            counts, m, data, sync = self._moving[0]
+            if m and self.cuda and not block and not sync.query():
+                break
+            self._moving.pop(0)
+            if m == 0:
+                continue
+            if self.cuda:
+                sync.synchronize()
+                arr = data[2].numpy()
+            else:
+                sync.wait()
+                arr = data.numpy()
+            arr = arr.reshape(self.world, m, REC_BYTES)
+            out.extend(arr[r, :int(counts[r])] for r in range(self.world))
+        return out
+
+    def finish(self, block=False):
+        """TupleBatch of every rank's tuples whose payload has landed (rank-major per round); None when nothing is ready."""
+        parts = self._take(block)
+        return TupleBatch(np.concatenate(parts)) if parts else None
+
+    def drain(self):
+        """Complete every round in flight (collective: every rank must call it)."""
+        self._launch_payload()
+        parts = self._take(True)
+        return TupleBatch(np.concatenate(parts)) if parts else TupleBatch(np.zeros((0, REC_BYTES), dtype=np.uint8))
 
 
 def all_gather_tuples(records, device, cap=None, group=None):
@@ -180,7 +202,7 @@ def all_gather_tuples(records, device, cap=None, group=None):
     the payload is sized from the gathered counts); returns the list of all ranks' tuples (rank-major)."""
     g = AsyncTupleGather(device, group)
     g.start(records)
-    return g.finish().tuples()
+    return g.drain().tuples()
 
 
 def shard_seeds(n_games_per_rank, rank, base_seed=0):

@@ -74,19 +74,32 @@ class GameRecord:
         if self._boards is not None:
             return
         g = self._slot
-        self._boards, self._moves, self._chosen, self.visits, self.pi_val = [], [], [], [], []
-        for lg in self._logs:
-            n = int(lg["n"][g])
-            v = lg["visits"][g, :n].astype(np.int64)
-            self._boards.append(lg["boards"][g])
-            self._moves.append(lg["moves"][g, :n])
-            self._chosen.append(int(lg["choice"][g]))
-            self.visits.append(lg["visits"][g, :n])
-            with np.errstate(divide="ignore", invalid="ignore"):
-                lv = (1.0 / self._T) * np.log(v)                    # softmax(1/T * log(visits)), main.py:1341, 1111-1116
-                pr = np.exp(lv - np.max(lv))
-                pr /= np.sum(pr)
-            self.pi_val.append(pr)
+        logs = self._logs
+        L = len(logs)
+        self._boards = [lg["boards"][g] for lg in logs]
+        nn = np.fromiter((lg["n"][g] for lg in logs), dtype=np.int32, count=L)
+        self._chosen = [int(lg["choice"][g]) for lg in logs]
+        V = np.stack([lg["visits"][g] for lg in logs]) if L else np.zeros((0, MAXCHILD), np.int32)
+        M = np.stack([lg["moves"][g] for lg in logs]) if L else np.zeros((0, MAXCHILD), np.uint16)
+        self._moves = [M[i, :nn[i]] for i in range(L)]
+        self.visits = [V[i, :nn[i]] for i in range(L)]
+        # pi = softmax(1/T * log(visits)) (main.py:1341, 1111-1116): element-wise log / exp for the whole game at once, the
+        # order-sensitive row sums in csrc/cz_host.cu exactly as np.sum does them (the same call get_action's batch path uses)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            lv = (1.0 / self._T) * np.log(V.astype(np.int64))
+            lv[np.arange(MAXCHILD)[None, :] >= nn[:, None]] = -np.inf
+            ex = np.ascontiguousarray(np.exp(lv - np.max(lv, axis=1, keepdims=True))) if L else np.zeros((0, MAXCHILD))
+        probs = np.empty((L, MAXCHILD), dtype=np.float64)
+        if L:
+            import ctypes as C
+            from ._lib import lib
+            vp = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+            mt = np.zeros((L, MT_WORDS), dtype=np.uint32); mt[:, 624] = 624          # scratch generators: the draws are discarded
+            ch, fb = np.zeros(L, np.int32), np.zeros(L, np.uint8)
+            lib().cz_host_choose_moves(L, None, vp(nn), vp(ex), 0, vp(mt), vp(ch), vp(probs), vp(fb), 1)
+            for i in np.nonzero(fb)[0]:                                               # (NaN rows: plain numpy, as get_action would)
+                pr = ex[i, :nn[i]].copy(); pr /= np.sum(pr); probs[i, :nn[i]] = pr
+        self.pi_val = [probs[i, :nn[i]] for i in range(L)]
         self._logs = None
 
     def _materialise(self):

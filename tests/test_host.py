@@ -115,7 +115,25 @@ for rk in range(world):
 assert len(out) == len(exp), (len(out), len(exp))
 for (s, p, z), (s0, p0, z0) in zip(out, exp):
     assert s == s0 and z == z0 and np.array_equal(p, p0)
-if rank == 0: print("GLOO_OK", len(out))
+# the pipelined form: three rounds in flight (one of them empty on rank 1), nothing lost, nothing duplicated, round-major order
+from cchess_zero_b200.distributed import AsyncTupleGather
+ag = AsyncTupleGather(torch.device("cpu"))
+rounds = [[game(200 + rank)], [] if rank == 1 else [game(210)], [game(220 + rank), game(230 + rank)]]
+got = []
+for rd in rounds:
+    ag.start([r for _, r in rd])
+    tb = ag.finish()
+    if tb is not None: got += tb.tuples()
+got += ag.drain().tuples()
+exp2 = []
+for i, rd in enumerate(rounds):
+    for rk in range(world):
+        gs = [[game(200 + rk)], [] if rk == 1 else [game(210)], [game(220 + rk), game(230 + rk)]][i]
+        for g, _ in gs: exp2 += list(zip(g["states"], g["pis"], g["z"]))
+assert len(got) == len(exp2), (len(got), len(exp2))
+for (s, p, z), (s0, p0, z0) in zip(got, exp2):
+    assert s == s0 and z == z0 and np.array_equal(p, p0)
+if rank == 0: print("GLOO_OK", len(out), len(got))
 dist.destroy_process_group()
 '''
 
