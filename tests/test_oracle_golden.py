@@ -207,3 +207,48 @@ def test_deterministic_event_loop_runs_the_reference_coroutines_to_the_same_tree
         o = O.Tree(O.from_state(r["state"]))
         o.search_fifo(0 if r["player"] == "w" else 1, r["rr"], d["playouts"], 16, d["net"])
         assert v == [int(x) for x in o.root_children()[1]]
+
+
+def test_fifo_schedule_across_tree_reuse_matches_the_reference_coroutines():
+    """Several consecutive searches at search_threads=16 with MCTS_tree.update_tree in between (the self-play / play-mode pattern):
+    the stored Q, the left-over visit counts of the re-used subtree and the frozen root N must carry over exactly as in the
+    reference's object tree.  Reference side: its own coroutines on the deterministic loop; other side: the C restatement."""
+    import os
+    import sys
+    from conftest import ROOT
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import stage_reference as S
+    if S.staged_dir() is None:
+        pytest.skip("reference not present")
+    import detloop as D
+    import ref_harness as H
+    ref = H.load_reference()
+    net, P = "hash_pos", 96
+    state, player, rr = O.START, "w", 0
+    rtree = None
+    ctree = O.Tree()
+    for ply in range(5):
+        loop = D.DetLoop("busy")
+        import asyncio
+        asyncio.set_event_loop(loop)
+        if rtree is None:
+            rtree = ref.MCTS_tree_py312(state, H.FAKE_NETS[net], 16)
+        rtree.loop = loop
+        rtree.sem = asyncio.Semaphore(16)                 # fresh primitives for the fresh loop (main() builds new coroutines each call)
+        rtree.queue = asyncio.Queue(16)
+        rtree.running_simulation_num = 0
+        with np.errstate(all="ignore"):
+            D.run_reference_search(ref, rtree, state, player, rr, P, loop)
+        loop.close()
+        assert ctree.search_fifo(0 if player == "w" else 1, rr, P, 16, net) == 0
+        mv, N, W, Pp, Q = ctree.root_children()
+        got = [(a, int(c.N), H.f32_bits(c.Q)) for a, c in rtree.root.child.items()]
+        want = [(O.move_str(m), int(n), H.f32_bits(q)) for m, n, q in zip(mv, N, Q)]
+        assert got == want, ply
+        best = int(np.argmax(N))
+        act = O.move_str(mv[best])
+        nxt = ref.GameBoard.sim_do_action(act, state)
+        rr = rr + 1 if ref.is_kill_move(state, nxt) == 0 else 0
+        rtree.update_tree(act)
+        ctree.update(best)
+        state, player = nxt, ("b" if player == "w" else "w")
