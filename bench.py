@@ -58,7 +58,7 @@ def parse():
     ap.add_argument("--res-blocks", type=int, default=7)
     ap.add_argument("--precision", default=os.environ.get("CCHESS_NN_PRECISION", "fp16"))
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--first-conv", default=None, choices=["gather", "tc"], help="first-layer kernel: CUDA-core gather-add or tcgen05/TMEM")
+    ap.add_argument("--first-conv", default=None, choices=["gather", "tc", "mma"], help="first-layer kernel: mma.sync with register-built one-hot operand (default), CUDA-core gather-add, or tcgen05/TMEM")
     ap.add_argument("--lanes", type=int, default=1, choices=[1, 2], help="2 = pipeline two half-batches (tree kernel under the other half's network)")
     ap.add_argument("--library-ends", action="store_true", help="use cuDNN/cuBLAS for the first conv and the heads instead of csrc/cz_net.cu")
     ap.add_argument("--legs", default=os.environ.get("CCHESS_BENCH_LEGS", ALL_LEGS), help="comma list of extra legs (%s) or 'none'" % ALL_LEGS)

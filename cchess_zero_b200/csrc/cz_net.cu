@@ -68,6 +68,77 @@ __global__ void __launch_bounds__(256) k_first_conv(const uint8_t *__restrict__ 
     }
 }
 
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+// ------------------------------------------------------------------------------------------
+// first convolution on mma.sync with the ONE-HOT operand built in registers (default since round 2).
+//   D[16 cells][128 ch] = A[16][144] . B[144][128],  K = 9 taps x 16 piece slots (slot 0 = empty -> zero weight row; slot 15 of the
+//   centre tap is a constant 1 against the bias row, as in the tcgen05 variant).  A never exists anywhere: lane (g, t) of the warp
+//   derives its m16n8k16 fragment words for tap `tap` from the two piece codes of its rows g and g + 8 -- a 1.0 in the half that
+//   matches the code, zero otherwise (~10 ALU instructions per tap).  B is the weight matrix pre-arranged on the host in FRAGMENT
+//   order [k-step 9][n-tile 16][lane 32][2 words], copied once per CTA into shared memory: one conflict-free LDS.64 per MMA.
+//   A CTA (8 warps) handles 4 positions = 24 row tiles, 3 per warp; ~0.5 k instructions per tile against ~1.3 k for the gather-add.
+// ------------------------------------------------------------------------------------------
+constexpr int FCM_POS = 4;
+__global__ void __launch_bounds__(256) k_first_conv_mma(const uint8_t *__restrict__ boards, int B, const uint2 *__restrict__ wfrag /* [9][16][32] */,
+                                                         __half *__restrict__ out /* [B][90][128] */) {
+    __shared__ uint2 sW[9 * 16 * 32];                          // 36 864 B
+    __shared__ uint8_t pb[FCM_POS][11 * 12 + 12];              // zero-bordered images: pb[(r+1)*12 + f+1] = canonical board byte r*9+f (r < 9, f < 10)
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int pos0 = blockIdx.x * FCM_POS;
+    for (int i = tid; i < 9 * 16 * 32 / 2; i += 256) reinterpret_cast<uint4 *>(sW)[i] = __ldg(reinterpret_cast<const uint4 *>(wfrag) + i);
+    for (int i = tid; i < FCM_POS * 144; i += 256) {
+        const int p = i / 144, j = i - p * 144;
+        uint8_t v = 0;
+        if (j < 132 && pos0 + p < B) {
+            const int r = j / 12 - 1, f = j % 12 - 1;
+            if (r >= 0 && r < 9 && f >= 0 && f < 10) v = boards[(size_t)(pos0 + p) * 96 + r * 9 + f];   // the reference's cell <- s[rank*9+file]
+        }
+        pb[p][j] = v;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int tile = warp; tile < FCM_POS * 6; tile += 8) {
+        const int p = tile / 6, mt = tile - p * 6;
+        if (pos0 + p >= B) break;
+        const int c0 = mt * 16 + g, c1 = c0 + 8;               // this lane's two rows (cells); rows >= 90 are padding
+        const int r0 = c0 / 10, f0 = c0 - r0 * 10, r1 = c1 / 10, f1 = c1 - r1 * 10;
+        const uint8_t *q0 = pb[p] + r0 * 12 + f0, *q1 = pb[p] + r1 * 12 + f1;   // top-left of the 3x3 windows
+        float acc[16][4];
+#pragma unroll
+        for (int nt = 0; nt < 16; nt++) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f; }
+#pragma unroll
+        for (int tap = 0; tap < 9; tap++) {
+            const int off = (tap / 3) * 12 + (tap % 3);
+            const int pc0 = c0 < 90 ? q0[off] : 0, pc1 = c1 < 90 ? q1[off] : 0;
+            uint32_t a[4];
+            const uint32_t one0 = 0x3C00u << ((pc0 & 1) * 16), one1 = 0x3C00u << ((pc1 & 1) * 16);
+            a[0] = (pc0 >> 1) == t ? one0 : 0u;                // k = 2t, 2t+1   <-> codes 0..7
+            a[1] = (pc1 >> 1) == t ? one1 : 0u;
+            a[2] = (pc0 >> 1) == t + 4 ? one0 : 0u;            // k = 2t+8, 2t+9 <-> codes 8..15
+            a[3] = (pc1 >> 1) == t + 4 ? one1 : 0u;
+            if (tap == 4 && t == 3) { if (c0 < 90) a[2] |= 0x3C000000u; if (c1 < 90) a[3] |= 0x3C000000u; }   // slot 15 of the centre tap: 1 x bias row
+            const uint2 *wk = sW + tap * 16 * 32 + lane;
+#pragma unroll
+            for (int nt = 0; nt < 16; nt++) {
+                const uint2 bw = wk[nt * 32];
+                const uint32_t b[2] = {bw.x, bw.y};
+                mma16816(acc[nt], a, b);
+            }
+        }
+        __half *o0 = out + ((size_t)(pos0 + p) * 90 + c0) * 128 + t * 2, *o1 = out + ((size_t)(pos0 + p) * 90 + c1) * 128 + t * 2;
+#pragma unroll
+        for (int nt = 0; nt < 16; nt++) {
+            if (c0 < 90) *reinterpret_cast<__half2 *>(o0 + nt * 8) = __floats2half2_rn(fmaxf(acc[nt][0], 0.f), fmaxf(acc[nt][1], 0.f));
+            if (c1 < 90) *reinterpret_cast<__half2 *>(o1 + nt * 8) = __floats2half2_rn(fmaxf(acc[nt][2], 0.f), fmaxf(acc[nt][3], 0.f));
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // first convolution on the 5th-generation tensor cores (tcgen05 + TMEM), one 128-cell tile per CTA.
 //   D[128 cells][128 ch] (f32, TMEM) = A[128][144] . B[144][128],  K = 9 taps x 16 "piece slots"
@@ -318,11 +389,6 @@ __global__ void __launch_bounds__(256) k_value_mlp(const float *__restrict__ hv 
 // ------------------------------------------------------------------------------------------
 // heads, stage 2b: policy FC on tensor cores (legacy mma.sync path: 0.77 GFLOP, bound by its 8.5 MB f32 output)
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
-    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
-                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
-}
 
 // ------------------------------------------------------------------------------------------
 // heads, stage 1 on the (legacy) tensor path: the same conv1x1 (128 -> 3) as one streaming pass.
@@ -547,6 +613,13 @@ int cz_net_first_conv(const uint8_t *canon_boards, int B, const void *w1, const 
     if (!canon_boards || !w1 || !b1 || !out || B <= 0) return CZ_EINVAL;
     k_first_conv<<<B, 256, 0, (cudaStream_t)stream>>>(canon_boards, B, reinterpret_cast<const __half *>(w1), reinterpret_cast<const float4 *>(b1),
                                                       reinterpret_cast<__half *>(out));
+    return cudaGetLastError() == cudaSuccess ? CZ_OK : CZ_ECUDA;
+}
+
+int cz_net_first_conv_mma(const uint8_t *canon_boards, int B, const void *w_frag, void *out, void *stream) {
+    if (!canon_boards || !w_frag || !out || B <= 0) return CZ_EINVAL;
+    k_first_conv_mma<<<(B + FCM_POS - 1) / FCM_POS, 256, 0, (cudaStream_t)stream>>>(canon_boards, B, reinterpret_cast<const uint2 *>(w_frag),
+                                                                                     reinterpret_cast<__half *>(out));
     return cudaGetLastError() == cudaSuccess ? CZ_OK : CZ_ECUDA;
 }
 

@@ -222,12 +222,13 @@ class NativePlan:
     dtype = torch.uint8
 
     def __init__(self, net, max_batch, first_conv=None, owner=None):
-        """first_conv: "gather" (CUDA-core gather-add, k_first_conv) or "tc" (tcgen05 + TMEM, k_first_conv_tc)."""
+        """first_conv: "mma" (mma.sync, one-hot operand built in registers; default), "gather" (CUDA-core gather-add, k_first_conv)
+        or "tc" (tcgen05 + TMEM, k_first_conv_tc)."""
         import ctypes as C
         from ._lib import lib
         self._C, self._lib = C, lib()
-        self.first_conv = first_conv or os.environ.get("CCHESS_FIRST_CONV", "gather")
-        assert self.first_conv in ("gather", "tc")
+        self.first_conv = first_conv or os.environ.get("CCHESS_FIRST_CONV", "mma")
+        assert self.first_conv in ("gather", "tc", "mma")
         base = InferencePlan(net, "fp16", owner=owner)
         self.blocks, self.fused, self._base = base.blocks, base.fused, base
         self.net, self.owner, self.version = net, owner, base.version
@@ -265,7 +266,14 @@ class NativePlan:
             wp_pad[:2112] = wp
             bp_pad = torch.zeros((2176,), dtype=torch.float32, device=dev)
             bp_pad[:2112] = bp
-            return dict(w1=w1, b1=b1, w1_umma=wpad.reshape(18, 8, 16, 8).permute(0, 2, 3, 1).contiguous(),
+            # m16n8k16 B-fragment order for k_first_conv_mma: [tap][n-tile][lane] -> ({W[2t][n], W[2t+1][n]}, {W[2t+8][n], W[2t+9][n]})
+            lanes = torch.arange(32, device=dev)
+            gg, tt = lanes // 4, lanes % 4
+            ncol = (torch.arange(16, device=dev)[:, None] * 8 + gg[None, :])                      # [16 tiles][32 lanes] -> channel
+            def krow(off):                                                                         # wpad[tap][2t+off][n] as [9,16,32]
+                return wpad[:, (2 * tt + off)[None, :].expand(16, 32), ncol]
+            frag = torch.stack([krow(0), krow(1), krow(8), krow(9)], dim=-1).contiguous()          # [9,16,32,4] fp16 = 2 words per lane
+            return dict(w1=w1, b1=b1, w1_umma=wpad.reshape(18, 8, 16, 8).permute(0, 2, 3, 1).contiguous(), w1_frag=frag,
                         wp_tiled=wp_pad.reshape(17, 128, 24, 8).permute(0, 2, 1, 3).contiguous(), bp_pad=bp_pad,
                         wh=wh.float().reshape(3, 128).contiguous(), bh=bh.float().contiguous(),
                         w1t=net.v_fc1.weight.detach().float().t().contiguous(),        # [90,256]
@@ -295,7 +303,9 @@ class NativePlan:
         B = boards.shape[0]
         assert B <= self.max_batch and boards.dtype == torch.uint8 and logits_out.dtype == torch.float32
         st = self._C.c_void_p(torch.cuda.current_stream().cuda_stream)
-        if self.first_conv == "tc":
+        if self.first_conv == "mma":
+            rc = self._lib.cz_net_first_conv_mma(boards.data_ptr(), B, self.w1_frag.data_ptr(), self.x1.data_ptr(), st)
+        elif self.first_conv == "tc":
             rc = self._lib.cz_net_first_conv_tc(boards.data_ptr(), B, self.w1_umma.data_ptr(), self.b1.data_ptr(), self.x1.data_ptr(), st)
         else:
             rc = self._lib.cz_net_first_conv(boards.data_ptr(), B, self.w1.data_ptr(), self.b1.data_ptr(), self.x1.data_ptr(), st)

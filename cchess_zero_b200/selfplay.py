@@ -288,7 +288,6 @@ class SelfPlay:
         for g, sd in enumerate(seeds):
             st = np.random.RandomState(int(sd)).get_state()
             self._mt[g, :624], self._mt[g, 624] = st[1], st[2]
-        self._log = []                                   # per-ply batch logs still referenced by running games
         self._span = [[] for _ in range(n_games)]        # the log entries of each slot's current game
         self.exploration = exploration
         self.temperature = temperature
@@ -303,15 +302,8 @@ class SelfPlay:
         self.plies = 0
         self.waves = 0
         self.graph = None
-        self._alphas = {}
         self._threads = max(1, min(16, (len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else 4)))
         rules._init_tables()
-
-    def _alpha(self, n):
-        a = self._alphas.get(n)
-        if a is None:
-            a = self._alphas[n] = 0.3 * np.ones(n)
-        return a
 
     # -- evaluation step ---------------------------------------------------------------------
     def _eval(self, nn_in):

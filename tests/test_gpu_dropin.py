@@ -140,7 +140,7 @@ def test_selfplay_with_real_network(precision, graph, tmp_path, monkeypatch):
     assert (st["ply"] <= 6).all() and st["ply"].max() == 6
 
 
-@pytest.mark.parametrize("blocks,first_conv", [(2, "gather"), (7, "gather"), (2, "tc"), (7, "tc")])
+@pytest.mark.parametrize("blocks,first_conv", [(2, "gather"), (7, "gather"), (2, "tc"), (7, "tc"), (2, "mma"), (7, "mma")])
 def test_native_network_ends_match_library_plan(blocks, first_conv):
     """csrc/cz_net.cu (first conv from board bytes, fused heads) against the cuDNN/cuBLAS plan and against fp64."""
     from cchess_zero_b200 import rules
@@ -180,7 +180,7 @@ def test_native_network_ends_match_library_plan(blocks, first_conv):
     e_nat = max((lo.double().cpu() - rl).abs().max().item(), (vo.double().cpu() - rv.reshape(-1)).abs().max().item())
     e_lib = max((lib_l.double().cpu() - rl).abs().max().item(), (lib_v.double().cpu().reshape(-1) - rv.reshape(-1)).abs().max().item())
     print("max abs err vs fp64: native(%s) %.3g library %.3g" % (first_conv, e_nat, e_lib))
-    if first_conv == "tc":   # the two first-conv kernels sum the same fp16 weights in fp32: their tower inputs must agree closely
+    if first_conv in ("tc", "mma"):   # the first-conv kernels sum the same fp16 weights in fp32: their tower inputs must agree closely
         nat2 = NativePlan(net, 256, "gather")
         lo2 = torch.zeros_like(lo); vo2 = torch.zeros_like(vo)
         nat2(torch.from_numpy(canon).cuda(), lo2, vo2)
