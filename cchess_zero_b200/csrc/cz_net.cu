@@ -75,13 +75,14 @@ __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], 
 }
 
 // ------------------------------------------------------------------------------------------
-// first convolution on mma.sync with the ONE-HOT operand built in registers (default since round 2).
+// first convolution on mma.sync with the ONE-HOT operand built in registers (alternative; measured 20.4 us vs 12.8 us for the gather-add
+// at 1024 positions: each warp streams the whole 36 KB of weight fragments from shared memory per 16-cell tile -- not adopted).
 //   D[16 cells][128 ch] = A[16][144] . B[144][128],  K = 9 taps x 16 piece slots (slot 0 = empty -> zero weight row; slot 15 of the
 //   centre tap is a constant 1 against the bias row, as in the tcgen05 variant).  A never exists anywhere: lane (g, t) of the warp
 //   derives its m16n8k16 fragment words for tap `tap` from the two piece codes of its rows g and g + 8 -- a 1.0 in the half that
 //   matches the code, zero otherwise (~10 ALU instructions per tap).  B is the weight matrix pre-arranged on the host in FRAGMENT
 //   order [k-step 9][n-tile 16][lane 32][2 words], copied once per CTA into shared memory: one conflict-free LDS.64 per MMA.
-//   A CTA (8 warps) handles 4 positions = 24 row tiles, 3 per warp; ~0.5 k instructions per tile against ~1.3 k for the gather-add.
+//   A CTA (8 warps) handles 4 positions = 24 row tiles, 3 per warp.
 // ------------------------------------------------------------------------------------------
 constexpr int FCM_POS = 4;
 __global__ void __launch_bounds__(256) k_first_conv_mma(const uint8_t *__restrict__ boards, int B, const uint2 *__restrict__ wfrag /* [9][16][32] */,

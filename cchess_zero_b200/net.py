@@ -222,12 +222,13 @@ class NativePlan:
     dtype = torch.uint8
 
     def __init__(self, net, max_batch, first_conv=None, owner=None):
-        """first_conv: "mma" (mma.sync, one-hot operand built in registers; default), "gather" (CUDA-core gather-add, k_first_conv)
-        or "tc" (tcgen05 + TMEM, k_first_conv_tc)."""
+        """first_conv: "gather" (CUDA-core gather-add, k_first_conv; default: 12.8 us for 1024 positions in a graph), "tc" (tcgen05 + TMEM,
+        k_first_conv_tc: 12.1 us) or "mma" (mma.sync with the one-hot operand built in registers: 20.4 us -- every warp re-reads the
+        36 KB weight fragments from shared memory per 16-cell tile; kept as a tested alternative, measured and not adopted)."""
         import ctypes as C
         from ._lib import lib
         self._C, self._lib = C, lib()
-        self.first_conv = first_conv or os.environ.get("CCHESS_FIRST_CONV", "mma")
+        self.first_conv = first_conv or os.environ.get("CCHESS_FIRST_CONV", "gather")
         assert self.first_conv in ("gather", "tc", "mma")
         base = InferencePlan(net, "fp16", owner=owner)
         self.blocks, self.fused, self._base = base.blocks, base.fused, base

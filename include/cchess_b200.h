@@ -193,7 +193,7 @@ int cz_net_first_conv(const uint8_t *canon_boards, int B, const void *w1, const 
  * with k = tap*16 + piece code (code 0 rows are zero; row (centre tap, code 15) holds the bias, every other code-15 row is
  * zero); 36 864 bytes.  b1 is ignored (kept for signature symmetry with cz_net_first_conv). */
 int cz_net_first_conv_tc(const uint8_t *canon_boards, int B, const void *w_umma, const float *b1, void *out, void *stream);
-/* Same result on mma.sync with the one-hot operand built in registers (the default first layer since round 2).  w_frag: dev, the
+/* Same result on mma.sync with the one-hot operand built in registers (alternative first layer; slower than the gather-add).  w_frag: dev, the
  * weights of cz_net_first_conv_tc's K = tap*16 + piece-code convention (bias row included) in m16n8k16 B-fragment order
  * [9 k-steps][16 n-tiles][32 lanes][2 words]: word0 = {W[k0+2t][n], W[k0+2t+1][n]}, word1 = the same at k + 8, n = 8*tile + lane/4, t = lane%4. */
 int cz_net_first_conv_mma(const uint8_t *canon_boards, int B, const void *w_frag, void *out, void *stream);
