@@ -815,7 +815,7 @@ __global__ void __launch_bounds__(32 * MAX_WPB, 1) k_wave_fifo(Dev E, T *nn_in, 
         for (int it = 0; it < FIFO_MAX_ITERS && !need_nn && done < target; it++) {
             int nnxt = 0;
             for (int e = 0; e < ncur; e++) {
-                const uint32_t ev = cur[e];
+                const uint32_t ev = cur[e & 63];          // (a ring: iteration 1 appends while it runs, at most K entries are live)
                 const int slot = (int)(ev & 63u), kind = (int)(ev >> 6);
                 const size_t idx = (size_t)g * K + slot;
                 if (kind == (int)EV_AHOP) { if (lane == 0) nxt[nnxt] = (uint8_t)(slot | (EV_STEP << 6)); nnxt++; continue; }
@@ -920,7 +920,14 @@ __global__ void __launch_bounds__(32 * MAX_WPB, 1) k_wave_fifo(Dev E, T *nn_in, 
                     done++;
                     plen = 0;
                     if (lane == 0) atomicAdd(E.cnt_playout + g, 1ull);
-                    if (started < target) { started++; if (lane == 0) nxt[nnxt] = (uint8_t)(slot | (EV_STEP << 6)); nnxt++; }
+                    if (started < target) {
+                        started++;
+                        // Iteration 1 runs the first step of EVERY playout's task in index order and the semaphore is a plain counter there:
+                        // a playout that ends inside its first step (king capture / 60-move rule right below the root) hands its permit to
+                        // the next playout in the SAME iteration, behind the tasks already started.  Later, a release wakes a waiter: next iteration.
+                        if (iter == 1) { if (lane == 0) cur[ncur & 63] = (uint8_t)(slot | (EV_STEP << 6)); ncur++; }
+                        else { if (lane == 0) nxt[nnxt] = (uint8_t)(slot | (EV_STEP << 6)); nnxt++; }
+                    }
                 }
                 if (lane == 0) E.plenK[idx] = plen;
                 __syncwarp();

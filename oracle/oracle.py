@@ -225,10 +225,11 @@ def flip_label(m):
     return "".join(str(9 - int(a)) if a.isdigit() else a for a in m)
 
 
-def selfplay_game(net, playouts, rs, exploration=True, temperature=1, max_plies=10000):
+def selfplay_game(net, playouts, rs, exploration=True, temperature=1, max_plies=10000, search_threads=1):
     """cchess_main.selfplay (main.py:1493-1554) + get_action (1332-1358) over the C tree.
 
     rs: np.random.RandomState standing in for the global np.random of the reference.
+    search_threads > 1: every search runs the reference's K-coroutine schedule in canonical form (co_tree_search_fifo).
     Returns dict(states, pis (dense [n,2086] f64), z, actions, visits).
     """
     lab = labels()
@@ -240,7 +241,7 @@ def selfplay_game(net, playouts, rs, exploration=True, temperature=1, max_plies=
     z = None
     with np.errstate(divide="ignore"):
         while True:
-            err = tree.search(side, rr, playouts, net)
+            err = tree.search(side, rr, playouts, net) if search_threads <= 1 else tree.search_fifo(side, rr, playouts, search_threads, net)
             if err:
                 raise RuntimeError("oracle tree error %d" % err)
             mv, N, W, P, Q = tree.root_children()

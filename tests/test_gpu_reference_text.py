@@ -79,6 +79,27 @@ def test_reference_selfplay_text_reproduces_reference_tuples(ref_cchess_main, tm
         m.log_file.close()
 
 
+@pytest.mark.parametrize("i", range(6))
+def test_reference_selfplay_text_at_its_default_search_threads_reproduces_reference_tuples(ref_cchess_main, tmp_path, monkeypatch, i):
+    """The reference's default configuration end to end: its own selfplay() text with search_threads = 16 (and 8, 4) over the package's
+    MCTS_tree must give the tuples the unmodified reference gives when its coroutines run on the canonical deterministic schedule
+    (oracle/gen_golden_k16_selfplay.py; whole games, including king captures right below the root)."""
+    monkeypatch.chdir(tmp_path)
+    from oracle.fakenets_np import FAKE_NETS
+    cls, ns = ref_cchess_main
+    g = load_golden("selfplay_k16.json")["games"][i]
+    m = _make(cls, ns, g["playouts"], FAKE_NETS[g["net"]], threads=g["search_threads"])
+    np.random.seed(g["seed"])
+    with contextlib.redirect_stdout(io.StringIO()), np.errstate(all="ignore"):
+        data, n = m.selfplay()
+    data = list(data)
+    assert n == g["n"]
+    assert [d[0] for d in data] == g["states"]
+    assert [float(d[2]) for d in data] == g["z"]
+    assert sha(np.asarray([d[1] for d in data], dtype=np.float64).tobytes()) == g["sha_pi"]
+    m.log_file.close()
+
+
 def test_reference_play_text_reproduces_reference_moves(ref_cchess_main, tmp_path, monkeypatch):
     """select_move / get_hint / human_move / check_end of the reference's text (main.py:1278-1491) over the package."""
     from oracle.fakenets_np import FAKE_NETS

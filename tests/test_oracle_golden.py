@@ -103,6 +103,20 @@ def test_selfplay_full_game_at_1200_playouts_against_reference():
     assert sha(np.asarray(r["pis"], dtype=np.float64).tobytes()) == g["sha_pi"]
 
 
+@pytest.mark.parametrize("i", range(6))
+def test_selfplay_at_search_threads_16_against_reference_coroutines(i):
+    """Whole self-play games of the unmodified reference at search_threads = 16 / 8 / 4 (its own coroutines on the canonical
+    deterministic schedule, oracle/gen_golden_k16_selfplay.py) against the C restatement of that schedule."""
+    g = load_golden("selfplay_k16.json")["games"][i]
+    with np.errstate(all="ignore"):
+        r = O.selfplay_game(g["net"], g["playouts"], np.random.RandomState(g["seed"]), search_threads=g["search_threads"])
+    assert len(r["states"]) == g["n"] and r["states"] == g["states"]
+    assert [float(v) for v in r["z"]] == g["z"]
+    assert sha(np.asarray(r["pis"], dtype=np.float64).tobytes()) == g["sha_pi"]
+    for p, sp in zip(r["pis"], g["pi_sparse"]):
+        assert [[int(k), float(p[k]).hex()] for k in np.nonzero(p)[0]] == sp
+
+
 def test_leaf_parallel_spec_with_one_slot_is_the_reference_search():
     """oracle co_tree_search_multi (the serial spec of the package's own K-leaves-per-wave schedule) must degenerate to the
     reference-pinned search for K = 1; for K > 1 it must conserve visits."""
