@@ -61,6 +61,51 @@ def search(ref, state, player, rr, K, delay=0.0):
     return [a for a in t.root.child], [int(c.N) for c in t.root.child.values()]
 
 
+def terminal_positions(ref, n, seed=31):
+    """Positions in which the side to move can capture the king at once (random play walks into them: the reference generates
+    pseudo-legal moves), plus positions one quiet move short of the 60-move rule: playouts that END INSIDE THEIR FIRST STEP, the case
+    in which asyncio's semaphore hands permits on within the first loop iteration."""
+    rng = random.Random(seed)
+    out = []
+    while len(out) < n:
+        state, player, rr = START, "w", 0
+        for ply in range(200):
+            moves = ref.GameBoard.get_legal_moves(state, player)
+            caps = [m for m in moves if ("K" not in ref.GameBoard.sim_do_action(m, state)) or ("k" not in ref.GameBoard.sim_do_action(m, state))]
+            if caps and ply > 4:
+                out.append((state, player, rr if len(out) % 3 else 59))       # every third one also sits on the draw rule
+                break
+            nxt = ref.GameBoard.sim_do_action(rng.choice(moves), state)
+            rr = rr + 1 if ref.is_kill_move(state, nxt) == 0 else 0
+            state, player = nxt, ("b" if player == "w" else "w")
+            if rr >= 59:
+                break
+    return out
+
+
+def main_terminal(n=30, playouts=120):
+    ref = H.load_reference()
+    recs = []
+    for i, (state, player, rr) in enumerate(terminal_positions(ref, n)):
+        runs = []
+        for net in ("hash_pos", "hash_signed"):
+            base = H.FAKE_NETS[net]
+            vs = []
+            for rep in range(3):
+                t = H.make_mcts(base, 16, state)
+                with np.errstate(all="ignore"):
+                    t.main(state, player, rr, playouts)
+                vs.append([int(c.N) for c in t.root.child.values()])
+            runs.append(dict(net=net, k16_runs=vs))
+        recs.append(dict(state=state, player=player, rr=rr, runs=runs))
+        print("terminal", i, player, rr, flush=True)
+    out = os.path.join(os.path.dirname(OUT), "k16_terminal.json")
+    with open(out, "w") as f:
+        json.dump(dict(playouts=playouts, records=recs, how="oracle/gen_golden_k16.py --terminal: unmodified reference MCTS_tree.main on uvloop, "
+                       "search_threads 16, three runs per position and evaluator"), f)
+    print("wrote", out)
+
+
 def main():
     ref = H.load_reference()
     recs, same = [], 0
@@ -81,4 +126,4 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    main_terminal() if "--terminal" in sys.argv else main()

@@ -73,6 +73,24 @@ def test_fifo_schedule_reproduces_real_reference_runs_at_search_threads_16():
     e.close()
 
 
+def test_fifo_schedule_with_playouts_that_end_in_their_first_step_reproduces_real_reference_runs():
+    """Positions where the king can be captured at once (and some on the 60-move rule): playouts end inside the first loop iteration
+    and asyncio's semaphore hands their permits on within it.  Three real uvloop runs of the reference per position and evaluator
+    (tests/golden/k16_terminal.json); the engine must equal one of them everywhere and the first on at least 90 %."""
+    d = load_golden("k16_terminal.json")
+    recs = d["records"]
+    for k, net in enumerate(("hash_pos", "hash_signed")):
+        e, rc = _run(recs, 16, d["playouts"], net)
+        first = 0
+        for g, r in enumerate(recs):
+            assert r["runs"][k]["net"] == net
+            v = [int(x) for x in rc["visits"][g, : rc["n"][g]]]
+            assert v in r["runs"][k]["k16_runs"], (net, g)
+            first += v == r["runs"][k]["k16_runs"][0]
+        assert first >= 0.9 * len(recs)
+        e.close()
+
+
 def test_mcts_tree_honours_search_threads_and_play_continues_on_the_reused_tree(tmp_path, monkeypatch):
     """MCTS_tree(state, forward, 16): the facade runs the FIFO engine; update_tree keeps the subtree with its stored Q; a second
     search on the re-used root equals the C specification run through the same two searches."""

@@ -196,6 +196,22 @@ def test_fifo_schedule_spec_reproduces_real_reference_runs_at_search_threads_16(
     assert self_consistent == d["reference_k16_identical_under_2ms_latency"]
 
 
+def test_fifo_schedule_spec_with_playouts_that_end_in_their_first_step():
+    """King capturable at the root / 60-move rule one ply away: real uvloop runs of the reference (three per position and evaluator,
+    tests/golden/k16_terminal.json) against the C restatement of the schedule."""
+    d = load_golden("k16_terminal.json")
+    first = total = 0
+    for r in d["records"]:
+        for run in r["runs"]:
+            o = O.Tree(O.from_state(r["state"]))
+            assert o.search_fifo(0 if r["player"] == "w" else 1, r["rr"], d["playouts"], 16, run["net"]) == 0
+            v = [int(x) for x in o.root_children()[1]]
+            assert v in run["k16_runs"], (r["state"], run["net"])
+            first += v == run["k16_runs"][0]
+            total += 1
+    assert first >= 0.9 * total
+
+
 def test_deterministic_event_loop_runs_the_reference_coroutines_to_the_same_trees():
     """oracle/detloop.py: the UNMODIFIED coroutines of the reference (tree_search / start_tree_search / prediction_worker) on a
     deterministic event loop give the visit counts of the real uvloop run AND of the C restatement.  Needs the reference (live or
