@@ -1077,6 +1077,22 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_status(Dev E) {
 // ---- play a move: board update + MCTS_tree.update_tree with subtree compaction ------------
 // Cheney-style breadth-first copy of the chosen child's subtree into the other arena half.  Also leaves the game's
 // packed status record (with Q of the move played = mcts.Q(act), main.py:1350) in st_status.
+// One node block (a multiple of 8 words at an 8-word-aligned offset) from the old arena half to the new one: 16-byte accesses, up to four
+// loads in flight per lane before the first store (a word-by-word loop serialises a memory round trip per 32 words: the re-root was
+// 6 ms per ply for 1024 games that way).
+__device__ __forceinline__ void copy_block(uint32_t *__restrict__ dst, const uint32_t *__restrict__ src, uint32_t words, int lane) {
+    const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
+    uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+    const uint32_t n4 = words >> 2;
+    for (uint32_t j0 = 0; j0 < n4; j0 += 128) {
+        uint4 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) { const uint32_t j = j0 + (uint32_t)(k * 32 + lane); if (j < n4) v[k] = __ldg(s4 + j); }
+#pragma unroll
+        for (int k = 0; k < 4; k++) { const uint32_t j = j0 + (uint32_t)(k * 32 + lane); if (j < n4) d4[j] = v[k]; }
+    }
+}
+
 __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_play(Dev E) {
     const int lane = threadIdx.x & 31, g = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
     if (g >= E.B) return;
@@ -1106,7 +1122,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_play(Dev E) {
     if (child != NONE) {
         ncnt = (int)((meta >> 16) & 0xFFu);
         uint32_t size = HDR + (uint32_t)E.narr * (uint32_t)((ncnt + 7) & ~7);
-        for (uint32_t i = lane; i < size; i += 32) neu[i] = old[child + i];
+        copy_block(neu, old + child, size, lane);
         alloc = size;
         __syncwarp();
         uint32_t scan = 0;
@@ -1129,7 +1145,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_play(Dev E) {
                     const int l = __ffs(m) - 1;
                     m &= m - 1;
                     const uint32_t so = __shfl_sync(CZ_FULL, oc, l), dn = __shfl_sync(CZ_FULL, off, l), n = __shfl_sync(CZ_FULL, sz, l);
-                    for (uint32_t j = lane; j < n; j += 32) neu[dn + j] = old[so + j];
+                    copy_block(neu + dn, old + so, n, lane);
                 }
                 alloc += (uint32_t)tot;
                 __syncwarp();
