@@ -248,8 +248,8 @@ class Runner:
         native = precision == "fp16" and not a.library_ends
         pvx = self.pv
         if pv is not None and pv.precision != precision:        # same weights, another arithmetic
-            from cchess_zero_b200.net import InferencePlan
-            factory = lambda n: InferencePlan(pvx.net, precision)  # noqa: E731
+            from cchess_zero_b200.net import make_plan
+            factory = lambda n: make_plan(pvx.net, precision)  # noqa: E731
         else:
             factory = (lambda n: pvx.native_plan(n, a.first_conv)) if native else (lambda n: pvx.plan())
         self.plan = factory(games // a.lanes)
@@ -378,11 +378,12 @@ class Runner:
 
 
 def leg_precision(a, rank, world, local_rank, pv):
-    """The main workload in the other arithmetics, same weights: tf32 and fp32 (the reference's own arithmetic is fp32).
+    """The main workload in the other arithmetics, same weights: tf32, tf32x3 (fp32-accurate on the TF32 tensor cores: the mode that
+    meets "within 1e-3 fp32" at trained-network magnitudes) and fp32 (the reference's own arithmetic).
     fp32 convolutions run ~57x slower than fp16 (no tensor cores), so that leg plays one ply of a 120-playout search: the rate per
     wave is what is measured (the network is > 99 % of such a wave), the line says which playout count was used."""
     out = {}
-    for prec, steps, warm, playouts in (("tf32", 2, 1, a.playouts), ("fp32", 1, 0, min(a.playouts, 120))):
+    for prec, steps, warm, playouts in (("tf32", 2, 1, a.playouts), ("tf32x3", 1, 1, a.playouts // 2), ("fp32", 1, 0, min(a.playouts, 120))):
         r = Runner(a, rank, world, local_rank, a.games, playouts, a.res_blocks, prec, pv=pv, arena_words=1 << 20)
         m = r.plies(steps, warm)
         out[prec] = dict(value=m["value"], e2e=m["e2e"], plies_timed=steps, playouts=playouts, ms_per_step=m["e2e_ms"] / steps,
@@ -435,11 +436,11 @@ def leg_config5(a, local_rank, pv):
     return out
 
 
-def leg_threads16(a, rank, world, local_rank, pv):
-    """256 games x `playouts` playouts with search_threads = 16 inside every game (the reference's default schedule, exact): the
-    network batch is 256 x 16 rows per wave, ~14 of 16 rows of a game carry a leaf."""
+def leg_threads16(a, rank, world, local_rank, pv, games=256):
+    """`games` games x `playouts` playouts with search_threads = 16 inside every game (the reference's default schedule, exact): the
+    network batch is games x 16 rows per wave, ~11 of 16 rows of a game carry a leaf."""
     from cchess_zero_b200.selfplay import SelfPlay
-    games, K = 256, 16
+    K = 16
     sp = SelfPlay(games, None, a.playouts, seeds=[rank * games + g for g in range(games)], device=local_rank, auto_reset=True, keep_records=False,
                   plan_factory=lambda n: pv.native_plan(n, a.first_conv), search_threads=K, arena_words=1 << 21)
     sp.capture_graph()
@@ -597,6 +598,7 @@ def run_ours(a, rank, world, local_rank):
             extra["config5"] = leg_config5(a, local_rank, pv)
         if "threads16" in legs:
             extra["search_threads_16"] = leg_threads16(a, rank, world, local_rank, pv)
+            extra["search_threads_16_full_batch"] = leg_threads16(a, rank, world, local_rank, pv, games=a.games)
         if "dedup" in legs:
             extra["eval_dedup"] = leg_dedup(a, rank, world, local_rank, pv)
     cpu = None

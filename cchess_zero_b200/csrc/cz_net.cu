@@ -606,6 +606,25 @@ __global__ void __launch_bounds__(128) k_policy_fc(const __half *__restrict__ hp
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------------
+// "3xTF32" operand split for the fp32-accurate inference mode (net.py: SplitTf32Plan).  y f32 [P][128] (NHWC activations of one
+// convolution) -> hi f32 [P][128] = tf32(y) and x2 f32 [P][256] = { y - hi | hi }, where tf32() rounds to the 10-bit TF32 mantissa
+// (nearest, ties away; the low 13 bits of hi are zero, so whatever conversion the tensor-core kernel applies to it is the identity).
+// Two TF32 convolutions then give hi(x)*hi(w) (operand hi, K = 1152: the only long accumulation chain of full-size terms) and
+// lo(x)*hi(w) + hi(x)*lo(w) (operand x2 against { hi(w) | lo(w) }, terms 2^-11 smaller); the dropped lo*lo term and the rounding of
+// the two lo operands are O(2^-22) relative.  Streaming kernel: 16 B in, 48 B out per thread.
+__device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u); }
+
+__global__ void __launch_bounds__(256) k_split_tf32(const float4 *__restrict__ y, float4 *__restrict__ hi, float4 *__restrict__ x2, long long n4) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 v = __ldg(y + i);
+        const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+        const float4 l = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+        float4 *o = x2 + (i >> 5) * 64 + (i & 31);
+        hi[i] = h; o[0] = l; o[32] = h;
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -709,6 +728,19 @@ int cz_net_heads_tc(const void *x, int B, const float *wh, const float *bh, cons
     if (cudaGetLastError() != cudaSuccess) return CZ_ECUDA;
     if (cudaStreamWaitEvent(st, ev_join[dev], 0) != cudaSuccess) return CZ_ECUDA;
     return CZ_OK;
+}
+
+// y dev f32 [n_pix][128] -> hi dev f32 [n_pix][128] = tf32(y), x2 dev f32 [n_pix][256] = { y - hi | hi } (see k_split_tf32)
+int cz_net_split_tf32(const float *y, float *hi, float *x2, long long n_pix, void *stream) {
+    if (!y || !hi || !x2 || n_pix <= 0) return CZ_EINVAL;
+    const long long n4 = n_pix * 32;
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    long long blocks = (n4 + 255) / 256;
+    if (blocks > 8LL * sms) blocks = 8LL * sms;          // grid-stride, 8 resident CTAs of 256 threads per SM
+    k_split_tf32<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4 *>(y), reinterpret_cast<float4 *>(hi),
+                                                                    reinterpret_cast<float4 *>(x2), n4);
+    return cudaGetLastError() == cudaSuccess ? CZ_OK : CZ_ECUDA;
 }
 
 }  // extern "C"

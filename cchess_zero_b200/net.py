@@ -90,7 +90,12 @@ class PolicyValueNet(nn.Module):
         return logits, value
 
 
-_DT = {"fp32": torch.float32, "tf32": torch.float32, "bf16": torch.bfloat16, "fp16": torch.float16}
+_DT = {"fp32": torch.float32, "tf32": torch.float32, "tf32x3": torch.float32, "bf16": torch.bfloat16, "fp16": torch.float16}
+
+
+def make_plan(net, precision, owner=None):
+    """The inference plan of a precision name: "tf32x3" (fp32-accurate on the TF32 tensor cores) has its own class."""
+    return SplitTf32Plan(net, owner=owner) if precision == "tf32x3" else InferencePlan(net, precision, owner=owner)
 
 
 class InferencePlan:
@@ -170,7 +175,7 @@ class InferencePlan:
             return False
 
     def _ctx(self):
-        return _Tf32(self.precision == "tf32")
+        return _Tf32(self.precision in ("tf32", "tf32x3"))
 
     def make_input(self, B):
         return torch.zeros((B, 9, 10, 14), dtype=self.dtype, device=self.w_in[0].device)
@@ -204,6 +209,125 @@ class InferencePlan:
             p = h[..., :2].reshape(B, 180)
             v = h[..., 2].reshape(B, 90).float()
             logits = F.linear(p, self.p_fc[0], self.p_fc[1]).float()
+            value = torch.tanh(F.linear(F.relu_(F.linear(v, self.v_fc1[0], self.v_fc1[1])), self.v_fc2[0], self.v_fc2[1]))
+        if logits_out is not None:
+            logits_out.copy_(logits)
+            value_out.copy_(value.reshape(value_out.shape))
+            return None
+        return logits, value
+
+
+def tf32_hi(t):
+    """Round an f32 tensor to the 10-bit TF32 mantissa (nearest, ties away from zero): the low 13 bits of the result are zero, so the
+    tensor-core kernels' own f32 -> tf32 conversion leaves it unchanged.  Same operation as csrc/cz_net.cu: tf32_hi."""
+    return ((t.contiguous().view(torch.int32) + 0x1000) & -8192).view(torch.float32).reshape(t.shape)
+
+
+def split_weights(w):
+    """[O, C, kh, kw] f32 -> (hi(w) [O, C, kh, kw], { hi(w) | w - hi(w) } [O, 2C, kh, kw]): the weight side of the 3xTF32 product."""
+    h = tf32_hi(w)
+    return h, torch.cat([h, w - h], 1)
+
+
+def split_acts(x):
+    """[B, C, H, W] f32 -> (hi(x) [B, C, H, W], { x - hi(x) | hi(x) } [B, 2C, H, W]): torch statement of csrc/cz_net.cu: k_split_tf32."""
+    h = tf32_hi(x)
+    return h, torch.cat([x - h, h], 1)
+
+
+class SplitTf32Plan(InferencePlan):
+    """precision="tf32x3": the reference's fp32 arithmetic (policy_value_network.py:202-214) reproduced to ~1e-5 of max |logit| ON
+    the tensor cores, for the contract "NN outputs match within 1e-3 fp32" at trained-network magnitudes (fp16 / tf32 carry 10-11-bit
+    mantissas through 15-39 convolutions and miss an absolute 1e-3 on logits of size 8), at a tenth of the
+    cost of cuDNN's fp32 convolutions (which do not use the tensor cores: 57x slower than fp16).
+
+    Every activation x and weight w is split into hi = tf32(x) and lo = x - hi; per convolution
+        s   = conv_tf32({ lo(x) | hi(x) }, { hi(w) | lo(w) })                 the two small cross terms, K = 2 x 1152
+        out = relu(conv_tf32(hi(x), hi(w)) + s [+ skip] + bias)               the full-size term, fused library epilogue, f32
+    What is dropped (lo*lo, the tf32 rounding of the two lo operands) is O(2^-22) relative.  The two terms are accumulated
+    SEPARATELY because the tensor cores' f32 accumulator truncates (tools/tf32x3_probe.py: -6.6e-9 relative per accumulated term,
+    linear in K): one convolution over { hi | lo | hi } x { hi | hi | lo } (K = 3456) measured 9.6e-6 relative per layer, this
+    arrangement 3.4e-6 for 8 % more time (hi*hi in two / four input-channel groups: 1.6e-6 / 7.7e-7 for +35 % / +90 %).
+    The hi / lo split of a convolution's result is csrc/cz_net.cu: k_split_tf32 (one streaming kernel per convolution).  The first
+    convolution takes the one-hot planes (exact in any precision) against { hi(w) | lo(w) } with 2 x 14 channels; the heads
+    (3 of 128 channels, 180 -> 2086, 90 -> 256 -> 1) run in true fp32."""
+
+    def __init__(self, net, owner=None):
+        import ctypes as C
+        from ._lib import lib
+        self._C, self._lib = C, lib()
+        self._bufs = {}
+        super().__init__(net, "tf32x3", owner=owner)
+
+    def _fold_all(self, net):
+        d = super()._fold_all(net)                                   # f32 folded weights, channels_last
+        cl = lambda t: t.contiguous(memory_format=torch.channels_last)  # noqa: E731
+        with torch.no_grad():
+            w, b = d["w_in"]
+            d["w_in"] = (cl(split_weights(w)[1]), b)                     # [128, 28, 3, 3]: { hi | lo } against the planes twice
+
+            def ws(wb):
+                h, w2 = split_weights(wb[0])
+                return cl(h), cl(w2), wb[1]                             # [128,128,3,3], [128,256,3,3], bias
+            d["blocks"] = [(ws(c1), ws(c2)) for c1, c2 in d["blocks"]]
+        return d
+
+    def _probe_fused(self):
+        try:
+            dev = self.w_in[0].device
+            x = torch.randn(4, 128, 9, 10, device=dev).contiguous(memory_format=torch.channels_last)
+            s = torch.randn(4, 128, 9, 10, device=dev).contiguous(memory_format=torch.channels_last)
+            w = torch.randn(128, 128, 3, 3, device=dev).mul_(0.02).contiguous(memory_format=torch.channels_last)
+            b = torch.randn(128, device=dev)
+            with self._ctx():
+                a2 = torch.cudnn_convolution_add_relu(x, w, s, 1.0, b, (1, 1), (1, 1), (1, 1), 1)
+            r = F.conv2d(x.double(), w.double(), b.double(), padding=1)
+            return bool(torch.allclose(a2.double(), F.relu(r + s.double()), atol=5e-2, rtol=5e-2))
+        except Exception:
+            return False
+
+    def _split(self, y):
+        """y: [B,128,9,10] f32 channels_last -> (hi [B,128,9,10], { lo | hi } [B,256,9,10]), channels_last views of one pair of buffers
+        per batch size (allocated on the first -- eager, warm-up -- call; their previous consumers were issued on the same stream)."""
+        B = y.shape[0]
+        if not y.is_contiguous(memory_format=torch.channels_last):
+            y = y.contiguous(memory_format=torch.channels_last)
+        bufs = self._bufs.get(B)
+        if bufs is None:
+            bufs = self._bufs[B] = (torch.empty((B, 9, 10, 128), dtype=torch.float32, device=y.device),
+                                    torch.empty((B, 9, 10, 256), dtype=torch.float32, device=y.device))
+        rc = self._lib.cz_net_split_tf32(y.data_ptr(), bufs[0].data_ptr(), bufs[1].data_ptr(), B * 90,
+                                         self._C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        if rc:
+            raise RuntimeError("cz_net_split_tf32 failed (%d)" % rc)
+        return bufs[0].permute(0, 3, 1, 2), bufs[1].permute(0, 3, 1, 2)
+
+    def _conv3(self, x, wts, skip=None):
+        """relu(conv(x, w) + bias [+ skip]) from the three TF32 products; x f32 [B,128,9,10] channels_last."""
+        w_hh, w_small, b = wts
+        hi, x2 = self._split(x)
+        s = F.conv2d(x2, w_small, None, padding=1)
+        if skip is not None:
+            s.add_(skip)
+        if self.fused:
+            return torch.cudnn_convolution_add_relu(hi, w_hh, s, 1.0, b, (1, 1), (1, 1), (1, 1), 1)
+        return F.relu_(F.conv2d(hi, w_hh, b, padding=1).add_(s))
+
+    @torch.no_grad()
+    def __call__(self, nn_in, logits_out=None, value_out=None):
+        """nn_in: [B,9,10,14] one-hot planes (any float dtype) on the device."""
+        B = nn_in.shape[0]
+        x = nn_in.permute(0, 3, 1, 2).float()
+        with self._ctx():
+            x = F.relu_(F.conv2d(torch.cat([x, x], 1).contiguous(memory_format=torch.channels_last), self.w_in[0], self.w_in[1], padding=1))
+            for c1, c2 in self.blocks:
+                y = self._conv3(x, c1)
+                x = self._conv3(y, c2, skip=x)
+        with _Tf32(False):
+            h = F.relu_(F.conv2d(x, self.w_head[0], self.w_head[1])).permute(0, 2, 3, 1)
+            p = h[..., :2].reshape(B, 180)
+            v = h[..., 2].reshape(B, 90)
+            logits = F.linear(p, self.p_fc[0], self.p_fc[1])
             value = torch.tanh(F.linear(F.relu_(F.linear(v, self.v_fc1[0], self.v_fc1[1])), self.v_fc2[0], self.v_fc2[1]))
         if logits_out is not None:
             logits_out.copy_(logits)
@@ -496,7 +620,7 @@ class policy_value_network(object):
     def plan(self):
         if self._plan is None:
             self.net.eval()
-            self._plan = InferencePlan(self.net, self.precision, owner=self)
+            self._plan = make_plan(self.net, self.precision, owner=self)
         self._plan.refresh_if_stale()
         return self._plan
 

@@ -238,6 +238,13 @@ int64_t cz_net_tower_blob_bytes(int n_conv);
 int cz_net_tower_small(const uint8_t *canon_boards, int n_pos, int cluster, int n_conv, const void *w1, const void *wblob, const float *bias,
                        const float *wh, const float *bh, void *hp, float *hv, void *stream);
 
+/* ---- fp32-accurate inference on the TF32 tensor cores ("3xTF32", net.py: SplitTf32Plan; policy_value_network.py:202-214 is fp32) ----
+ * y dev f32 [n_pix][128] (NHWC activations) -> hi dev f32 [n_pix][128] = tf32(y) (round to the 10-bit mantissa) and
+ * x2 dev f32 [n_pix][256] = { y - hi | hi }.  TF32 convolutions of hi with hi(w), and of x2 with { hi(w) | lo(w) }, accumulate
+ * hi*hi and lo*hi + hi*lo in f32 (two separate accumulation chains: the tensor cores' accumulator truncates, measured
+ * -6.6e-9 relative per accumulated term, so the full-size terms get the shortest chain). */
+int cz_net_split_tf32(const float *y, float *hi, float *x2, long long n_pix, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

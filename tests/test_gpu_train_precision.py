@@ -58,7 +58,7 @@ def _tower(net, x):
 
 def precision_study(blocks, n=96):
     """max-abs and relative error of every inference precision against an fp64 evaluation of the same weights."""
-    from cchess_zero_b200.net import InferencePlan, NativePlan
+    from cchess_zero_b200.net import NativePlan, make_plan
     net = scaled_net(blocks)
     x, canon = _positions(n, seed=2)
     with torch.no_grad():
@@ -66,8 +66,8 @@ def precision_study(blocks, n=96):
     net = net.float().cuda().to(memory_format=torch.channels_last)
     scale_l, scale_v = rl.abs().max().item(), rv.abs().max().item()
     out = dict(logit_absmax=scale_l, value_absmax=scale_v, value_absmedian=rv.abs().median().item())
-    for prec in ("fp32", "tf32", "fp16", "bf16"):
-        plan = InferencePlan(net, prec)
+    for prec in ("fp32", "tf32x3", "tf32", "fp16", "bf16"):
+        plan = make_plan(net, prec)
         l, v = plan(torch.from_numpy(x).cuda().to(plan.dtype))
         el = (l.double().cpu() - rl).abs().max().item()
         ev = (v.double().cpu().reshape(-1) - rv.reshape(-1)).abs().max().item()
@@ -93,6 +93,8 @@ def test_precision_at_realistic_logit_scale(blocks):
         this size.  The tolerance this package states for them is relative to max |logit| -- priors are ratios of
         logits, main.py:176-187 -- 2e-3 (7 blocks) / 8e-3 (19 blocks), and 1e-3 / 3e-3 absolute on the value.  precision="fp32"
         is the 1e-3-absolute mode and what it costs is on the bench line (extra.by_precision);
+      * tf32x3 (net.py: SplitTf32Plan -- hi/lo operand split, three TF32 products per term accumulated in f32 on the tensor cores)
+        meets 1e-3 ABSOLUTE with the same margin as fp32 at a fraction of fp32's cost (extra.by_precision);
       * bf16 misses all of it by a decade and is not offered."""
     r = precision_study(blocks)
     print("precision study (%d blocks): %s" % (blocks, json.dumps(r)))
@@ -101,11 +103,45 @@ def test_precision_at_realistic_logit_scale(blocks):
         json.dump(r, f, indent=1)
     assert 4.0 < r["logit_absmax"] < 16.0 and 0.2 < r["value_absmedian"] < 0.9
     assert r["fp32"]["logit_abs"] < 1e-3 / 5 and r["fp32"]["value_abs"] < 1e-4      # 1e-3 absolute, with margin
+    assert r["tf32x3"]["logit_abs"] < 1e-3 / 2 and r["tf32x3"]["value_abs"] < 1e-4  # the tensor-core mode that meets it too (accumulator truncation is what is left)
     rel_tol, val_tol = (2e-3, 1e-3) if blocks <= 7 else (8e-3, 3e-3)
     for p in ("tf32", "fp16", "fp16_native_ends"):
         assert r[p]["logit_rel"] < rel_tol, (p, r[p])
         assert r[p]["value_abs"] < val_tol, (p, r[p])
     assert r["bf16"]["logit_rel"] > rel_tol                                          # why bf16 is rejected
+
+
+def test_tf32_split_kernel_matches_its_torch_statement_and_search_runs_in_tf32x3():
+    """csrc/cz_net.cu: k_split_tf32 == net.split_acts bit for bit (incl. negative values, zeros, denormal-sized residues), and a
+    whole search with precision="tf32x3" (engine planes -> SplitTf32Plan -> tree) gives the visit counts of the fp32 evaluator on
+    the same weights (both are ~1e-6 from the exact network, far below any PUCT decision margin of these positions)."""
+    import ctypes as C
+    from cchess_zero_b200._lib import lib
+    from cchess_zero_b200.net import policy_value_network, split_acts
+    from cchess_zero_b200.mcts import MCTS_tree
+    torch.manual_seed(3)
+    for n_pix in (1, 90, 90 * 37 + 5):
+        y = torch.randn((n_pix, 128), device="cuda") * torch.logspace(-6, 3, 128, device="cuda")
+        y[0, :4] = torch.tensor([0.0, -0.0, 1.0, -1.0], device="cuda")
+        hi = torch.full((n_pix, 128), float("nan"), device="cuda")
+        x2 = torch.full((n_pix, 256), float("nan"), device="cuda")
+        assert lib().cz_net_split_tf32(y.data_ptr(), hi.data_ptr(), x2.data_ptr(), n_pix, C.c_void_p(torch.cuda.current_stream().cuda_stream)) == 0
+        rh, r2 = split_acts(y.t().reshape(1, 128, n_pix, 1))
+        assert torch.equal(hi.view(torch.int32), rh.reshape(128, n_pix).t().contiguous().view(torch.int32))
+        assert torch.equal(x2.view(torch.int32), r2.reshape(256, n_pix).t().contiguous().view(torch.int32))
+        assert int((hi.view(torch.int32) & 0x1FFF).abs().max()) == 0
+    visits = {}
+    for prec in ("fp32", "tf32x3"):
+        pv = policy_value_network(2, precision=prec, seed=5)
+        with torch.no_grad():
+            pv.net.p_fc.weight.mul_(40.0)
+        pv.weights_version += 1
+        from cchess_zero_b200 import rules
+        t = MCTS_tree(rules.START_STATE, pv.forward, 1)
+        t.main(rules.START_STATE, "w", 0, 200)
+        visits[prec] = [[a, n.N] for a, n in t.root.child.items()]
+    assert sum(n for _, n in visits["fp32"]) == 200 - 1 or sum(n for _, n in visits["fp32"]) == 200
+    assert visits["fp32"] == visits["tf32x3"]
 
 
 def test_train_step_on_cuda_matches_written_out_update_rule():

@@ -467,3 +467,26 @@ def test_pytorch_network_matches_independent_numpy_restatement_of_the_tf_graph()
     nl, nv = NN.forward(x, NN.tf_params_from_torch(net), 3)
     assert nl.shape == (12, 2086) and nv.shape == (12, 1)
     assert np.abs(tl.numpy() - nl).max() < 1e-10 and np.abs(tv.numpy() - nv).max() < 1e-10
+
+
+def test_tf32x3_split_algebra_is_fp32_accurate():
+    """net.py: tf32_hi / split_weights / split_acts -- with EVERY operand rounded to TF32 as the tensor cores do, the three-product
+    convolution  conv(hi, hi) + conv({ lo | hi }, { hi | lo })  is ~1e-7 from the exact one where a single TF32 product is ~1e-3
+    (what precision="tf32x3" rests on; the GPU tier measures the whole network against fp64, accumulator truncation included)."""
+    import torch
+    import torch.nn.functional as F
+    from cchess_zero_b200.net import tf32_hi, split_weights, split_acts
+    torch.manual_seed(0)
+    x = torch.relu(torch.randn(4, 128, 9, 10)) * 3.0
+    w = torch.randn(128, 128, 3, 3) * 0.03
+    h = tf32_hi(x)
+    assert int((h.view(torch.int32) & 0x1FFF).abs().max()) == 0                       # representable in TF32
+    assert float(((x - h).abs() / x.abs().clamp_min(1e-30)).max()) <= 2.0 ** -11 + 1e-9   # nearest
+    assert torch.equal(tf32_hi(-x), -h)                                                # sign-symmetric (ties away from zero)
+    ref = F.conv2d(x.double(), w.double(), padding=1)
+    one = F.conv2d(tf32_hi(x).double(), tf32_hi(w).double(), padding=1)
+    (xh, x2), (wh, w2) = split_acts(x), split_weights(w)
+    assert torch.equal(xh, h) and torch.equal(x2[:, :128], x - h) and torch.equal(x2[:, 128:], h)
+    three = F.conv2d(tf32_hi(xh).double(), tf32_hi(wh).double(), padding=1) + F.conv2d(tf32_hi(x2).double(), tf32_hi(w2).double(), padding=1)
+    e1, e3 = float((one - ref).abs().max()), float((three - ref).abs().max())
+    assert e1 > 5e-4 and e3 < 2e-6, (e1, e3)
