@@ -570,6 +570,14 @@ def run_ours(a, rank, world, local_rank):
                  max_arena_words=c1["max_arena_words"], max_depth=c1["max_depth"],
                  mean_L=(c1["sum_L"] - m["c0"]["sum_L"]) / max(1, c1["n_playout"] - m["c0"]["n_playout"]),
                  mean_children=(c1["sum_C"] - m["c0"]["sum_C"]) / max(1, c1["n_expand"] - m["c0"]["n_expand"]))
+    _, _, peaks = measured_peaks()
+    tpeak = float(peaks.get("bf16_tflops_sustained", 0) or 0)
+    # the kernels that DOMINATE a wave are the library tcgen05 convolutions of the residual tower: their share of the roofline over the
+    # whole search (all other kernels, launch gaps and the tree kernel included in the time), against the measured sustained bf16 peak
+    extra["tower_roofline"] = dict(bound="tensor", achieved=extra["nn_tflops"], unit="TFLOP/s", peak=tpeak or None,
+                                   frac=(extra["nn_tflops"] / tpeak) if tpeak else None,
+                                   peak_source="MEASURED_PEAKS.json bf16_tflops_sustained" if tpeak else None,
+                                   note="network FLOPs of every evaluated leaf (%.1f MFLOP each) / device time of the whole search" % (FLOPS_PER_EVAL.get(a.res_blocks, 0) / 1e6))
     if "soak" in legs:
         s = leg_soak(main, a.soak_plies)
         extra["soak"] = s

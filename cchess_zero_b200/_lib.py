@@ -63,6 +63,7 @@ def _sig(L):
     L.cz_net_heads_tc.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.cz_net_heads_fc.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.cz_net_split_tf32.argtypes = [vp, vp, vp, i64, vp]
+    L.cz_net_epilogue_split.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, vp]
     L.cz_net_tower_blob_bytes.argtypes = [i32]
     L.cz_net_tower_blob_bytes.restype = i64
     L.cz_net_tower_small.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp]

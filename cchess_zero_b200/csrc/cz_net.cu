@@ -607,21 +607,79 @@ __global__ void __launch_bounds__(128) k_policy_fc(const __half *__restrict__ hp
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------------
-// "3xTF32" operand split for the fp32-accurate inference mode (net.py: SplitTf32Plan).  y f32 [P][128] (NHWC activations of one
-// convolution) -> hi f32 [P][128] = tf32(y) and x2 f32 [P][256] = { y - hi | hi }, where tf32() rounds to the 10-bit TF32 mantissa
-// (nearest, ties away; the low 13 bits of hi are zero, so whatever conversion the tensor-core kernel applies to it is the identity).
-// Two TF32 convolutions then give hi(x)*hi(w) (operand hi, K = 1152: the only long accumulation chain of full-size terms) and
-// lo(x)*hi(w) + hi(x)*lo(w) (operand x2 against { hi(w) | lo(w) }, terms 2^-11 smaller); the dropped lo*lo term and the rounding of
-// the two lo operands are O(2^-22) relative.  Streaming kernel: 16 B in, 48 B out per thread.
+// Operand split for the fp32-accurate inference mode (net.py: SplitTf32Plan).  y f32 [P][128] (NHWC activations of one convolution)
+//   -> hi f32 [P][128] = tf32(y): rounded to the 10-bit TF32 mantissa (nearest, ties away; the low 13 bits are zero, so whatever
+//      conversion the tensor-core kernel applies to it is the identity), and
+//   -> x2 fp16 [P][256] = { (y - hi) * 2^11 | hi }: both halves have <= 11 significant bits, i.e. they are EXACT in fp16 (up to
+//      fp16's range: |hi| <= 65504, residues below 2^-24 * 2^11 flush).
+// A TF32 convolution hi(x) * hi(w) (K = 1152: the only long accumulation chain of full-size terms) plus an fp16 convolution
+// x2 * { hi(w) | lo(w) * 2^11 } (the two cross terms, 2^-11 smaller, scaled back by 2^-11 in the epilogue) give the product to
+// O(2^-22): dropped are lo*lo and the 11-bit rounding of the two lo operands.  Streaming kernel: 32 B in, 64 B out per thread.
 __device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u); }
+#define SPLIT_SCALE 2048.0f
 
-__global__ void __launch_bounds__(256) k_split_tf32(const float4 *__restrict__ y, float4 *__restrict__ hi, float4 *__restrict__ x2, long long n4) {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-        const float4 v = __ldg(y + i);
-        const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
-        const float4 l = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
-        float4 *o = x2 + (i >> 5) * 64 + (i & 31);
-        hi[i] = h; o[0] = l; o[32] = h;
+__global__ void __launch_bounds__(256) k_split_tf32(const float4 *__restrict__ y, float4 *__restrict__ hi, uint4 *__restrict__ x2, long long n8) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+        const float4 a = __ldg(y + 2 * i), b = __ldg(y + 2 * i + 1);
+        const float4 ha = make_float4(tf32_hi(a.x), tf32_hi(a.y), tf32_hi(a.z), tf32_hi(a.w));
+        const float4 hb = make_float4(tf32_hi(b.x), tf32_hi(b.y), tf32_hi(b.z), tf32_hi(b.w));
+        hi[2 * i] = ha; hi[2 * i + 1] = hb;
+        uint4 l, h;
+        *reinterpret_cast<__half2 *>(&l.x) = __floats2half2_rn((a.x - ha.x) * SPLIT_SCALE, (a.y - ha.y) * SPLIT_SCALE);
+        *reinterpret_cast<__half2 *>(&l.y) = __floats2half2_rn((a.z - ha.z) * SPLIT_SCALE, (a.w - ha.w) * SPLIT_SCALE);
+        *reinterpret_cast<__half2 *>(&l.z) = __floats2half2_rn((b.x - hb.x) * SPLIT_SCALE, (b.y - hb.y) * SPLIT_SCALE);
+        *reinterpret_cast<__half2 *>(&l.w) = __floats2half2_rn((b.z - hb.z) * SPLIT_SCALE, (b.w - hb.w) * SPLIT_SCALE);
+        *reinterpret_cast<__half2 *>(&h.x) = __floats2half2_rn(ha.x, ha.y);
+        *reinterpret_cast<__half2 *>(&h.y) = __floats2half2_rn(ha.z, ha.w);
+        *reinterpret_cast<__half2 *>(&h.z) = __floats2half2_rn(hb.x, hb.y);
+        *reinterpret_cast<__half2 *>(&h.w) = __floats2half2_rn(hb.z, hb.w);
+        uint4 *o = x2 + (i >> 4) * 32 + (i & 15);          // row of 256 halves = 32 uint4: { lo: 16 | hi: 16 }
+        o[0] = l; o[16] = h;
+    }
+}
+
+// One pass per convolution: v = ReLU(t + 2^-11 s + bias [+ skip]) from the two library convolutions' raw results, then the split of v
+// for the NEXT convolution.  t f32 [P][128] (hi*hi), s fp16 [P][128] or null (cross terms, scaled), skip f32 or null; outputs (each
+// optional): x f32 (the value itself: next block's skip / the heads' input; may alias skip), hi f32, x2 fp16 [P][256] = { lo 2^11 | hi }.
+// Streaming: 32-80 B in, 64-96 B out per thread (8 channels).
+__global__ void __launch_bounds__(256) k_epilogue_split(const float4 *__restrict__ t, const uint4 *__restrict__ s, const float4 *__restrict__ bias,
+                                                        const float4 *skip, float4 *x, float4 *__restrict__ hi, uint4 *__restrict__ x2, long long n8) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+        float4 a = __ldg(t + 2 * i), b = __ldg(t + 2 * i + 1);
+        if (s) {
+            const uint4 sv = __ldg(s + i);
+            const float2 s0 = __half22float2(*reinterpret_cast<const __half2 *>(&sv.x)), s1 = __half22float2(*reinterpret_cast<const __half2 *>(&sv.y));
+            const float2 s2 = __half22float2(*reinterpret_cast<const __half2 *>(&sv.z)), s3 = __half22float2(*reinterpret_cast<const __half2 *>(&sv.w));
+            const float r = 1.0f / SPLIT_SCALE;
+            a.x += s0.x * r; a.y += s0.y * r; a.z += s1.x * r; a.w += s1.y * r;
+            b.x += s2.x * r; b.y += s2.y * r; b.z += s3.x * r; b.w += s3.y * r;
+        }
+        const float4 ba = __ldg(bias + 2 * (i & 15)), bb = __ldg(bias + 2 * (i & 15) + 1);
+        a.x += ba.x; a.y += ba.y; a.z += ba.z; a.w += ba.w;
+        b.x += bb.x; b.y += bb.y; b.z += bb.z; b.w += bb.w;
+        if (skip) {
+            const float4 ka = skip[2 * i], kb = skip[2 * i + 1];
+            a.x += ka.x; a.y += ka.y; a.z += ka.z; a.w += ka.w;
+            b.x += kb.x; b.y += kb.y; b.z += kb.z; b.w += kb.w;
+        }
+        a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
+        b.x = fmaxf(b.x, 0.f); b.y = fmaxf(b.y, 0.f); b.z = fmaxf(b.z, 0.f); b.w = fmaxf(b.w, 0.f);
+        if (x) { x[2 * i] = a; x[2 * i + 1] = b; }
+        if (!hi) continue;
+        const float4 ha = make_float4(tf32_hi(a.x), tf32_hi(a.y), tf32_hi(a.z), tf32_hi(a.w));
+        const float4 hb = make_float4(tf32_hi(b.x), tf32_hi(b.y), tf32_hi(b.z), tf32_hi(b.w));
+        hi[2 * i] = ha; hi[2 * i + 1] = hb;
+        uint4 l, h;
+        *reinterpret_cast<__half2 *>(&l.x) = __floats2half2_rn((a.x - ha.x) * SPLIT_SCALE, (a.y - ha.y) * SPLIT_SCALE);
+        *reinterpret_cast<__half2 *>(&l.y) = __floats2half2_rn((a.z - ha.z) * SPLIT_SCALE, (a.w - ha.w) * SPLIT_SCALE);
+        *reinterpret_cast<__half2 *>(&l.z) = __floats2half2_rn((b.x - hb.x) * SPLIT_SCALE, (b.y - hb.y) * SPLIT_SCALE);
+        *reinterpret_cast<__half2 *>(&l.w) = __floats2half2_rn((b.z - hb.z) * SPLIT_SCALE, (b.w - hb.w) * SPLIT_SCALE);
+        *reinterpret_cast<__half2 *>(&h.x) = __floats2half2_rn(ha.x, ha.y);
+        *reinterpret_cast<__half2 *>(&h.y) = __floats2half2_rn(ha.z, ha.w);
+        *reinterpret_cast<__half2 *>(&h.z) = __floats2half2_rn(hb.x, hb.y);
+        *reinterpret_cast<__half2 *>(&h.w) = __floats2half2_rn(hb.z, hb.w);
+        uint4 *o = x2 + (i >> 4) * 32 + (i & 15);
+        o[0] = l; o[16] = h;
     }
 }
 
@@ -730,16 +788,33 @@ int cz_net_heads_tc(const void *x, int B, const float *wh, const float *bh, cons
     return CZ_OK;
 }
 
-// y dev f32 [n_pix][128] -> hi dev f32 [n_pix][128] = tf32(y), x2 dev f32 [n_pix][256] = { y - hi | hi } (see k_split_tf32)
-int cz_net_split_tf32(const float *y, float *hi, float *x2, long long n_pix, void *stream) {
+// y dev f32 [n_pix][128] -> hi dev f32 [n_pix][128] = tf32(y), x2 dev fp16 [n_pix][256] = { (y - hi) * 2^11 | hi } (see k_split_tf32)
+int cz_net_split_tf32(const float *y, float *hi, void *x2, long long n_pix, void *stream) {
     if (!y || !hi || !x2 || n_pix <= 0) return CZ_EINVAL;
-    const long long n4 = n_pix * 32;
+    const long long n8 = n_pix * 16;
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    long long blocks = (n4 + 255) / 256;
+    long long blocks = (n8 + 255) / 256;
     if (blocks > 8LL * sms) blocks = 8LL * sms;          // grid-stride, 8 resident CTAs of 256 threads per SM
     k_split_tf32<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4 *>(y), reinterpret_cast<float4 *>(hi),
-                                                                    reinterpret_cast<float4 *>(x2), n4);
+                                                                    reinterpret_cast<uint4 *>(x2), n8);
+    return cudaGetLastError() == cudaSuccess ? CZ_OK : CZ_ECUDA;
+}
+
+// The f32 epilogue of one three-product convolution fused with the operand split for the next one (k_epilogue_split):
+//   v = ReLU(t + 2^-11 s + bias [+ skip]);  x (optional) = v;  hi / x2 (optional, both or neither) = split of v as in cz_net_split_tf32.
+// t dev f32 [n_pix][128]; s dev fp16 [n_pix][128] or NULL; bias dev f32 [128]; skip dev f32 [n_pix][128] or NULL (x may alias skip).
+int cz_net_epilogue_split(const float *t, const void *s, const float *bias, const float *skip, float *x, float *hi, void *x2, long long n_pix, void *stream) {
+    if (!t || !bias || n_pix <= 0 || (!x && !hi) || ((hi == nullptr) != (x2 == nullptr))) return CZ_EINVAL;
+    const long long n8 = n_pix * 16;
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    long long blocks = (n8 + 255) / 256;
+    if (blocks > 8LL * sms) blocks = 8LL * sms;
+    k_epilogue_split<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4 *>(t), reinterpret_cast<const uint4 *>(s),
+                                                                        reinterpret_cast<const float4 *>(bias), reinterpret_cast<const float4 *>(skip),
+                                                                        reinterpret_cast<float4 *>(x), reinterpret_cast<float4 *>(hi),
+                                                                        reinterpret_cast<uint4 *>(x2), n8);
     return cudaGetLastError() == cudaSuccess ? CZ_OK : CZ_ECUDA;
 }
 

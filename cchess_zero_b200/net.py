@@ -223,16 +223,21 @@ def tf32_hi(t):
     return ((t.contiguous().view(torch.int32) + 0x1000) & -8192).view(torch.float32).reshape(t.shape)
 
 
+SPLIT_SCALE = 2048.0      # 2^11: the lo halves travel scaled into fp16's normal range (csrc/cz_net.cu: SPLIT_SCALE)
+
+
 def split_weights(w):
-    """[O, C, kh, kw] f32 -> (hi(w) [O, C, kh, kw], { hi(w) | w - hi(w) } [O, 2C, kh, kw]): the weight side of the 3xTF32 product."""
+    """[O, C, kh, kw] f32 -> (hi(w) f32 [O, C, kh, kw], { hi(w) | (w - hi(w)) * 2^11 } fp16 [O, 2C, kh, kw]): the weight side of
+    the three-product convolution.  Both fp16 halves have <= 11 significant bits: exact in fp16 up to its range."""
     h = tf32_hi(w)
-    return h, torch.cat([h, w - h], 1)
+    return h, torch.cat([h, (w - h) * SPLIT_SCALE], 1).to(torch.float16)
 
 
 def split_acts(x):
-    """[B, C, H, W] f32 -> (hi(x) [B, C, H, W], { x - hi(x) | hi(x) } [B, 2C, H, W]): torch statement of csrc/cz_net.cu: k_split_tf32."""
+    """[B, C, H, W] f32 -> (hi(x) f32 [B, C, H, W], { (x - hi(x)) * 2^11 | hi(x) } fp16 [B, 2C, H, W]): torch statement of
+    csrc/cz_net.cu: k_split_tf32."""
     h = tf32_hi(x)
-    return h, torch.cat([x - h, h], 1)
+    return h, torch.cat([(x - h) * SPLIT_SCALE, h], 1).to(torch.float16)
 
 
 class SplitTf32Plan(InferencePlan):
@@ -241,15 +246,18 @@ class SplitTf32Plan(InferencePlan):
     mantissas through 15-39 convolutions and miss an absolute 1e-3 on logits of size 8), at a tenth of the
     cost of cuDNN's fp32 convolutions (which do not use the tensor cores: 57x slower than fp16).
 
-    Every activation x and weight w is split into hi = tf32(x) and lo = x - hi; per convolution
-        s   = conv_tf32({ lo(x) | hi(x) }, { hi(w) | lo(w) })                 the two small cross terms, K = 2 x 1152
-        out = relu(conv_tf32(hi(x), hi(w)) + s [+ skip] + bias)               the full-size term, fused library epilogue, f32
-    What is dropped (lo*lo, the tf32 rounding of the two lo operands) is O(2^-22) relative.  The two terms are accumulated
+    Every activation x and weight w is split into hi = tf32(x) (10-bit mantissa) and lo = x - hi; per convolution
+        s   = conv_fp16({ lo(x) 2^11 | hi(x) }, { hi(w) | lo(w) 2^11 })        the two small cross terms, K = 2 x 1152; the operands
+                                                                              have <= 11 significant bits, i.e. are exact in fp16
+        out = relu(conv_tf32(hi(x), hi(w)) + 2^-11 s [+ skip] + bias)         the full-size term; the f32 epilogue AND the hi / lo split
+                                                                              of `out` for the next convolution are one streaming
+                                                                              pass of this package (csrc/cz_net.cu: k_epilogue_split)
+    What is dropped (lo*lo, the 11-bit rounding of the two lo operands and of s) is O(2^-22) relative.  The two terms are accumulated
     SEPARATELY because the tensor cores' f32 accumulator truncates (tools/tf32x3_probe.py: -6.6e-9 relative per accumulated term,
-    linear in K): one convolution over { hi | lo | hi } x { hi | hi | lo } (K = 3456) measured 9.6e-6 relative per layer, this
-    arrangement 3.4e-6 for 8 % more time (hi*hi in two / four input-channel groups: 1.6e-6 / 7.7e-7 for +35 % / +90 %).
-    The hi / lo split of a convolution's result is csrc/cz_net.cu: k_split_tf32 (one streaming kernel per convolution).  The first
-    convolution takes the one-hot planes (exact in any precision) against { hi(w) | lo(w) } with 2 x 14 channels; the heads
+    linear in K): one TF32 convolution over { hi | lo | hi } x { hi | hi | lo } (K = 3456) measured 9.6e-6 relative per layer,
+    hi*hi apart from the cross terms 3.4e-6 (hi*hi in two / four input-channel groups: 1.6e-6 / 7.7e-7 for +35 % / +90 % time).
+    The first
+    convolution takes the one-hot planes (exact in any precision) against { hi(w) | lo(w) } with 2 x 14 channels in TF32; the heads
     (3 of 128 channels, 180 -> 2086, 90 -> 256 -> 1) run in true fp32."""
 
     def __init__(self, net, owner=None):
@@ -264,67 +272,58 @@ class SplitTf32Plan(InferencePlan):
         cl = lambda t: t.contiguous(memory_format=torch.channels_last)  # noqa: E731
         with torch.no_grad():
             w, b = d["w_in"]
-            d["w_in"] = (cl(split_weights(w)[1]), b)                     # [128, 28, 3, 3]: { hi | lo } against the planes twice
+            h = tf32_hi(w)
+            d["w_in"] = (cl(torch.cat([h, w - h], 1)), b)                # [128, 28, 3, 3]: { hi | lo } against the planes twice
 
             def ws(wb):
                 h, w2 = split_weights(wb[0])
-                return cl(h), cl(w2), wb[1]                             # [128,128,3,3], [128,256,3,3], bias
+                return cl(h), cl(w2), wb[1]                             # f32 [128,128,3,3], fp16 [128,256,3,3], bias
             d["blocks"] = [(ws(c1), ws(c2)) for c1, c2 in d["blocks"]]
         return d
 
     def _probe_fused(self):
-        try:
-            dev = self.w_in[0].device
-            x = torch.randn(4, 128, 9, 10, device=dev).contiguous(memory_format=torch.channels_last)
-            s = torch.randn(4, 128, 9, 10, device=dev).contiguous(memory_format=torch.channels_last)
-            w = torch.randn(128, 128, 3, 3, device=dev).mul_(0.02).contiguous(memory_format=torch.channels_last)
-            b = torch.randn(128, device=dev)
-            with self._ctx():
-                a2 = torch.cudnn_convolution_add_relu(x, w, s, 1.0, b, (1, 1), (1, 1), (1, 1), 1)
-            r = F.conv2d(x.double(), w.double(), b.double(), padding=1)
-            return bool(torch.allclose(a2.double(), F.relu(r + s.double()), atol=5e-2, rtol=5e-2))
-        except Exception:
-            return False
+        return False          # the epilogue is this package's own kernel (k_epilogue_split); the library convolutions run bare
 
-    def _split(self, y):
-        """y: [B,128,9,10] f32 channels_last -> (hi [B,128,9,10], { lo | hi } [B,256,9,10]), channels_last views of one pair of buffers
-        per batch size (allocated on the first -- eager, warm-up -- call; their previous consumers were issued on the same stream)."""
-        B = y.shape[0]
-        if not y.is_contiguous(memory_format=torch.channels_last):
-            y = y.contiguous(memory_format=torch.channels_last)
+    def _buffers(self, B, dev):
+        """x f32 [B,9,10,128] (block input / skip / heads' input), hi f32 [B,9,10,128], x2 fp16 [B,9,10,256]: one set per batch size,
+        allocated on the first (eager, warm-up) call; every consumer is issued on the same stream before the next producer."""
         bufs = self._bufs.get(B)
         if bufs is None:
-            bufs = self._bufs[B] = (torch.empty((B, 9, 10, 128), dtype=torch.float32, device=y.device),
-                                    torch.empty((B, 9, 10, 256), dtype=torch.float32, device=y.device))
-        rc = self._lib.cz_net_split_tf32(y.data_ptr(), bufs[0].data_ptr(), bufs[1].data_ptr(), B * 90,
-                                         self._C.c_void_p(torch.cuda.current_stream().cuda_stream))
-        if rc:
-            raise RuntimeError("cz_net_split_tf32 failed (%d)" % rc)
-        return bufs[0].permute(0, 3, 1, 2), bufs[1].permute(0, 3, 1, 2)
+            bufs = self._bufs[B] = (torch.empty((B, 9, 10, 128), dtype=torch.float32, device=dev),
+                                    torch.empty((B, 9, 10, 128), dtype=torch.float32, device=dev),
+                                    torch.empty((B, 9, 10, 256), dtype=torch.float16, device=dev))
+        return bufs
 
-    def _conv3(self, x, wts, skip=None):
-        """relu(conv(x, w) + bias [+ skip]) from the three TF32 products; x f32 [B,128,9,10] channels_last."""
-        w_hh, w_small, b = wts
-        hi, x2 = self._split(x)
-        s = F.conv2d(x2, w_small, None, padding=1)
-        if skip is not None:
-            s.add_(skip)
-        if self.fused:
-            return torch.cudnn_convolution_add_relu(hi, w_hh, s, 1.0, b, (1, 1), (1, 1), (1, 1), 1)
-        return F.relu_(F.conv2d(hi, w_hh, b, padding=1).add_(s))
+    def _epilogue(self, t, s, bias, skip, x, hi, x2, n_pix):
+        """v = relu(t + 2^-11 s + bias [+ skip]) -> x (optional) and the split (hi, x2) of v (optional): csrc/cz_net.cu: k_epilogue_split."""
+        cl = torch.channels_last
+        t = t.contiguous(memory_format=cl)                    # (the library already returns channels_last: no copy)
+        s = None if s is None else s.contiguous(memory_format=cl)
+        p = lambda z: None if z is None else z.data_ptr()  # noqa: E731
+        rc = self._lib.cz_net_epilogue_split(t.data_ptr(), p(s), bias.data_ptr(), p(skip), p(x), p(hi), p(x2), n_pix,
+                                             self._C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        if rc:
+            raise RuntimeError("cz_net_epilogue_split failed (%d)" % rc)
 
     @torch.no_grad()
     def __call__(self, nn_in, logits_out=None, value_out=None):
         """nn_in: [B,9,10,14] one-hot planes (any float dtype) on the device."""
         B = nn_in.shape[0]
+        X, HI, X2 = self._buffers(B, nn_in.device)
+        hi_v, x2_v = HI.permute(0, 3, 1, 2), X2.permute(0, 3, 1, 2)          # NCHW views of NHWC memory = channels_last
+        n_pix, nb = B * 90, len(self.blocks)
         x = nn_in.permute(0, 3, 1, 2).float()
         with self._ctx():
-            x = F.relu_(F.conv2d(torch.cat([x, x], 1).contiguous(memory_format=torch.channels_last), self.w_in[0], self.w_in[1], padding=1))
-            for c1, c2 in self.blocks:
-                y = self._conv3(x, c1)
-                x = self._conv3(y, c2, skip=x)
+            t = F.conv2d(torch.cat([x, x], 1).contiguous(memory_format=torch.channels_last), self.w_in[0], None, padding=1)
+            self._epilogue(t, None, self.w_in[1], None, X, HI if nb else None, X2 if nb else None, n_pix)
+            for i, ((wh1, ws1, b1), (wh2, ws2, b2)) in enumerate(self.blocks):
+                t, s = F.conv2d(hi_v, wh1, None, padding=1), F.conv2d(x2_v, ws1, None, padding=1)
+                self._epilogue(t, s, b1, None, None, HI, X2, n_pix)             # y = relu(conv1(x)): only its split is needed
+                t, s = F.conv2d(hi_v, wh2, None, padding=1), F.conv2d(x2_v, ws2, None, padding=1)
+                last = i == nb - 1
+                self._epilogue(t, s, b2, X, X, None if last else HI, None if last else X2, n_pix)   # x = relu(conv2(y) + x)
         with _Tf32(False):
-            h = F.relu_(F.conv2d(x, self.w_head[0], self.w_head[1])).permute(0, 2, 3, 1)
+            h = F.relu_(F.conv2d(X.permute(0, 3, 1, 2), self.w_head[0], self.w_head[1])).permute(0, 2, 3, 1)
             p = h[..., :2].reshape(B, 180)
             v = h[..., 2].reshape(B, 90)
             logits = F.linear(p, self.p_fc[0], self.p_fc[1])

@@ -238,12 +238,17 @@ int64_t cz_net_tower_blob_bytes(int n_conv);
 int cz_net_tower_small(const uint8_t *canon_boards, int n_pos, int cluster, int n_conv, const void *w1, const void *wblob, const float *bias,
                        const float *wh, const float *bh, void *hp, float *hv, void *stream);
 
-/* ---- fp32-accurate inference on the TF32 tensor cores ("3xTF32", net.py: SplitTf32Plan; policy_value_network.py:202-214 is fp32) ----
+/* ---- fp32-accurate inference on the tensor cores (net.py: SplitTf32Plan; policy_value_network.py:202-214 is fp32) ----
  * y dev f32 [n_pix][128] (NHWC activations) -> hi dev f32 [n_pix][128] = tf32(y) (round to the 10-bit mantissa) and
- * x2 dev f32 [n_pix][256] = { y - hi | hi }.  TF32 convolutions of hi with hi(w), and of x2 with { hi(w) | lo(w) }, accumulate
- * hi*hi and lo*hi + hi*lo in f32 (two separate accumulation chains: the tensor cores' accumulator truncates, measured
- * -6.6e-9 relative per accumulated term, so the full-size terms get the shortest chain). */
-int cz_net_split_tf32(const float *y, float *hi, float *x2, long long n_pix, void *stream);
+ * x2 dev fp16 [n_pix][256] = { (y - hi) * 2^11 | hi } (both exact in fp16).  A TF32 convolution of hi with hi(w) and an fp16
+ * convolution of x2 with { hi(w) | lo(w) * 2^11 } accumulate hi*hi and (lo*hi + hi*lo) * 2^11 in two separate f32 chains (the
+ * tensor cores' accumulator truncates, measured -6.6e-9 relative per accumulated term: the full-size terms get the short chain). */
+int cz_net_split_tf32(const float *y, float *hi, void *x2, long long n_pix, void *stream);
+/* The f32 epilogue of such a convolution fused with the split for the next one, one streaming pass:
+ *   v = ReLU(t + 2^-11 s + bias [+ skip]);   x = v (optional);   hi, x2 = split of v (optional, both or neither)
+ * t dev f32 [n_pix][128] (hi*hi, raw); s dev fp16 [n_pix][128] or NULL (cross terms, raw, scaled by 2^11); bias dev f32 [128];
+ * skip dev f32 [n_pix][128] or NULL (x may alias skip). */
+int cz_net_epilogue_split(const float *t, const void *s, const float *bias, const float *skip, float *x, float *hi, void *x2, long long n_pix, void *stream);
 
 #ifdef __cplusplus
 }

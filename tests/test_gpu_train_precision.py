@@ -121,15 +121,29 @@ def test_tf32_split_kernel_matches_its_torch_statement_and_search_runs_in_tf32x3
     from cchess_zero_b200.mcts import MCTS_tree
     torch.manual_seed(3)
     for n_pix in (1, 90, 90 * 37 + 5):
-        y = torch.randn((n_pix, 128), device="cuda") * torch.logspace(-6, 3, 128, device="cuda")
+        y = torch.randn((n_pix, 128), device="cuda") * torch.logspace(-4, 3, 128, device="cuda")
         y[0, :4] = torch.tensor([0.0, -0.0, 1.0, -1.0], device="cuda")
         hi = torch.full((n_pix, 128), float("nan"), device="cuda")
-        x2 = torch.full((n_pix, 256), float("nan"), device="cuda")
+        x2 = torch.full((n_pix, 256), float("nan"), device="cuda", dtype=torch.float16)
         assert lib().cz_net_split_tf32(y.data_ptr(), hi.data_ptr(), x2.data_ptr(), n_pix, C.c_void_p(torch.cuda.current_stream().cuda_stream)) == 0
         rh, r2 = split_acts(y.t().reshape(1, 128, n_pix, 1))
         assert torch.equal(hi.view(torch.int32), rh.reshape(128, n_pix).t().contiguous().view(torch.int32))
-        assert torch.equal(x2.view(torch.int32), r2.reshape(256, n_pix).t().contiguous().view(torch.int32))
+        assert torch.equal(x2.view(torch.int16), r2.reshape(256, n_pix).t().contiguous().view(torch.int16))
         assert int((hi.view(torch.int32) & 0x1FFF).abs().max()) == 0
+        # the fused epilogue + split: v = relu(t + 2^-11 s + bias + skip) written in place of skip, and v's split
+        t = torch.randn((n_pix, 128), device="cuda"); sc = (torch.randn((n_pix, 128), device="cuda") * 3).half()
+        bias = torch.randn(128, device="cuda"); skip = torch.randn((n_pix, 128), device="cuda")
+        want = torch.relu(((t + sc.float() * (1.0 / 2048.0)) + bias) + skip)
+        xs = skip.clone(); hi.fill_(float("nan")); x2.fill_(float("nan"))
+        assert lib().cz_net_epilogue_split(t.data_ptr(), sc.data_ptr(), bias.data_ptr(), xs.data_ptr(), xs.data_ptr(), hi.data_ptr(), x2.data_ptr(),
+                                           n_pix, C.c_void_p(torch.cuda.current_stream().cuda_stream)) == 0
+        assert torch.equal(xs, want)
+        rh, r2 = split_acts(want.t().reshape(1, 128, n_pix, 1))
+        assert torch.equal(hi, rh.reshape(128, n_pix).t()) and torch.equal(x2.view(torch.int16), r2.reshape(256, n_pix).t().contiguous().view(torch.int16))
+        xo = torch.empty_like(t)                                                # no cross terms, no skip, no split (first layer / last layer shapes)
+        assert lib().cz_net_epilogue_split(t.data_ptr(), None, bias.data_ptr(), None, xo.data_ptr(), None, None, n_pix,
+                                           C.c_void_p(torch.cuda.current_stream().cuda_stream)) == 0
+        assert torch.equal(xo, torch.relu(t + bias))
     visits = {}
     for prec in ("fp32", "tf32x3"):
         pv = policy_value_network(2, precision=prec, seed=5)
