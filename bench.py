@@ -438,7 +438,8 @@ def leg_config5(a, local_rank, pv):
 
 def leg_threads16(a, rank, world, local_rank, pv, games=256):
     """`games` games x `playouts` playouts with search_threads = 16 inside every game (the reference's default schedule, exact): the
-    network batch is games x 16 rows per wave, ~11 of 16 rows of a game carry a leaf."""
+    network batch is games x 16 rows per wave, of which ~11 of 16 carry a leaf: only those are evaluated (row compaction,
+    cz_engine_wave_compact; the network runs on bucketed batch sizes from lazily captured CUDA graphs)."""
     from cchess_zero_b200.selfplay import SelfPlay
     K = 16
     sp = SelfPlay(games, None, a.playouts, seeds=[rank * games + g for g in range(games)], device=local_rank, auto_reset=True, keep_records=False,
@@ -448,7 +449,7 @@ def leg_threads16(a, rank, world, local_rank, pv, games=256):
     for _ in range(2):
         sp.step()
     torch.cuda.synchronize()
-    c0, w0 = e.counters(), sp.waves
+    c0, w0, r0 = e.counters(), sp.waves, getattr(sp, "rows_evaluated", 0)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     steps = 4
@@ -462,6 +463,8 @@ def leg_threads16(a, rank, world, local_rank, pv, games=256):
     out = dict(workload="%d concurrent games x %d playouts, search_threads=%d inside every game (k_wave_fifo), res_block_nums=%d" % (games, a.playouts, K, a.res_blocks),
                e2e=n / (ms * 1e-3), unit="expansions/s", plies_timed=steps, ms_per_step=ms / steps, waves_per_step=(sp.waves - w0) / steps,
                network_rows_per_wave=games * K, leaves_per_wave=n / max(1, sp.waves - w0),
+               row_compaction=bool(getattr(sp, "compact", False)),
+               rows_evaluated_per_wave=((sp.rows_evaluated - r0) / max(1, sp.waves - w0)) if getattr(sp, "compact", False) else games * K,
                semantics="every game follows the reference's search_threads=16 coroutine schedule (canonical FIFO form, pinned to real uvloop runs)")
     e.close()
     return out

@@ -121,6 +121,12 @@ struct Dev {
     int hash_on;                      // maintain Zobrist keys of the pending leaves (board hashing; off by default)
     int narr;                         // arrays per node block: 5 (P W N META CHILD), 6 in FIFO mode (+ stored Q, main.py:193)
     uint32_t *fifo;                   // [B][FW] event-loop state of the search_threads = K schedule (k_wave_fifo); NULL otherwise
+    // row compaction of the K-row network batch (cz_engine_wave_compact): only rows that carry a leaf are evaluated
+    int compact;                      // this launch reads logits / value through row_map and publishes live_mask
+    uint32_t *live_mask;              // [B] bit s = slot s of the game awaits an evaluation queued by THIS launch
+    int32_t *row_map;                 // [B*K] (game, slot) -> row of the dense batch its leaf was evaluated in
+    int32_t *src_of;                  // [B*K] dense row -> g*K + slot
+    int32_t *dense_count;             // [1]   rows of the dense batch
     uint32_t *hdr;                    // [B][HW]
     uint8_t *root_board;              // [B][96]
     uint8_t *leaf_board;              // [B][96]
@@ -763,7 +769,7 @@ __global__ void __launch_bounds__(32 * MAX_WPB, 1) k_wave_fifo(Dev E, T *nn_in, 
     uint32_t fw = lane < FW ? fp[lane] : 0u;
     const uint32_t rbw = lane < 24 ? reinterpret_cast<const uint32_t *>(E.root_board + (size_t)g * 96)[lane] : 0u;
     uint32_t flags = HGET(H_FLAGS);
-    if (!(flags & F_ACTIVE)) return;
+    if (!(flags & F_ACTIVE)) { if (E.compact && lane == 0) E.live_mask[g] = 0u; return; }
     uint32_t *ar = arena_half(E, g, (flags & F_CUR) ? 1 : 0);
     const int K = E.K;
     int done = (int)HGET(H_DONE);
@@ -774,6 +780,9 @@ __global__ void __launch_bounds__(32 * MAX_WPB, 1) k_wave_fifo(Dev E, T *nn_in, 
     const int root_N = (int)HGET(H_ROOTN);
     const int side0 = (flags & F_SIDE) ? 1 : 0, rr0 = (int)HGET(H_RR);
     int pend = (int)F_PEND(flags);
+    uint32_t live = 0u;               // slots whose leaf goes to the network after this launch
+    // the network row that holds the evaluation of (game, slot): the slot's own row, or the dense row the compaction gave it
+#define NN_ROW(idx_) (E.compact ? (size_t)E.row_map[idx_] : (size_t)(idx_))
     int iter = (int)__shfl_sync(CZ_FULL, fw, FI_ITER), ncur = (int)__shfl_sync(CZ_FULL, fw, FI_NCUR);
     int nq = (int)__shfl_sync(CZ_FULL, fw, FI_NQ), started = (int)__shfl_sync(CZ_FULL, fw, FI_STARTED);
     {
@@ -790,7 +799,7 @@ __global__ void __launch_bounds__(32 * MAX_WPB, 1) k_wave_fifo(Dev E, T *nn_in, 
         uint32_t base;
         const int n = expand_reserve(E, S, alloc, base, errf, lane);
         if (n > 0) {
-            expand_write(ar, S, logits + (size_t)g * K * CZ_NLABEL, n, base, lane, true);
+            expand_write(ar, S, logits + NN_ROW((size_t)g * K) * CZ_NLABEL, n, base, lane, true);
             root_base = base; root_cnt = n;
             if (lane == 0) { atomicAdd(E.cnt_expand + g, 1ull); atomicAdd(E.cnt_C + g, (unsigned long long)n); }
         } else { flags &= ~F_ACTIVE; dead = true; }
@@ -800,7 +809,7 @@ __global__ void __launch_bounds__(32 * MAX_WPB, 1) k_wave_fifo(Dev E, T *nn_in, 
         if (lane < 24) reinterpret_cast<uint32_t *>(S.board)[lane] = rbw;
         __syncwarp();
         store_leaf_at<T>(E.leafK + (size_t)g * K * 96, S, side0, nn_in, (size_t)g * K, lane);
-        pend = 2;
+        pend = 2; live = 1u;
     } else if (!dead) {
         if (iter == 0) {   // gather(): the first K playouts acquire the semaphore in iteration 1, the rest wait in FIFO order
             iter = 1; nq = 0;
@@ -828,7 +837,7 @@ __global__ void __launch_bounds__(32 * MAX_WPB, 1) k_wave_fifo(Dev E, T *nn_in, 
                     uint32_t base;
                     const int n = expand_reserve(E, S, alloc, base, errf, lane);
                     if (n > 0) {
-                        expand_write(ar, S, logits + idx * CZ_NLABEL, n, base, lane, true);
+                        expand_write(ar, S, logits + NN_ROW(idx) * CZ_NLABEL, n, base, lane, true);
                         if (lane == 0) {
                             expand_link(ar, path[plen - 1], n, base, 0u);               // also clears `claimed`: now_expanding.remove(node)
                             atomicAdd(E.cnt_expand + g, 1ull); atomicAdd(E.cnt_C + g, (unsigned long long)n);
@@ -838,7 +847,7 @@ __global__ void __launch_bounds__(32 * MAX_WPB, 1) k_wave_fifo(Dev E, T *nn_in, 
                         ar[pe.x + 3 * PE_CS(pe)] &= 0x7FFFFFFFu;                         // give the claim back
                     }
                     __syncwarp();
-                    warp_unwind_q(path, ar, plen, n > 0 ? -value[idx] : 0.0f, lane);     // return value[0] * -1, unwound through every frame
+                    warp_unwind_q(path, ar, plen, n > 0 ? -value[NN_ROW(idx)] : 0.0f, lane);   // return value[0] * -1, unwound through every frame
                     ended = true;
                 } else {
                     int side, rr, cnt, parentN;
@@ -935,6 +944,7 @@ __global__ void __launch_bounds__(32 * MAX_WPB, 1) k_wave_fifo(Dev E, T *nn_in, 
             if (iter & 1) {               // prediction_worker: last callback of every odd iteration
                 if (nq > 0) {
                     if (lane < nq) nxt[nnxt + lane] = (uint8_t)(queue[lane] | (EV_RESUME << 6));
+                    live = __reduce_or_sync(CZ_FULL, lane < nq ? (1u << (queue[lane] & 31)) : 0u);
                     nnxt += nq; nq = 0; need_nn = true;
                 }
             }
@@ -956,6 +966,8 @@ __global__ void __launch_bounds__(32 * MAX_WPB, 1) k_wave_fifo(Dev E, T *nn_in, 
     if (lane >= FI_CUR && lane < FI_CUR + 16) fw = cws;
     if (lane >= FI_QUEUE && lane < FI_QUEUE + 8) fw = qws;
     if (lane < FW) fp[lane] = fw;
+    if (E.compact && lane == 0) E.live_mask[g] = live;
+#undef NN_ROW
     HSET(H_FLAGS, F_SETPEND(flags, pend));
     HSET(H_DONE, done);
     HSET(H_ALLOC, alloc);
@@ -965,6 +977,56 @@ __global__ void __launch_bounds__(32 * MAX_WPB, 1) k_wave_fifo(Dev E, T *nn_in, 
     if (lane == H_MAXALLOC && alloc > h) h = alloc;
     if (lane == H_ERR) h |= errf;
     if (lane < HW) hp[lane] = h;
+}
+
+// ---- row compaction of the search_threads = K network batch ----------------------------------------------------------------
+// After k_wave_fifo, only the (game, slot) rows named in live_mask carry a leaf to evaluate (on average ~11 of 16 per searching game,
+// none for games whose search is complete).  k_compact_scan numbers them densely in (game, slot) order -- deterministic -- and
+// k_compact_rows gathers their input rows from the staging buffer; the network then runs on the first ceil(count / bucket) * bucket
+// rows only, and the next k_wave_fifo finds each evaluation through row_map.
+__global__ void __launch_bounds__(1024) k_compact_scan(Dev E) {
+    __shared__ int s_warp[32];
+    __shared__ int s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (int g0 = 0; g0 < E.B; g0 += 1024) {
+        const int g = g0 + tid;
+        uint32_t m = g < E.B ? E.live_mask[g] : 0u;
+        const int c = __popc(m);
+        int incl = c;
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(CZ_FULL, incl, o); if (lane >= o) incl += t; }
+        if (lane == 31) s_warp[w] = incl;
+        __syncthreads();
+        if (w == 0) {
+            int v = s_warp[lane];
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(CZ_FULL, v, o); if (lane >= o) v += t; }
+            s_warp[lane] = v;
+        }
+        __syncthreads();
+        int base = s_carry + (w ? s_warp[w - 1] : 0) + incl - c;
+        while (m) {
+            const int slot = __ffs(m) - 1;
+            m &= m - 1;
+            E.row_map[(size_t)g * E.K + slot] = base;
+            E.src_of[base] = g * E.K + slot;
+            base++;
+        }
+        __syncthreads();
+        if (tid == 0) s_carry += s_warp[31];
+        __syncthreads();
+    }
+    if (tid == 0) E.dense_count[0] = s_carry;
+}
+
+// one warp per dense row, 8-byte units
+__global__ void __launch_bounds__(256) k_compact_rows(Dev E, const uint2 *__restrict__ stage, uint2 *__restrict__ dense, int units) {
+    const int lane = threadIdx.x & 31, n = E.dense_count[0];
+    for (int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < n; r += gridDim.x * (blockDim.x >> 5)) {
+        const uint2 *src = stage + (size_t)E.src_of[r] * units;
+        uint2 *dst = dense + (size_t)r * units;
+        for (int i = lane; i < units; i += 32) dst[i] = src[i];
+    }
 }
 
 // ---- GameBoard.reload + MCTS_tree.reload -------------------------------------------------
@@ -1497,7 +1559,7 @@ static int create_engine(int n_games, int64_t arena_words, int device, int leave
     AL(d.st_w, B * CZ_MAXCHILD); AL(d.st_p, B * CZ_MAXCHILD); AL(d.st_q, B * CZ_MAXCHILD); AL(d.st_count, 8); AL(d.st_status, B * CZ_STATUS_BYTES);
     AL(e->d_mask, B); AL(e->d_boards, B * 90); AL(e->d_sides, B); AL(e->d_rr, B);
     if (multi) { AL(d.pendK, B * K); AL(d.plenK, B * K); AL(d.pathK, B * K * MAXD); AL(d.leafK, B * K * 96); }
-    if (fifo) { AL(d.fifo, B * FW); }
+    if (fifo) { AL(d.fifo, B * FW); AL(d.live_mask, B); AL(d.row_map, B * K); AL(d.src_of, B * K); AL(d.dense_count, 8); }
     if (!rc) { uint32_t *a = nullptr; rc = dalloc(e, &a, B * 2 * (size_t)arena_words, false); d.arena = a; }
 #undef AL
     if (rc) { const std::string keep = g_err; cz_engine_destroy(e); g_err = keep; return rc; }
@@ -1621,6 +1683,37 @@ int cz_engine_wave(cz_engine *e, void *stream, void *nn_in, int nn_dtype, const 
     }
     return launch_wave<true, true>(e, stream, nn_in, nn_dtype, logits, value);
 }
+// search_threads = K engines: one wave with row compaction.  nn_stage [B*K rows] receives every slot's input row as cz_engine_wave
+// would write it; nn_dense [B*K rows] receives the rows that need an evaluation, densely, in (game, slot) order; logits / value are
+// read through the row map of the PREVIOUS cz_engine_wave_compact call (so the caller evaluates nn_dense[0 .. n) into
+// logits[0 .. n) / value[0 .. n), n from cz_engine_live_rows, between two calls).  Do not mix with cz_engine_wave inside a search.
+int cz_engine_wave_compact(cz_engine *e, void *stream, void *nn_stage, void *nn_dense, int nn_dtype, const float *logits, const float *value) {
+    if (!e || !nn_stage || !nn_dense || !logits || !value) return fail(CZ_EINVAL, "cz_engine_wave_compact: null");
+    if (!e->d.fifo) return fail(CZ_EINVAL, "cz_engine_wave_compact: needs a search_threads engine (cz_engine_create_fifo)");
+    const int row_bytes = nn_dtype == CZ_BOARD ? 96 : nn_dtype == CZ_F32 ? 1260 * 4 : (nn_dtype == CZ_F16 || nn_dtype == CZ_BF16) ? 1260 * 2 : 0;
+    if (!row_bytes) return fail(CZ_EINVAL, "wave: nn_dtype");
+    cudaStream_t st = (cudaStream_t)stream;
+    e->d.compact = 1;
+    const int rc = cz_engine_wave(e, stream, nn_stage, nn_dtype, logits, value);
+    e->d.compact = 0;
+    if (rc) return rc;
+    k_compact_scan<<<1, 1024, 0, st>>>(e->d);
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->device);
+    k_compact_rows<<<2 * sms, 256, 0, st>>>(e->d, (const uint2 *)nn_stage, (uint2 *)nn_dense, row_bytes / 8);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(e->h_i32 + 8, e->d.dense_count, 4, cudaMemcpyDeviceToHost, st));
+    return CZ_OK;
+}
+// Rows of the dense batch the last cz_engine_wave_compact produced (synchronises the stream).
+int cz_engine_live_rows(cz_engine *e, void *stream, int32_t *out_rows) {
+    if (!e || !out_rows) return fail(CZ_EINVAL, "cz_engine_live_rows: null");
+    CUDA_TRY(cudaSetDevice(e->device));
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    *out_rows = e->h_i32[8];
+    return CZ_OK;
+}
+
 int cz_engine_select(cz_engine *e, void *stream, void *nn_in, int nn_dtype) {
     if (!e || !nn_in) return fail(CZ_EINVAL, "cz_engine_select: null");
     if (e->d.pendK) return fail(CZ_EINVAL, "cz_engine_select: leaf-parallel engines only support cz_engine_wave");

@@ -81,6 +81,18 @@ class Engine:
         check(lib().cz_engine_wave(self.h, _stream(), nn_in.data_ptr(), _DT[nn_in.dtype], logits.data_ptr(), value.data_ptr()),
               "cz_engine_wave")
 
+    def wave_compact(self, nn_stage, nn_dense, logits, value):
+        """search_threads = K engines: a wave whose leaves are gathered densely into nn_dense (cz_engine_wave_compact); evaluate
+        nn_dense[:live_rows()] into logits / value before the next call."""
+        self.launches += 3           # k_wave_fifo, k_compact_scan, k_compact_rows
+        check(lib().cz_engine_wave_compact(self.h, _stream(), nn_stage.data_ptr(), nn_dense.data_ptr(), _DT[nn_stage.dtype],
+                                           logits.data_ptr(), value.data_ptr()), "cz_engine_wave_compact")
+
+    def live_rows(self):
+        out = C.c_int32(0)
+        check(lib().cz_engine_live_rows(self.h, _stream(), C.byref(out)), "cz_engine_live_rows")
+        return out.value
+
     def select(self, nn_in):
         self.launches += 1
         check(lib().cz_engine_select(self.h, _stream(), nn_in.data_ptr(), _DT[nn_in.dtype]), "cz_engine_select")

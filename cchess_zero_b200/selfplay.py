@@ -238,13 +238,16 @@ class SelfPlay:
 
     def __init__(self, n_games, forward, playouts, seeds=None, exploration=True, temperature=1,
                  nn_dtype=torch.float32, arena_words=0, auto_reset=True, device=None, keep_records=True, plan=None,
-                 plan_factory=None, lanes=1, engine=None, hashing=False, search_threads=1):
+                 plan_factory=None, lanes=1, engine=None, hashing=False, search_threads=1, compact=None):
         """plan: an InferencePlan / NativePlan (defines the input buffer, writes logits/value in place).
         plan_factory(n) + lanes=2: two half-batches, each with its own engine and plan; the search pipelines them so
         that one half's tree kernel runs under the other half's network (see capture_graph)."""
         self.B = n_games
         # search_threads = K > 1: every game runs the reference's K-coroutine schedule (k_wave_fifo); the network batch has K rows per game
         self.K = max(1, int(search_threads))
+        # ... of which only the rows that carry a leaf are evaluated (row compaction, cz_engine_wave_compact): default for K > 1
+        self.compact = (self.K > 1 and lanes == 1 and engine is None) if compact is None else bool(compact)
+        assert not self.compact or (self.K > 1 and lanes == 1), "row compaction belongs to the search_threads = K engine"
         if lanes > 1:
             assert plan_factory is not None and n_games % lanes == 0
             per = n_games // lanes
@@ -277,6 +280,10 @@ class SelfPlay:
                 forward = lambda x: plan(x, self.logits, self.value)  # noqa: E731
             else:
                 self.nn_in = torch.zeros((rows, 9, 10, 14), dtype=nn_dtype, device=dev)
+            if self.compact:                                   # the engine writes every slot's row here; the leaves go densely to nn_in
+                self.nn_stage = torch.zeros_like(self.nn_in)
+                self._bucket_graphs, self._use_graphs, self._pool = {}, False, None
+                self.rows_evaluated = 0
             self.lanes = None
         self.plan = plan
         self.forward = forward
@@ -370,10 +377,69 @@ class SelfPlay:
         self.waves += waves
         return waves
 
+    # -- search_threads = K with row compaction ---------------------------------------------------
+    def _eval_rows(self, n):
+        """Evaluate the first n rows of the dense batch into logits[:n] / value[:n]."""
+        x = self.nn_in[:n]
+        if self.plan is not None:
+            self.plan(x, self.logits[:n], self.value[:n])
+            return
+        lo, v = self.forward(x)
+        self.logits[:n].copy_(lo.reshape(n, NLABEL))
+        self.value[:n].copy_(v.reshape(n))
+
+    def _eval_bucket(self, n_live):
+        """The network on ceil(n_live / B) * B rows (K bucket sizes; one lazily captured CUDA graph each, sharing a memory pool)."""
+        n = min(self.B * self.K, -(-n_live // self.B) * self.B)
+        self.rows_evaluated += n
+        if not self._use_graphs:
+            return self._eval_rows(n)
+        g = self._bucket_graphs.get(n)
+        if g is None:
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                for _ in range(2):
+                    self._eval_rows(n)
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            if self._pool is None:
+                self._pool = torch.cuda.graph_pool_handle()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=self._pool, stream=torch.cuda.Stream()):
+                self._eval_rows(n)
+            self._bucket_graphs[n] = g
+        g.replay()
+
+    def _search_compact(self):
+        e = self.engine
+        if self.plan is not None and hasattr(self.plan, "refresh_if_stale"):
+            self.plan.refresh_if_stale()
+        for p in np.unique(self.playouts[self.live]):
+            e.begin_search(int(p), (self.live & (self.playouts == p)).astype(np.uint8))
+        pmax = int(self.playouts[self.live].max()) if self.live.any() else 0
+        waves = 0
+        while True:
+            e.wave_compact(self.nn_stage, self.nn_in, self.logits, self.value)
+            n = e.live_rows()                               # stream sync: the host picks the bucket
+            waves += 1
+            if n > 0:
+                self._eval_bucket(n)
+            elif e.unfinished() == 0:                       # nothing to evaluate and every search complete
+                break
+            if waves > 4 * pmax + 64:
+                e.raise_on_error()
+                raise EngineError("search did not converge")
+        self.waves += waves
+        return waves
+
     def capture_graph(self, warmup=3):
         """Capture (wave kernel -> network) into one CUDA graph; the search loop then replays it."""
         if self.lanes is not None:
             return self._capture_pipeline(warmup)
+        if self.compact:                                    # the wave runs eagerly (the host reads the row count); the network is one
+            self._use_graphs = True                         # graph per bucket size, captured on first use
+            return
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
@@ -392,6 +458,8 @@ class SelfPlay:
         """MCTS_tree.main for every live game: `playouts[g]` playouts each."""
         if self.lanes is not None:
             return self._search_pipeline()
+        if self.compact:
+            return self._search_compact()
         e = self.engine
         if self.plan is not None and hasattr(self.plan, "refresh_if_stale"):
             self.plan.refresh_if_stale()       # weights trained / restored since the last search (the graph reads them in place)

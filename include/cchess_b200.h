@@ -127,6 +127,16 @@ int cz_engine_begin_search(cz_engine *e, void *stream, const uint8_t *mask, int 
  * nn_in: dev [n_games][9][10][14] of `nn_dtype`; logits: dev f32 [n_games][2086]; value: dev f32 [n_games].
  * A game's row of logits/value is only read if that game has a pending leaf.                              */
 int cz_engine_wave(cz_engine *e, void *stream, void *nn_in, int nn_dtype, const float *logits, const float *value);
+/* search_threads = K engines (cz_engine_create_fifo): one wave WITH ROW COMPACTION of the K-rows-per-game network batch.  On average
+ * ~11 of the 16 slots of a searching game carry a leaf (the rest spin on a node that is being expanded, main.py:354-355), and games
+ * whose search is complete carry none; evaluating only those rows is what the reference's prediction_worker does (main.py:442-464
+ * evaluates "whatever is queued").  nn_stage [B*K rows] is written like cz_engine_wave's nn_in; nn_dense [B*K rows] receives the rows
+ * that need an evaluation, densely, in (game, slot) order; logits / value are read through the row map of the PREVIOUS call: between
+ * two calls the caller evaluates nn_dense[0 .. n) into logits[0 .. n) / value[0 .. n), n = cz_engine_live_rows (stream sync).
+ * Results are identical to cz_engine_wave's whenever the evaluator is row-independent. */
+int cz_engine_wave_compact(cz_engine *e, void *stream, void *nn_stage, void *nn_dense, int nn_dtype, const float *logits, const float *value);
+int cz_engine_live_rows(cz_engine *e, void *stream, int32_t *out_rows);
+
 /* the two halves of a wave as separate launches */
 int cz_engine_select(cz_engine *e, void *stream, void *nn_in, int nn_dtype);
 int cz_engine_expand_backup(cz_engine *e, void *stream, const float *logits, const float *value);

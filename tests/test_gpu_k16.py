@@ -143,3 +143,44 @@ def test_batched_selfplay_with_search_threads_16_equals_the_specification_game_b
             t.update(c)
             side ^= 1
             rr = rr + 1 if cap == 0 else 0
+
+
+def test_row_compaction_of_the_k16_batch_changes_nothing_but_the_rows_evaluated():
+    """SelfPlay(search_threads=16) evaluates only the rows that carry a leaf (cz_engine_wave_compact: dense rows in (game, slot) order,
+    evaluations found through the row map).  Same games, move for move and visit for visit, as the full K-rows-per-game batch; games
+    that finish (auto-reset), uneven playout counts and the root-expansion waves included.  With the package's network the network
+    runs on bucketed batch sizes from lazily captured CUDA graphs: the searches complete and fewer rows are evaluated."""
+    from cchess_zero_b200.fakenet import FakeNet
+    from cchess_zero_b200.net import policy_value_network
+    from cchess_zero_b200.selfplay import SelfPlay
+    B, K = 24, 16
+    P = np.array([48 + 8 * (g % 3) for g in range(B)])
+    runs = {}
+    for compact in (False, True):
+        sp = SelfPlay(B, FakeNet("hash_signed"), P, seeds=[900 + i for i in range(B)], arena_words=1 << 18, auto_reset=True, search_threads=K, compact=compact)
+        assert sp.compact == compact
+        logs = []
+        for _ in range(14):
+            out = sp.step()
+            logs.append((sp.boards.copy(), sp.sides.copy(), [len(r) for _, r in out["finished"]]))
+        c = sp.engine.raise_on_error()
+        runs[compact] = (logs, c["n_playout"], c["n_expand"], [(s, list(r.states), [np.asarray(ix).tolist() for ix in r.pi_idx], [np.asarray(v).tolist() for v in r.pi_val], np.asarray(r.z).tolist()) for s, r in sp.finished], sp.waves)
+        if compact:
+            assert 0 < sp.rows_evaluated < sp.waves * B * K
+        sp.engine.close()
+    a, b = runs[False], runs[True]
+    assert a[1] == b[1] and a[2] == b[2]
+    for (ba, sa, fa), (bb, sb, fb) in zip(a[0], b[0]):
+        assert np.array_equal(ba, bb) and np.array_equal(sa, sb) and fa == fb
+    assert a[3] == b[3]
+    # the package's network, bucket graphs
+    pv = policy_value_network(2, seed=1)
+    sp = SelfPlay(32, None, 160, seeds=list(range(32)), arena_words=1 << 18, search_threads=K, plan_factory=lambda n: pv.native_plan(n))
+    sp.capture_graph()
+    for _ in range(3):
+        sp.step()
+    c = sp.engine.raise_on_error()
+    assert c["n_playout"] == 3 * 32 * 160
+    assert len(sp._bucket_graphs) >= 2 and sp.rows_evaluated < sp.waves * 32 * K
+    assert all(n % 32 == 0 for n in sp._bucket_graphs)
+    sp.engine.close()
