@@ -470,7 +470,7 @@ class SmallTowerPlan:
         import ctypes as C
         from ._lib import lib
         self._C, self._lib = C, lib()
-        self.cluster = int(cluster or os.environ.get("CCHESS_TOWER_CLUSTER", "4"))   # measured 86-88 us per evaluation for cluster sizes 2-8 at 1-16 positions (profiles/r02_tower_ncu_summary.md)
+        self.cluster = int(cluster or os.environ.get("CCHESS_TOWER_CLUSTER", "4"))   # measured 70-72 us per evaluation for cluster sizes 2-8 at 1-16 positions (profiles/r02_tower_ncu_summary.md)
         assert self.cluster in (1, 2, 4, 8)
         self._base = InferencePlan(net, "fp16", owner=owner)
         self.fused = True
