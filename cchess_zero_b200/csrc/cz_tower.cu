@@ -278,7 +278,8 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1) k_tower_small(const __grid_c
                 const int chunk = (int)rank * (NC / 8) + cg * (W / 8) + c8;          // 8-channel chunk of the full image
                 const uint32_t dst = smem_u32(bufX) + img_off(chunk, P0 + j);
 #pragma unroll
-                for (int q = 0; q < CL; q++) {
+                for (int qi = 0; qi < CL; qi++) {
+                    const uint32_t q = (rank + 1u + (uint32_t)qi) & (uint32_t)(CL - 1);   // every CTA starts with a different receiver (ingress spread), itself last
                     if (ASYNC_ST) st_async_v4(dst, smem_u32(&act_ready[0]), (uint32_t)q, o);
                     else if (CL == 1) *reinterpret_cast<uint4 *>(bufX + img_off(chunk, P0 + j)) = o;
                     else st_cluster_v4(dst, (uint32_t)q, o);
@@ -337,7 +338,8 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1) k_tower_small(const __grid_c
                     oh[k] = cell ? __floats2half2_rn(fmaxf(f[2 * k], 0.f), fmaxf(f[2 * k + 1], 0.f)) : __floats2half2_rn(0.f, 0.f);
                 if (ASYNC_ST) {
 #pragma unroll
-                    for (int q = 0; q < CL; q++) st_async_v4(smem_u32(dstbuf) + choff, smem_u32(&act_ready[(L + 1) & 1]), (uint32_t)q, o);
+                    for (int qi = 0; qi < CL; qi++)     // receivers in rotated order: at any moment the CL senders address CL different CTAs
+                        st_async_v4(smem_u32(dstbuf) + choff, smem_u32(&act_ready[(L + 1) & 1]), (rank + 1u + (uint32_t)qi) & (uint32_t)(CL - 1), o);
                 } else if (CL == 1) *reinterpret_cast<uint4 *>(dstbuf + choff) = o;
                 else {
 #pragma unroll
