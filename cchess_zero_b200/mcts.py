@@ -170,17 +170,21 @@ class MCTS_tree(object):
                     self._plan(self._nn_in, self._logits, self._value)
             torch.cuda.current_stream().wait_stream(s)
             torch.cuda.synchronize()
+            # one playout at a time: several (wave -> evaluation) pairs per graph, so that the gap between two graph launches is paid
+            # once per REPS playouts (a wave of a completed search does nothing: at most REPS - 1 idle evaluations per move)
+            self._reps = int(os.environ.get("CCHESS_WAVES_PER_GRAPH", "8")) if self.K == 1 else 1
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                self.engine.wave(self._nn_in, self._logits, self._value)
-                self._plan(self._nn_in, self._logits, self._value)
+                for _ in range(self._reps):
+                    self.engine.wave(self._nn_in, self._logits, self._value)
+                    self._plan(self._nn_in, self._logits, self._value)
             self._graph = g
         self.engine.begin_search(playouts)
         waves = 0
         while True:
             self._graph.replay()
-            self.engine.launches += 1
-            waves += 1
+            self.engine.launches += self._reps
+            waves += self._reps
             if waves > playouts // self.K and self.engine.unfinished() == 0:      # K leaves per wave: fewer waves needed
                 break
             if waves > 4 * playouts + 64:

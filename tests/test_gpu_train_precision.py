@@ -368,3 +368,32 @@ def test_tcgen05_policy_fc_and_mma_head_conv_match_the_simt_heads(B):
     print("B=%d: tc vs mma heads: logits %.3g value %.3g; vs fp64: tc %.3g, mma %.3g" % (B, d_l, d_v, e_tc, e_mma))
     assert d_l < 1e-4 and d_v < 1e-5          # same fp16 operands, fp32 accumulation: only the summation order differs
     assert e_tc < max(1e-3, 1.25 * e_mma)
+
+
+def test_single_tree_graph_with_several_waves_per_replay_is_the_same_search(monkeypatch):
+    """MCTS_tree over the package's network replays a CUDA graph that holds 8 (wave -> evaluation) pairs (mcts.py: _search_graph);
+    waves issued after the search is complete must change nothing: same visit counts and Q as one pair per replay, for playout counts
+    that are not multiples of 8, and the tree stays reusable (update_tree + a second search)."""
+    from cchess_zero_b200 import rules
+    from cchess_zero_b200.mcts import MCTS_tree
+    from cchess_zero_b200.net import policy_value_network
+    pv = policy_value_network(2, seed=7)
+    with torch.no_grad():
+        pv.net.p_fc.weight.mul_(30.0)
+    pv.weights_version += 1
+    out = {}
+    for reps in ("1", "8"):
+        monkeypatch.setenv("CCHESS_WAVES_PER_GRAPH", reps)
+        t = MCTS_tree(rules.START_STATE, pv.forward, 1)
+        assert t._plan is not None
+        res = []
+        for playouts in (51, 333):
+            t.main(t._state, "w" if t._side == 0 else "b", t._rr, playouts)
+            ch = [(a, n.N, float(n.Q)) for a, n in t.root.child.items()]
+            res.append(ch)
+            best = max(ch, key=lambda x: x[1])[0]
+            t.update_tree(best)
+        assert t._reps == int(reps)
+        out[reps] = res
+        t.engine.close()
+    assert out["1"] == out["8"]
