@@ -15,12 +15,14 @@ e2e   : expansions / time of the whole SelfPlay.step() loop through the public A
         sampling, tuple recording and (N > 1) the NCCL gather of the finished games' tuples.
 
 Further bounded legs, reported under `extra` of the same JSON line (each can be switched off with --legs):
-  precision : the same workload in tf32 and fp32 (a few plies each)         -> extra.by_precision      (N = 1)
+  precision : the same workload in tf32, tf32x3 (fp32-accurate on the tensor cores) and fp32 (a few plies each)
+                                                                             -> extra.by_precision      (N = 1)
   config3   : BASELINE configs[2] per-rank shape, 512 games x 1600 playouts -> extra.config3
   config4   : BASELINE configs[3], 19 residual blocks                       -> extra.config4           (N = 1)
   config5   : BASELINE configs[4], play-mode move latency p50/p95 through get_hint + select_move (ChessGame.py:153-181)
                                                                              -> extra.config5           (N = 1)
-  threads16 : batched self-play with the reference's search_threads=16 schedule inside every game     -> extra.search_threads_16 (N = 1)
+  threads16 : batched self-play with the reference's search_threads=16 schedule inside every game, 256 games and the full batch,
+              row compaction of the K-rows-per-game network batch  -> extra.search_threads_16, extra.search_threads_16_full_batch (N = 1)
   dedup     : board hashing: share of the evaluated leaves of one ply that repeat a position            -> extra.eval_dedup        (N = 1)
   soak      : every game slot plays on for >= 3 mean game lengths; games/hour from plies/s and the measured
               game-length distribution (no short-game selection bias)       -> extra.games_per_hour
