@@ -25,6 +25,37 @@ def test_abi_exports_every_declared_symbol():
     assert L.cz_version() >= 1
 
 
+def test_ctypes_binding_matches_the_header_prototypes():
+    """Every prototype of include/cchess_b200.h against the ctypes signature cchess_zero_b200/_lib.py binds it with: same number of
+    parameters, pointers bound as pointers, integers as 32- / 64-bit integers (an ABI drift between the header and the binding would
+    otherwise show up as a crash on the GPU box only)."""
+    import ctypes as C
+    from cchess_zero_b200 import _lib
+    L = _lib.lib()
+    hdr = open(os.path.join(ROOT, "include", "cchess_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", " ", hdr, flags=re.S)
+    protos = re.findall(r"\b(?:int|int64_t|const char \*|void)\s*\*?\s*(cz_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr)
+    assert len(protos) >= 45
+    checked = 0
+    for name, params in protos:
+        params = params.strip()
+        plist = [] if params in ("", "void") else [q.strip() for q in params.split(",")]
+        at = getattr(getattr(L, name), "argtypes", None)
+        if at is None:
+            assert not plist, "%s: %d parameters in the header, no argtypes bound" % (name, len(plist))
+            continue
+        assert len(at) == len(plist), "%s: header has %d parameters, binding %d" % (name, len(plist), len(at))
+        for q, t in zip(plist, at):
+            is_ptr = "*" in q or "[" in q
+            bound_ptr = t in (C.c_void_p, C.c_char_p) or hasattr(t, "contents") or getattr(t, "_type_", None) == "P" or "LP_" in getattr(t, "__name__", "")
+            assert is_ptr == bound_ptr, "%s: parameter '%s' bound as %s" % (name, q, t)
+            if not is_ptr:
+                want64 = bool(re.search(r"\b(int64_t|long long|size_t|uint64_t)\b", q))
+                assert (C.sizeof(t) == 8) == want64, "%s: parameter '%s' bound as %s" % (name, q, t)
+        checked += 1
+    assert checked >= 40
+
+
 def test_host_only_entry_points_match_oracle():
     from cchess_zero_b200 import rules
     from oracle import oracle as O
