@@ -36,7 +36,20 @@ t = MCTS_tree(rules.START_STATE, pv.forward, 1, leaf_parallel=4)
 t.main(rules.START_STATE, "w", 0, 32)
 boards = torch.zeros((3, 96), dtype=torch.uint8, device="cuda"); boards[:, :90] = torch.from_numpy(np.stack([b] * 3)).cuda()
 lo = torch.zeros((3, 2086), device="cuda"); vo = torch.zeros((3,), device="cuda")
-for cl in (1, 2, 4, 8):
+# cluster size 1 is left out: memcheck rejects shared::cluster stores (st.async / remote arrive addressed through mapa) in a launch whose
+# cluster has a single CTA ("Cluster needs to have at least 2 blocks"); the hardware executes them (tests/test_gpu_train_precision.py runs
+# that variant against fp64), and no default path uses it (SmallTowerPlan defaults to 4)
+for cl in (2, 4, 8):
     pv.small_plan(4, cl)(boards, lo, vo)
 torch.cuda.synchronize()
 print("round-2 kernels ok", sp3.plies, sp4.plies, float(lo.abs().max()))
+# later in round 2: row compaction of the K-thread batch (sp3 above runs through cz_engine_wave_compact by default), the tf32x3 plan
+# (k_epilogue_split + library convolutions), the single-tree graph with several waves per replay
+assert sp3.compact and sp3.rows_evaluated > 0
+pv3 = policy_value_network(res_block_nums=1, precision="tf32x3")
+x = torch.zeros((3, 9, 10, 14), device="cuda"); x[:, :, :, 2] = 1.0
+l3, v3 = pv3.plan()(x)
+t2 = MCTS_tree(rules.START_STATE, pv.forward, 1)
+t2.main(rules.START_STATE, "w", 0, 20)
+torch.cuda.synchronize()
+print("later round-2 kernels ok", sp3.rows_evaluated, float(l3.abs().max()), t2._reps)
